@@ -1,0 +1,323 @@
+"""ctypes binding of ``libgraphlily_b200.so`` (the C ABI in ``include/graphlily_b200.h``).
+
+This is the only route from Python to the CUDA kernels and it has no fallback: if the
+shared library is missing the import fails, and without a CUDA device every compute call
+raises :class:`GlbError` -- nothing here ever computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgraphlily_b200.so")
+
+OP_MUL_ADD, OP_LOGICAL_AND_OR, OP_ADD_MIN = 0, 1, 2
+MASK_NONE, MASK_WRITE_TO_ZERO, MASK_WRITE_TO_ONE = 0, 1, 2
+
+IDX_VAL = np.dtype([("index", np.uint32), ("val", np.float32)])
+
+_vp = C.c_void_p
+_u32p = C.POINTER(C.c_uint32)
+_f32p = C.POINTER(C.c_float)
+
+
+class GlbError(RuntimeError):
+    pass
+
+
+class Epilogue(C.Structure):
+    """glb_spmv_epilogue_t"""
+    _fields_ = [("add_enable", C.c_int), ("add_val", C.c_float), ("assign_inout", _vp),
+                ("assign_val", C.c_float), ("assign_mask_type", C.c_int)]
+
+
+class HostLayout(C.Structure):
+    """glb_host_layout_t"""
+    _fields_ = [("chunk", C.c_uint32), ("nnz", C.c_uint64), ("n_chunks", C.c_uint32), ("n_nz_rows", C.c_uint32),
+                ("n_empty", C.c_uint32), ("n_fixups", C.c_uint32), ("cols", _u32p), ("nz_rows", _u32p),
+                ("empty_rows", _u32p), ("chunk_first", _u32p), ("fixups", _u32p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/graphlily_b200.h declares.
+SIGNATURES = {
+    "glb_version": (C.c_int, []),
+    "glb_last_error": (C.c_char_p, []),
+    "glb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "glb_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "glb_ctx_destroy": (C.c_int, [_vp]),
+    "glb_ctx_sync": (C.c_int, [_vp]),
+    "glb_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "glb_buffer_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "glb_buffer_free": (C.c_int, [_vp, _vp]),
+    "glb_buffer_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "glb_buffer_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "glb_buffer_h2d_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "glb_buffer_d2h_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "glb_buffer_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "glb_buffer_fill_f32": (C.c_int, [_vp, _vp, C.c_float, C.c_size_t]),
+    "glb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "glb_host_free": (C.c_int, [_vp]),
+    "glb_csr_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "glb_csr_destroy": (C.c_int, [_vp]),
+    "glb_csr_info": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "glb_csr_format_host": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(HostLayout)]),
+    "glb_host_layout_free": (C.c_int, [C.POINTER(HostLayout)]),
+    "glb_csc_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "glb_csc_destroy": (C.c_int, [_vp]),
+    "glb_spmv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "glb_spmv_fused": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.POINTER(Epilogue)]),
+    "glb_spmv_host": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "glb_spmspv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "glb_sparse_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    "glb_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float]),
+    "glb_ewise_add": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float]),
+    "glb_assign_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float, C.c_int]),
+    "glb_assign_sparse": (C.c_int, [_vp, _vp, _vp, C.c_float]),
+    "glb_assign_sparse_relax": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "glb_nccl_available": (C.c_int, []),
+    "glb_nccl_unique_id": (C.c_int, [_vp]),
+    "glb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "glb_comm_destroy": (C.c_int, [_vp]),
+    "glb_allgather_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C graphlily_b200/csrc` "
+            "(or __graft_entry__.build()); graphlily_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise GlbError(f"glb error {rc}: {lib.glb_last_error().decode(errors='replace')}")
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib.glb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def _ptr(a):
+    """Raw address of a numpy array / DeviceBuffer / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, DeviceBuffer):
+        return a.ptr
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class Context:
+    """One CUDA device + one stream (glb_ctx_t)."""
+
+    def __init__(self, device=0, stream=None):
+        h = _vp()
+        check(lib.glb_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def sync(self):
+        check(lib.glb_ctx_sync(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib.glb_ctx_destroy(self.handle)
+            self.handle = None
+
+    # ---- buffers ------------------------------------------------------------------
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, array):
+        array = np.ascontiguousarray(array)
+        buf = DeviceBuffer(self, array.nbytes)
+        buf.write(array)
+        return buf
+
+    def zeros_f32(self, n, value=0.0):
+        buf = DeviceBuffer(self, 4 * n)
+        check(lib.glb_buffer_fill_f32(self.handle, buf.ptr, float(value), n))
+        return buf
+
+
+class DeviceBuffer:
+    """Owning handle over device memory (the role of cl::Buffer)."""
+
+    def __init__(self, ctx, nbytes):
+        p = _vp()
+        check(lib.glb_buffer_alloc(ctx.handle, int(nbytes), C.byref(p)))
+        self.ctx, self.ptr, self.nbytes = ctx, p.value, int(nbytes)
+
+    def write(self, array):
+        array = np.ascontiguousarray(array)
+        assert array.nbytes <= self.nbytes
+        check(lib.glb_buffer_h2d(self.ctx.handle, self.ptr, array.ctypes.data, array.nbytes))
+
+    def read(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib.glb_buffer_d2h(self.ctx.handle, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def read_sparse(self):
+        """Device sparse vector -> (indices, values), head slot stripped."""
+        head = self.read(IDX_VAL, 1)
+        n = int(head["index"][0])
+        body = self.read(IDX_VAL, n + 1)[1:]
+        return body["index"].copy(), body["val"].copy()
+
+    def free(self):
+        if self.ptr and self.ctx.handle:
+            lib.glb_buffer_free(self.ctx.handle, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sparse_to_numpy(idx, val, capacity=None):
+    """(indices, values) -> idx_val_t array with the {nnz, 0} head slot."""
+    idx = np.asarray(idx, np.uint32)
+    n = len(idx)
+    out = np.zeros(max(n + 1, capacity or 0), dtype=IDX_VAL)
+    out["index"][0] = n
+    out["index"][1:n + 1] = idx
+    out["val"][1:n + 1] = np.asarray(val, np.float32)
+    return out
+
+
+class CsrMatrix:
+    """Device-resident CSR row shard in warp-segment layout (glb_csr_t)."""
+
+    def __init__(self, ctx, m, row_begin=0, row_end=None):
+        row_end = int(m.num_rows) if row_end is None else row_end
+        self._keep = (np.ascontiguousarray(m.indptr, np.uint32), np.ascontiguousarray(m.indices, np.uint32),
+                      np.ascontiguousarray(m.data, np.float32))
+        h = _vp()
+        check(lib.glb_csr_create(ctx.handle, int(m.num_rows), int(m.num_cols), self._keep[0].ctypes.data,
+                                 self._keep[1].ctypes.data, self._keep[2].ctypes.data, row_begin, row_end, C.byref(h)))
+        self._keep = None  # the layout lives on the device now
+        self.ctx, self.handle = ctx, h
+        self.num_rows, self.num_cols = int(m.num_rows), int(m.num_cols)
+        self.row_begin, self.row_end = row_begin, row_end
+
+    def info(self):
+        a = (C.c_uint64 * 8)()
+        check(lib.glb_csr_info(self.handle, a))
+        keys = ("rows", "cols", "nnz", "chunks", "fixups", "empty_rows", "device_bytes", "chunk_nnz")
+        return dict(zip(keys, (int(v) for v in a)))
+
+    def spmv(self, op, zero, mask_type, x, mask, y, epilogue=None):
+        if epilogue is None:
+            check(lib.glb_spmv(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x), _ptr(mask), _ptr(y)))
+        else:
+            check(lib.glb_spmv_fused(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x), _ptr(mask), _ptr(y),
+                                     C.byref(epilogue)))
+
+    def spmv_host(self, op, zero, mask_type, x_host, mask_host, y_host):
+        check(lib.glb_spmv_host(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x_host), _ptr(mask_host),
+                                _ptr(y_host)))
+
+    def close(self):
+        if self.handle:
+            lib.glb_csr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CscMatrix:
+    """Device-resident CSC (glb_csc_t); ``m.indptr`` runs over columns, ``m.indices`` are row ids."""
+
+    def __init__(self, ctx, m):
+        ip, ix, d = (np.ascontiguousarray(m.indptr, np.uint32), np.ascontiguousarray(m.indices, np.uint32),
+                     np.ascontiguousarray(m.data, np.float32))
+        h = _vp()
+        check(lib.glb_csc_create(ctx.handle, int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data,
+                                 d.ctypes.data, C.byref(h)))
+        self.ctx, self.handle = ctx, h
+        self.num_rows, self.num_cols = int(m.num_rows), int(m.num_cols)
+
+    def spmspv(self, op, zero, mask_type, x, mask, y):
+        check(lib.glb_spmspv(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x), _ptr(mask), _ptr(y)))
+
+    def close(self):
+        if self.handle:
+            lib.glb_csc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- apply operators ----------------------------------------------------------------
+def ewise_add(ctx, src, dst, length, val):
+    check(lib.glb_ewise_add(ctx.handle, _ptr(src), _ptr(dst), length, val))
+
+
+def assign_dense(ctx, mask, inout, length, val, mask_type):
+    check(lib.glb_assign_dense(ctx.handle, _ptr(mask), _ptr(inout), length, val, mask_type))
+
+
+def assign_sparse(ctx, sparse_list, inout, val):
+    check(lib.glb_assign_sparse(ctx.handle, _ptr(sparse_list), _ptr(inout), val))
+
+
+def assign_sparse_relax(ctx, sparse_list, inout, new_frontier):
+    check(lib.glb_assign_sparse_relax(ctx.handle, _ptr(sparse_list), _ptr(inout), _ptr(new_frontier)))
+
+
+def sparse_count(ctx, sparse_list):
+    n = C.c_uint32(0)
+    check(lib.glb_sparse_count(ctx.handle, _ptr(sparse_list), C.byref(n)))
+    return n.value
+
+
+def sparse_to_dense(ctx, sparse_list, dense, length, zero):
+    check(lib.glb_sparse_to_dense(ctx.handle, _ptr(sparse_list), _ptr(dense), length, zero))
+
+
+def d2d(ctx, dst, src, nbytes):
+    check(lib.glb_buffer_d2d(ctx.handle, _ptr(dst), _ptr(src), nbytes))
+
+
+def format_host(m, row_begin=0, row_end=None):
+    """Host-only view of the warp-segment layout (no GPU needed); returns a dict of numpy arrays."""
+    row_end = int(m.num_rows) if row_end is None else row_end
+    ip, ix = np.ascontiguousarray(m.indptr, np.uint32), np.ascontiguousarray(m.indices, np.uint32)
+    L = HostLayout()
+    check(lib.glb_csr_format_host(int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data, row_begin, row_end,
+                                  C.byref(L)))
+
+    def arr(p, n):
+        return np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+
+    out = dict(chunk=L.chunk, nnz=int(L.nnz), n_chunks=L.n_chunks, cols=arr(L.cols, int(L.nnz)),
+               nz_rows=arr(L.nz_rows, L.n_nz_rows), empty_rows=arr(L.empty_rows, L.n_empty),
+               chunk_first=arr(L.chunk_first, L.n_chunks), fixups=arr(L.fixups, 3 * L.n_fixups).reshape(-1, 3))
+    lib.glb_host_layout_free(C.byref(L))
+    return out

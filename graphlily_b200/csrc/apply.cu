@@ -1,0 +1,134 @@
+// Element-wise "apply" operators (overlay modes 3-6).
+//
+//   mode 3  kernel_add_scalar_vector_dense          /root/reference/graphlily/hw/kernel_add_scalar_vector_dense_impl.h:6-27
+//   mode 4  kernel_assign_vector_dense              kernel_assign_vector_dense_impl.h:8-47
+//   mode 5  kernel_assign_vector_sparse_no_new_frontier   kernel_assign_vector_sparse_no_new_frontier_impl.h:4-55
+//   mode 6  kernel_assign_vector_sparse_new_frontier      kernel_assign_vector_sparse_new_frontier_impl.h:4-78
+// with the semantics of the modules' compute_reference_results
+// (add_scalar_vector_dense_module.h:195-204, assign_vector_dense_module.h:223-246,
+//  assign_vector_sparse_module.h:306-335).
+//
+// All four are pure HBM streams / scatters: 128-bit vector accesses where the layout allows,
+// grids sized as multiples of the SM count, list lengths read on the device from slot 0.
+#include "glb_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+__global__ void __launch_bounds__(kThreads) ewise_add_kernel(const float *in, float *out, uint32_t len, float val) {
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    uint32_t done = 0;
+    if (aligned) {
+        const uint32_t n4 = len >> 2;
+        const float4 *in4 = reinterpret_cast<const float4 *>(in);
+        float4 *out4 = reinterpret_cast<float4 *>(out);
+        for (uint32_t i = tid; i < n4; i += stride) {
+            float4 v = in4[i];
+            v.x = __fadd_rn(v.x, val);
+            v.y = __fadd_rn(v.y, val);
+            v.z = __fadd_rn(v.z, val);
+            v.w = __fadd_rn(v.w, val);
+            out4[i] = v;
+        }
+        done = n4 << 2;
+    }
+    for (uint32_t i = done + tid; i < len; i += stride) out[i] = __fadd_rn(in[i], val);
+}
+
+__global__ void __launch_bounds__(kThreads) assign_dense_kernel(const float *mask, float *inout, uint32_t len, float val,
+                                                              int write_to_one) {
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+        const bool nz = mask[i] != 0.0f;
+        if (nz == (write_to_one != 0)) inout[i] = val;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) assign_sparse_kernel(const glb_idx_val_t *__restrict__ list, float *inout,
+                                                               float val) {
+    const uint32_t n = list[0].index;
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) inout[list[i + 1].index] = val;
+}
+
+__global__ void __launch_bounds__(kThreads) assign_sparse_relax_kernel(const glb_idx_val_t *__restrict__ list,
+                                                                     float *inout, glb_idx_val_t *new_frontier) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = list[0].index;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_round; i += stride) {
+        bool emit = false;
+        glb_idx_val_t e = {0u, 0.0f};
+        if (i < n) {
+            e = list[i + 1];
+            if (inout[e.index] > e.val) {
+                inout[e.index] = e.val;
+                emit = true;
+            }
+        }
+        const unsigned b = __ballot_sync(kFull, emit);
+        if (b) {
+            uint32_t base = 0;
+            const int leader = __ffs(int(b)) - 1;
+            if (int(lane) == leader) base = atomicAdd(&new_frontier[0].index, uint32_t(__popc(b)));
+            base = __shfl_sync(kFull, base, leader);
+            if (emit) new_frontier[1 + base + __popc(b & ((1u << lane) - 1u))] = e;
+        }
+    }
+}
+
+inline unsigned grid_for(glb_ctx_t ctx, uint64_t work_items, int per_sm) {
+    uint64_t blocks = (work_items + kThreads - 1) / kThreads;
+    const uint64_t cap = uint64_t(ctx->num_sms) * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return unsigned(blocks);
+}
+
+}  // namespace
+
+extern "C" {
+
+int glb_ewise_add(glb_ctx_t ctx, const float *in, float *out, uint32_t len, float val) {
+    GLB_REQUIRE(ctx && (len == 0 || (in && out)), "NULL argument");
+    if (len == 0) return GLB_OK;
+    ewise_add_kernel<<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(in, out, len, val);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_assign_dense(glb_ctx_t ctx, const float *mask, float *inout, uint32_t len, float val, int mask_type) {
+    GLB_REQUIRE(ctx && (len == 0 || (mask && inout)), "NULL argument");
+    // the reference prints "Please set the mask type" and exits (assign_vector_dense_module.h:88-95)
+    GLB_REQUIRE(mask_type == GLB_MASK_WRITE_TO_ZERO || mask_type == GLB_MASK_WRITE_TO_ONE,
+                "dense assign needs kMaskWriteToZero or kMaskWriteToOne");
+    if (len == 0) return GLB_OK;
+    assign_dense_kernel<<<grid_for(ctx, len, 8), kThreads, 0, ctx->stream>>>(mask, inout, len, val,
+                                                                             mask_type == GLB_MASK_WRITE_TO_ONE);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_assign_sparse(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, float val) {
+    GLB_REQUIRE(ctx && list && inout, "NULL argument");
+    assign_sparse_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, inout, val);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_assign_sparse_relax(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, glb_idx_val_t *new_frontier) {
+    GLB_REQUIRE(ctx && list && inout && new_frontier, "NULL argument");
+    GLB_REQUIRE(static_cast<const void *>(list) != static_cast<const void *>(new_frontier),
+                "new_frontier must not alias list");
+    GLB_CUDA(cudaMemsetAsync(new_frontier, 0, sizeof(glb_idx_val_t), ctx->stream));  // head = {0, 0.0f}
+    assign_sparse_relax_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, inout, new_frontier);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+}  // extern "C"

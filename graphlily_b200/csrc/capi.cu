@@ -1,0 +1,254 @@
+// Runtime part of the C ABI: error text, context (device + stream), buffers, NCCL binding.
+// Replaces what BaseModule::set_up_runtime / cl::Buffer / enqueueMigrateMemObjects do in the
+// reference (/root/reference/graphlily/module/base_module.h:82-133).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "glb_internal.h"
+
+static thread_local char g_err[1024] = "";
+
+void glb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int glb_version(void) { return GLB_VERSION; }
+
+const char *glb_last_error(void) { return g_err; }
+
+int glb_device_count(int *count) {
+    GLB_REQUIRE(count, "count is NULL");
+    *count = 0;
+    GLB_CUDA(cudaGetDeviceCount(count));
+    return GLB_OK;
+}
+
+int glb_ctx_create(int device, void *cuda_stream, glb_ctx_t *out) {
+    GLB_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    GLB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        glb_set_error("glb_ctx_create: device %d not available (%d CUDA devices); there is no CPU fallback", device, n);
+        return GLB_ECUDA;
+    }
+    GLB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GLB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        glb_set_error("glb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                      prop.minor);
+        return GLB_ECUDA;
+    }
+    glb_ctx_t ctx = new glb_ctx_s();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        ctx->owns_stream = false;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            glb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete ctx;
+            return GLB_ECUDA;
+        }
+        ctx->owns_stream = true;
+    }
+    *out = ctx;
+    return GLB_OK;
+}
+
+int glb_ctx_destroy(glb_ctx_t ctx) {
+    if (!ctx) return GLB_OK;
+    cudaSetDevice(ctx->device);
+    glb_comm_destroy(ctx);
+    if (ctx->hx) cudaFreeHost(ctx->hx);
+    if (ctx->hmask) cudaFreeHost(ctx->hmask);
+    if (ctx->hy) cudaFreeHost(ctx->hy);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GLB_OK;
+}
+
+int glb_ctx_sync(glb_ctx_t ctx) {
+    GLB_REQUIRE(ctx, "ctx is NULL");
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GLB_OK;
+}
+
+int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream) {
+    GLB_REQUIRE(ctx && cuda_stream, "NULL argument");
+    *cuda_stream = ctx->stream;
+    return GLB_OK;
+}
+
+// ------------------------------------------------------------------------ buffers
+int glb_buffer_alloc(glb_ctx_t ctx, size_t bytes, void **dptr) {
+    GLB_REQUIRE(ctx && dptr, "NULL argument");
+    *dptr = nullptr;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 4);
+    if (e != cudaSuccess) {
+        glb_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA;
+    }
+    return GLB_OK;
+}
+
+int glb_buffer_free(glb_ctx_t ctx, void *dptr) {
+    GLB_REQUIRE(ctx, "ctx is NULL");
+    if (!dptr) return GLB_OK;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    GLB_CUDA(cudaFree(dptr));
+    return GLB_OK;
+}
+
+int glb_buffer_h2d_async(glb_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    GLB_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), "NULL argument");
+    if (bytes) GLB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return GLB_OK;
+}
+
+int glb_buffer_d2h_async(glb_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    GLB_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "NULL argument");
+    if (bytes) GLB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return GLB_OK;
+}
+
+int glb_buffer_h2d(glb_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    int rc = glb_buffer_h2d_async(ctx, dst_dev, src_host, bytes);
+    if (rc) return rc;
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GLB_OK;
+}
+
+int glb_buffer_d2h(glb_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    int rc = glb_buffer_d2h_async(ctx, dst_host, src_dev, bytes);
+    if (rc) return rc;
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GLB_OK;
+}
+
+int glb_buffer_d2d(glb_ctx_t ctx, void *dst_dev, const void *src_dev, size_t bytes) {
+    GLB_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_dev)), "NULL argument");
+    if (bytes) GLB_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return GLB_OK;
+}
+
+int glb_host_alloc(size_t bytes, void **hptr) {
+    GLB_REQUIRE(hptr, "hptr is NULL");
+    *hptr = nullptr;
+    cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 4);
+    if (e != cudaSuccess) {
+        glb_set_error("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+        return GLB_ENOMEM;
+    }
+    return GLB_OK;
+}
+
+int glb_host_free(void *hptr) {
+    if (hptr) GLB_CUDA(cudaFreeHost(hptr));
+    return GLB_OK;
+}
+
+// ------------------------------------------------------------------------ NCCL (dlopen)
+// libnccl is resolved at run time so the library loads on hosts without NCCL; in a torch
+// process dlopen("libnccl.so.2") returns the copy torch already mapped.
+typedef struct { char internal[GLB_NCCL_UNIQUE_ID_BYTES]; } nccl_uid_t;
+typedef int (*pfn_get_uid)(nccl_uid_t *);
+typedef int (*pfn_init_rank)(void **, int, nccl_uid_t, int);
+typedef int (*pfn_destroy)(void *);
+typedef int (*pfn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef const char *(*pfn_errstr)(int);
+
+static struct {
+    bool tried = false;
+    void *handle = nullptr;
+    pfn_get_uid get_uid = nullptr;
+    pfn_init_rank init_rank = nullptr;
+    pfn_destroy destroy = nullptr;
+    pfn_allgather allgather = nullptr;
+    pfn_errstr errstr = nullptr;
+} g_nccl;
+
+static bool nccl_load() {
+    if (g_nccl.tried) return g_nccl.handle != nullptr;
+    g_nccl.tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return false;
+    g_nccl.get_uid = (pfn_get_uid)dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.init_rank = (pfn_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.destroy = (pfn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.allgather = (pfn_allgather)dlsym(g_nccl.handle, "ncclAllGather");
+    g_nccl.errstr = (pfn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allgather) {
+        dlclose(g_nccl.handle);
+        g_nccl.handle = nullptr;
+        return false;
+    }
+    return true;
+}
+
+#define GLB_NCCL(call)                                                                              \
+    do {                                                                                            \
+        int r__ = (call);                                                                           \
+        if (r__ != 0) {                                                                             \
+            glb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                              \
+                          g_nccl.errstr ? g_nccl.errstr(r__) : "nccl error");                      \
+            return GLB_ENCCL;                                                                       \
+        }                                                                                           \
+    } while (0)
+
+int glb_nccl_available(void) { return nccl_load() ? 1 : 0; }
+
+int glb_nccl_unique_id(void *id128) {
+    GLB_REQUIRE(id128, "id is NULL");
+    if (!nccl_load()) { glb_set_error("libnccl.so.2 not found"); return GLB_ENCCL; }
+    nccl_uid_t id;
+    GLB_NCCL(g_nccl.get_uid(&id));
+    memcpy(id128, &id, sizeof(id));
+    return GLB_OK;
+}
+
+int glb_comm_init(glb_ctx_t ctx, const void *id128, int rank, int nranks) {
+    GLB_REQUIRE(ctx && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+    if (!nccl_load()) { glb_set_error("libnccl.so.2 not found"); return GLB_ENCCL; }
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    nccl_uid_t id;
+    memcpy(&id, id128, sizeof(id));
+    GLB_NCCL(g_nccl.init_rank(&ctx->nccl_comm, nranks, id, rank));
+    ctx->nccl_rank = rank;
+    ctx->nccl_nranks = nranks;
+    return GLB_OK;
+}
+
+int glb_comm_destroy(glb_ctx_t ctx) {
+    if (ctx && ctx->nccl_comm && g_nccl.destroy) {
+        g_nccl.destroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return GLB_OK;
+}
+
+int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank) {
+    GLB_REQUIRE(ctx && buf, "NULL argument");
+    if (!ctx->nccl_comm) { glb_set_error("glb_allgather_f32: glb_comm_init was not called"); return GLB_ENCCL; }
+    const float *send = buf + size_t(ctx->nccl_rank) * count_per_rank;
+    GLB_NCCL(g_nccl.allgather(send, buf, count_per_rank, /*ncclFloat32*/ 7, ctx->nccl_comm, ctx->stream));
+    return GLB_OK;
+}
+
+}  // extern "C"

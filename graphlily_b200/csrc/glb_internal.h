@@ -1,0 +1,107 @@
+// Internal declarations shared by the translation units of libgraphlily_b200.so.
+#ifndef GLB_INTERNAL_H_
+#define GLB_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "graphlily_b200.h"
+
+// ---------------------------------------------------------------- error plumbing
+void glb_set_error(const char *fmt, ...);
+
+#define GLB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            glb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return GLB_ECUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+#define GLB_REQUIRE(cond, msg)                                      \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            glb_set_error("%s: %s", __func__, msg);                 \
+            return GLB_EINVAL;                                      \
+        }                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+struct glb_ctx_s {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    void *nccl_comm = nullptr;  // ncclComm_t when built with GLB_WITH_NCCL
+    int nccl_rank = 0, nccl_nranks = 1;
+    // scratch for glb_spmv_host (grown on demand)
+    float *hx = nullptr, *hmask = nullptr, *hy = nullptr;
+    size_t hx_n = 0, hmask_n = 0, hy_n = 0;
+};
+
+// ---------------------------------------------------------------- warp-segment CSR (SpMV)
+//
+// The nnz stream of the row shard is cut into fixed chunks of GLB_CHUNK non-zeros; one warp
+// owns one chunk and reads it with 128-bit loads, four consecutive non-zeros per lane.
+//   cols[p]  bit31 = "p is the first non-zero of its row" (cleared at chunk position 0,
+//            where chunk_first carries the information instead); bits 0..30 = column
+//   vals[p]  fp32 value
+//   nz_rows[k]      row id of the k-th non-empty row of the shard
+//   chunk_first[c]  ordinal k of the row holding the chunk's first non-zero,
+//                   bit31 = that row starts exactly at the chunk start
+// Rows that cross a chunk boundary (or end exactly on one) are finished by the fix-up
+// kernel from per-chunk carries: see spmv.cu.
+#define GLB_CHUNK 1024u
+#define GLB_FLAG 0x80000000u
+
+struct glb_fixup_t {
+    uint32_t row;    // global row id
+    uint32_t c_begin;  // first chunk contributing its tail carry
+    uint32_t c_end;    // last chunk; bit31 = it contributes its HEAD carry (row ends mid-chunk)
+};
+
+struct glb_csr_s {
+    glb_ctx_t ctx = nullptr;
+    uint32_t num_rows = 0, num_cols = 0;  // global dims
+    uint32_t row_begin = 0, row_end = 0;  // shard
+    uint64_t nnz = 0;                     // in shard
+    uint32_t n_chunks = 0;
+    uint32_t n_nz_rows = 0;
+    uint32_t n_fix_short = 0, n_fix_long = 0, n_empty = 0;
+    // device arrays
+    uint32_t *cols = nullptr;
+    float *vals = nullptr;
+    uint32_t *nz_rows = nullptr;
+    uint32_t *chunk_first = nullptr;
+    glb_fixup_t *fix_short = nullptr;  // span <= 32 chunks: one thread each
+    glb_fixup_t *fix_long = nullptr;   // longer spans: one warp each
+    uint32_t *empty_rows = nullptr;
+    float *head_carry = nullptr, *tail_carry = nullptr;  // per chunk
+    // scratch vectors for glb_spmv_host
+    float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
+    size_t device_bytes = 0;
+};
+
+// ---------------------------------------------------------------- CSC (SpMSpV)
+struct glb_csc_s {
+    glb_ctx_t ctx = nullptr;
+    uint32_t num_rows = 0, num_cols = 0;
+    uint64_t nnz = 0;
+    uint32_t *indptr = nullptr;   // num_cols + 1
+    uint32_t *indices = nullptr;  // row ids
+    float *vals = nullptr;
+    float *acc = nullptr;         // dense accumulator, num_rows, kept at `acc_zero` between runs
+    float acc_zero = 0.0f;
+    bool acc_valid = false;
+    uint32_t *counter = nullptr;  // output cursor
+};
+
+// launchers (defined in the .cu files)
+int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
+                    float *y, const glb_spmv_epilogue_t *ep);
+
+#endif  // GLB_INTERNAL_H_

@@ -1,0 +1,281 @@
+// SpMSpV: y = A[:, idx(x)] (+).(x) x, CSC, sparse in -> sparse out (overlay mode 2).
+//
+// Replaces kernel_spmspv (/root/reference/graphlily/hw/kernel_spmspv_impl.h:448-562) and
+// formatCSC (graphlily/io/data_formatter.h:608-721).  Semantics: SpMSpVModule::
+// compute_reference_results (graphlily/module/spmspv_module.h:446-520) followed by the device
+// write-back rule (kernel_spmspv_impl.h:200-229,263-281,551-555): only entries != zero that
+// pass the mask are listed, the head slot is {count, zero}, order is unspecified.
+//
+// Three stream-ordered launches, none sized by device data (persistent grids read the
+// frontier length from x[0].index):
+//   1. scatter (light columns): one warp per active column, lanes stride down the column and
+//      combine a (x) v into a dense accumulator that rests at the (+)-identity:
+//      atomicAdd / benign store of 1.0f / ordered-int atomicMin;
+//      columns longer than kHeavy are queued instead;
+//   2. scatter (heavy columns): the whole grid strides down each queued column;
+//   3. compact: scan the accumulator, fold `zero`, apply the mask, reset touched entries,
+//      emit with warp-aggregated atomics on y[0].index.
+#include <math.h>
+#include <string.h>
+
+#include "glb_internal.h"
+#include "semiring.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kHeavy = 2048;          // column length that goes to the grid-wide pass
+constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
+
+template <int OP>
+__device__ __forceinline__ float spmspv_mul(float a, float v) {
+    if (OP == GLB_OP_ADD_MIN) {
+        if (a > kFloatInf || v > kFloatInf) return kFloatInf;
+        const float s = __fadd_rn(a, v);
+        return s > kFloatInf ? kFloatInf : s;
+    }
+    return Semi<OP>::mul(a, v);
+}
+
+template <int OP>
+__device__ __forceinline__ void combine(float *acc, float p) {
+    if (OP == GLB_OP_MUL_ADD) {
+        atomicAdd(acc, p);
+    } else if (OP == GLB_OP_LOGICAL_AND_OR) {
+        if (p != 0.0f) *acc = 1.0f;  // idempotent: racing writers store the same word
+    } else {
+        // float min through integer atomics: non-negative floats order like ints,
+        // negative floats order inversely as unsigned
+        if (p >= 0.0f) atomicMin(reinterpret_cast<int *>(acc), __float_as_int(p));
+        else atomicMax(reinterpret_cast<unsigned *>(acc), __float_as_uint(p));
+    }
+}
+
+struct SpmspvParams {
+    const uint32_t *__restrict__ indptr;
+    const uint32_t *__restrict__ indices;
+    const float *__restrict__ vals;
+    const glb_idx_val_t *__restrict__ x;
+    const float *__restrict__ mask;
+    glb_idx_val_t *y;
+    float *acc;
+    uint32_t *heavy;  // [0] = count, then entries (k indices into x)
+    uint32_t num_rows;
+    float zero;
+    int mask_type;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) spmspv_scatter_light(const SpmspvParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
+    const uint32_t nnz_x = P.x[0].index;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.y[0].index = 0;
+        P.y[0].val = P.zero;
+    }
+    for (uint32_t k = warp; k < nnz_x; k += n_warps) {
+        const glb_idx_val_t e = P.x[k + 1];
+        const uint32_t s = P.indptr[e.index], t = P.indptr[e.index + 1];
+        if (t - s > kHeavy) {
+            if (lane == 0) P.heavy[1 + atomicAdd(P.heavy, 1u)] = k;
+            continue;
+        }
+        for (uint32_t i = s + lane; i < t; i += 32)
+            combine<OP>(P.acc + P.indices[i], spmspv_mul<OP>(P.vals[i], e.val));
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) spmspv_scatter_heavy(const SpmspvParams P) {
+    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t n_threads = gridDim.x * kThreads;
+    const uint32_t n_heavy = P.heavy[0];
+    for (uint32_t h = 0; h < n_heavy; ++h) {
+        const glb_idx_val_t e = P.x[P.heavy[1 + h] + 1];
+        const uint32_t s = P.indptr[e.index], t = P.indptr[e.index + 1];
+        for (uint32_t i = s + tid; i < t; i += n_threads)
+            combine<OP>(P.acc + P.indices[i], spmspv_mul<OP>(P.vals[i], e.val));
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) spmspv_compact(const SpmspvParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_threads = gridDim.x * kThreads;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.heavy[0] = 0;  // ready for the next run
+    const uint32_t n_round = (P.num_rows + 31u) & ~31u;       // keep warps converged for the ballots
+    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_round; r += n_threads) {
+        bool emit = false;
+        float val = 0.0f;
+        if (r < P.num_rows) {
+            const float a = P.acc[r];
+            if (a != Semi<OP>::ident()) {
+                P.acc[r] = Semi<OP>::ident();
+                val = Semi<OP>::with_zero(P.zero, a);
+                bool off = false;
+                if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (P.mask[r] == P.zero);
+                else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (P.mask[r] != P.zero);
+                emit = !off && (val != P.zero);
+            }
+        }
+        const unsigned b = __ballot_sync(kFull, emit);
+        if (b) {
+            uint32_t base = 0;
+            const int leader = __ffs(int(b)) - 1;
+            if (int(lane) == leader) base = atomicAdd(&P.y[0].index, uint32_t(__popc(b)));
+            base = __shfl_sync(kFull, base, leader);
+            if (emit) {
+                glb_idx_val_t o;
+                o.index = r;
+                o.val = val;
+                P.y[1 + base + __popc(b & ((1u << lane) - 1u))] = o;
+            }
+        }
+    }
+}
+
+__global__ void fill_f32_kernel(float *dst, float val, size_t n) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = val;
+}
+
+__global__ void sparse_scatter_kernel(const glb_idx_val_t *__restrict__ list, float *dense, uint32_t len) {
+    const uint32_t n = list[0].index;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const glb_idx_val_t e = list[i + 1];
+        if (e.index < len) dense[e.index] = e.val;
+    }
+}
+
+template <int OP>
+int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
+    const float ident = (OP == GLB_OP_ADD_MIN) ? HUGE_VALF : 0.0f;
+    const int grid = ctx->num_sms * 8;
+    if (!m->acc_valid || memcmp(&m->acc_zero, &ident, sizeof(float)) != 0) {
+        fill_f32_kernel<<<grid, kThreads, 0, ctx->stream>>>(m->acc, ident, m->num_rows);
+        m->acc_zero = ident;
+        m->acc_valid = true;
+    }
+    spmspv_scatter_light<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+    spmspv_scatter_heavy<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+    spmspv_compact<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int glb_buffer_fill_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n) {
+    GLB_REQUIRE(ctx && (n == 0 || dst_dev), "NULL argument");
+    if (n == 0) return GLB_OK;
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    const size_t cap = size_t(ctx->num_sms) * 16;
+    if (blocks > cap) blocks = cap;
+    fill_f32_kernel<<<unsigned(blocks), kThreads, 0, ctx->stream>>>(dst_dev, val, n);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
+                   const float *data, glb_csc_t *out) {
+    GLB_REQUIRE(ctx && out && indptr, "NULL argument");
+    *out = nullptr;
+    const uint64_t nnz = indptr[num_cols];
+    GLB_REQUIRE(nnz == 0 || (indices && data), "NULL indices/data");
+    for (uint32_t c = 0; c < num_cols; ++c) GLB_REQUIRE(indptr[c + 1] >= indptr[c], "indptr not monotone");
+    for (uint64_t i = 0; i < nnz; ++i) GLB_REQUIRE(indices[i] < num_rows, "row index out of range");
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    glb_csc_t m = new glb_csc_s();
+    m->ctx = ctx;
+    m->num_rows = num_rows;
+    m->num_cols = num_cols;
+    m->nnz = nnz;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 4);
+    };
+    alloc(reinterpret_cast<void **>(&m->indptr), sizeof(uint32_t) * (size_t(num_cols) + 1));
+    alloc(reinterpret_cast<void **>(&m->indices), sizeof(uint32_t) * nnz);
+    alloc(reinterpret_cast<void **>(&m->vals), sizeof(float) * nnz);
+    alloc(reinterpret_cast<void **>(&m->acc), sizeof(float) * num_rows);
+    alloc(reinterpret_cast<void **>(&m->counter), sizeof(uint32_t) * (size_t(num_cols) + 2));  // heavy-column queue
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->indptr, indptr, sizeof(uint32_t) * (size_t(num_cols) + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(m->indices, indices, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(m->vals, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->counter, 0, sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        glb_set_error("glb_csc_create: %s", cudaGetErrorString(e));
+        glb_csc_destroy(m);
+        return e == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA;
+    }
+    *out = m;
+    return GLB_OK;
+}
+
+int glb_csc_destroy(glb_csc_t m) {
+    if (!m) return GLB_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->counter);
+    delete m;
+    return GLB_OK;
+}
+
+int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
+               glb_idx_val_t *y) {
+    GLB_REQUIRE(ctx && m && x && y, "NULL argument");
+    GLB_REQUIRE(m->ctx == ctx, "matrix belongs to another context");
+    GLB_REQUIRE(mask_type >= GLB_MASK_NONE && mask_type <= GLB_MASK_WRITE_TO_ONE, "invalid mask type");
+    GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask, "mask is NULL but mask_type != kNoMask");
+    GLB_REQUIRE(static_cast<const void *>(x) != static_cast<const void *>(y), "y must not alias x");
+    SpmspvParams P;
+    P.indptr = m->indptr;
+    P.indices = m->indices;
+    P.vals = m->vals;
+    P.x = x;
+    P.mask = mask;
+    P.y = y;
+    P.acc = m->acc;
+    P.heavy = m->counter;
+    P.num_rows = m->num_rows;
+    P.zero = zero;
+    P.mask_type = mask_type;
+    switch (op) {
+        case GLB_OP_MUL_ADD: return run_spmspv<GLB_OP_MUL_ADD>(ctx, m, P);
+        case GLB_OP_LOGICAL_AND_OR: return run_spmspv<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);
+        case GLB_OP_ADD_MIN: return run_spmspv<GLB_OP_ADD_MIN>(ctx, m, P);
+    }
+    glb_set_error("glb_spmspv: invalid semiring op %d", op);
+    return GLB_EINVAL;
+}
+
+int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count) {
+    GLB_REQUIRE(ctx && list && count, "NULL argument");
+    glb_idx_val_t head;
+    GLB_CUDA(cudaMemcpyAsync(&head, list, sizeof(head), cudaMemcpyDeviceToHost, ctx->stream));
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = head.index;
+    return GLB_OK;
+}
+
+int glb_sparse_to_dense(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, uint32_t len, float zero) {
+    GLB_REQUIRE(ctx && list && (len == 0 || dense), "NULL argument");
+    if (len == 0) return GLB_OK;
+    int rc = glb_buffer_fill_f32(ctx, dense, zero, len);
+    if (rc) return rc;
+    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, len);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+/* graphlily_b200.h -- the C ABI of libgraphlily_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for GraphLily's hot path.  In the reference the seam is
+ * "module class -> OpenCL kernel `overlay`":
+ *     extern "C" void overlay(..., mode)        /root/reference/graphlily/hw/overlay.cpp:14-81,308-414
+ * whose `mode` selects one of six device functions, driven by kernel_.setArg(i, ...) +
+ * enqueueTask + finish (spmv_module.h:104-128,471-475).  Here every overlay mode is one
+ * entry point taking plain device pointers and sizes (no torch / C++ types):
+ *
+ *     overlay mode 1  kernel_spmv                          -> glb_spmv / glb_spmv_fused
+ *     overlay mode 2  kernel_spmspv                        -> glb_spmspv
+ *     overlay mode 3  kernel_add_scalar_vector_dense       -> glb_ewise_add
+ *     overlay mode 4  kernel_assign_vector_dense           -> glb_assign_dense
+ *     overlay mode 5  kernel_assign_vector_sparse_no_new_frontier -> glb_assign_sparse
+ *     overlay mode 6  kernel_assign_vector_sparse_new_frontier    -> glb_assign_sparse_relax
+ *
+ * plus what the OpenCL runtime did around it: context / queue (BaseModule::set_up_runtime,
+ * base_module.h:106-133), buffers (cl::Buffer + enqueueMigrateMemObjects), device-to-device
+ * copies (base_module.h:82-85) and the matrix upload (send_matrix_host_to_device,
+ * spmv_module.h:374-420, spmspv_module.h:290-370) -- which is where the device layout is built
+ * (CPSR / formatCSC in the reference, the warp-segment layout here).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a GLB_E* code otherwise; glb_last_error() gives the
+ *    text (thread-local).  There is NO CPU fallback: without a CUDA device every compute
+ *    entry point fails with GLB_ECUDA.
+ *  - all kernels are enqueued on the context's stream and return without synchronising;
+ *    glb_ctx_sync, glb_buffer_d2h / glb_buffer_h2d and glb_sparse_count synchronise, which are
+ *    the points where the reference calls command_queue_.finish() and the host reads data.
+ *  - values are fp32 (`val_t = float`, global.h:64 variant), indices uint32 (idx_t, global.h:65).
+ *  - sparse vectors follow global.h:69-70,153-164: element 0 is {index = nnz, val = unused},
+ *    elements 1..nnz are {index, val}; order unspecified.
+ */
+#ifndef GRAPHLILY_B200_H_
+#define GRAPHLILY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLB_VERSION 100
+
+/* status codes */
+#define GLB_OK 0
+#define GLB_EINVAL 1  /* bad argument (the reference prints and exit()s, e.g. assign_vector_dense_module.h:88-95) */
+#define GLB_ECUDA 2   /* CUDA runtime / launch failure, or no device */
+#define GLB_ENOMEM 3  /* host or device allocation failure */
+#define GLB_ENCCL 4   /* NCCL failure or library built without NCCL */
+
+/* OperationType, global.h:83-87 */
+#define GLB_OP_MUL_ADD 0
+#define GLB_OP_LOGICAL_AND_OR 1
+#define GLB_OP_ADD_MIN 2
+
+/* MaskType, global.h:103-107 */
+#define GLB_MASK_NONE 0
+#define GLB_MASK_WRITE_TO_ZERO 1 /* write where mask is zero     */
+#define GLB_MASK_WRITE_TO_ONE 2  /* write where mask is non-zero */
+
+/* idx_val_t with val_t = float, global.h:69 */
+typedef struct glb_idx_val {
+    uint32_t index;
+    float val;
+} glb_idx_val_t;
+
+typedef struct glb_ctx_s *glb_ctx_t; /* one CUDA device + one stream (cl::Context + cl::CommandQueue)  */
+typedef struct glb_csr_s *glb_csr_t; /* device-resident CSR row shard in warp-segment layout (SpMV)    */
+typedef struct glb_csc_s *glb_csc_t; /* device-resident CSC (SpMSpV)                                    */
+
+/* ------------------------------------------------------------------ runtime ------- */
+int glb_version(void);
+const char *glb_last_error(void);
+int glb_device_count(int *count);
+
+/* BaseModule::set_up_runtime / ModuleCollection::set_up_runtime (base_module.h:106-133,
+ * module_collection.h:69-114).  `cuda_stream` may be an existing cudaStream_t (e.g. the
+ * caller's torch stream) or NULL to create a private non-blocking stream. */
+int glb_ctx_create(int device, void *cuda_stream, glb_ctx_t *out);
+int glb_ctx_destroy(glb_ctx_t ctx);
+int glb_ctx_sync(glb_ctx_t ctx); /* command_queue_.finish() */
+int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream);
+
+/* ------------------------------------------------------------------ buffers -------
+ * cl::Buffer + enqueueMigrateMemObjects (e.g. spmv_module.h:424-459, 229-253). */
+int glb_buffer_alloc(glb_ctx_t ctx, size_t bytes, void **dptr);
+int glb_buffer_free(glb_ctx_t ctx, void *dptr);
+int glb_buffer_h2d(glb_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes); /* blocking */
+int glb_buffer_d2h(glb_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes); /* blocking */
+int glb_buffer_h2d_async(glb_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes);
+int glb_buffer_d2h_async(glb_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* BaseModule::copy_buffer_device_to_device, base_module.h:82-85 (stream-ordered). */
+int glb_buffer_d2d(glb_ctx_t ctx, void *dst_dev, const void *src_dev, size_t bytes);
+int glb_buffer_fill_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n);
+/* page-locked host memory: the role of xcl2's aligned_allocator (xcl2.hpp:61-76). */
+int glb_host_alloc(size_t bytes, void **hptr);
+int glb_host_free(void *hptr);
+
+/* ------------------------------------------------------------------ matrices ------
+ * SpMVModule::load_and_format_matrix + send_matrix_host_to_device (spmv_module.h:282-420):
+ * takes a host CSR (CSRMatrix<float>, data_loader.h:19-31), builds the warp-segment layout
+ * for rows [row_begin, row_end) and uploads it.  Row ids stay GLOBAL: glb_spmv writes
+ * y[r] for r in the shard only, so ranks of a row-sharded run fill disjoint slices of one
+ * full-length vector.  Pass row_begin = 0, row_end = num_rows for the whole matrix. */
+int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr,
+                   const uint32_t *indices, const float *data, uint32_t row_begin, uint32_t row_end,
+                   glb_csr_t *out);
+int glb_csr_destroy(glb_csr_t m);
+/* info[0]=rows in shard, [1]=num_cols, [2]=nnz in shard, [3]=chunks, [4]=fix-up rows,
+ * [5]=empty rows in shard, [6]=device bytes of the layout, [7]=nnz per chunk. */
+int glb_csr_info(glb_csr_t m, uint64_t info[8]);
+
+/* Host-only view of the warp-segment layout glb_csr_create builds (no CUDA call), so the
+ * formatter -- the counterpart of csr2cpsr, data_formatter.h:457-534 -- can be checked on a
+ * machine without a GPU.  cols[p] bit31 = "p starts a row" (never set at a chunk start);
+ * chunk_first[c] = ordinal into nz_rows of the row holding the chunk's first non-zero,
+ * bit31 = that row starts exactly there; fixups = n_fixups x {row, c_begin, c_end}: the row's
+ * value is tail_carry[c_begin .. c_last] (+) head_carry[c_end] when bit31 of c_end is set
+ * (c_last = c_end - 1), else tail_carry[c_begin .. c_end]. */
+typedef struct glb_host_layout {
+    uint32_t chunk;      /* non-zeros per chunk (one warp each) */
+    uint64_t nnz;
+    uint32_t n_chunks, n_nz_rows, n_empty, n_fixups;
+    uint32_t *cols;        /* nnz */
+    uint32_t *nz_rows;     /* n_nz_rows */
+    uint32_t *empty_rows;  /* n_empty */
+    uint32_t *chunk_first; /* n_chunks */
+    uint32_t *fixups;      /* 3 * n_fixups */
+} glb_host_layout_t;
+int glb_csr_format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
+                        uint32_t row_begin, uint32_t row_end, glb_host_layout_t *out);
+int glb_host_layout_free(glb_host_layout_t *layout);
+
+/* SpMSpVModule::load_and_format_matrix + send_matrix_host_to_device (spmspv_module.h:264-370):
+ * host CSC (CSCMatrix<float>, data_loader.h:92-104; indptr has num_cols+1 entries). */
+int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr,
+                   const uint32_t *indices, const float *data, glb_csc_t *out);
+int glb_csc_destroy(glb_csc_t m);
+
+/* ------------------------------------------------------------------ overlay mode 1
+ * kernel_spmv (kernel_spmv_impl.h:392-819) == SpMVModule::compute_reference_results
+ * (spmv_module.h:478-532): y[r] = zero (+) SUM_{i in row r} data[i] (x) x[indices[i]], then
+ *   WRITE_TO_ZERO: mask[r] != 0 -> y[r] = 0     WRITE_TO_ONE: mask[r] == 0 -> y[r] = 0
+ * (literal 0, not `zero`).  x has num_cols entries, mask / y num_rows entries; y must not
+ * alias x.  `mask` may be NULL iff mask_type == GLB_MASK_NONE. */
+int glb_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x,
+             const float *mask, float *y);
+
+/* The per-iteration launch sequences of the apps, folded into the SpMV write-back:
+ *   v = masked SpMV row result (as glb_spmv)
+ *   if (add_enable)     v = v + add_val                 eWiseAddModule::run   (pagerank.h:86-88)
+ *   y[r] = v
+ *   if (assign_inout)   DenseAssign with mask := v       AssignVectorDenseModule::run (bfs.h:117-124)
+ *        WRITE_TO_ONE : v != 0 -> assign_inout[r] = assign_val
+ *        WRITE_TO_ZERO: v == 0 -> assign_inout[r] = assign_val
+ * `assign_inout` may alias `mask` (BFS: both are the distance vector). */
+typedef struct glb_spmv_epilogue {
+    int add_enable;
+    float add_val;
+    float *assign_inout;
+    float assign_val;
+    int assign_mask_type;
+} glb_spmv_epilogue_t;
+int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x,
+                   const float *mask, float *y, const glb_spmv_epilogue_t *ep);
+
+/* End-to-end convenience with HOST vectors (what SpMVModule does around run():
+ * send_vector_host_to_device, [send_mask_host_to_device], run, send_results_device_to_host).
+ * x_host / mask_host / y_host should be page-locked (glb_host_alloc) for full PCIe speed. */
+int glb_spmv_host(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x_host,
+                  const float *mask_host, float *y_host);
+
+/* ------------------------------------------------------------------ overlay mode 2
+ * kernel_spmspv (kernel_spmspv_impl.h:448-562) == SpMSpVModule::compute_reference_results
+ * (spmspv_module.h:446-520) followed by the device's sparse write-back: for each active
+ * (c, v) of x and each (r, a) of CSC column c: acc[r] = acc[r] (+) a (x) v  (ADD_MIN clamps at
+ * 999999999); rows failing the mask (compared against `zero`) are dropped; `y` receives
+ * {count, zero} then every {r, acc[r]} with acc[r] != zero (kernel_spmspv_impl.h:200-229,
+ * 263-281,551-555).  x: device list, capacity >= nnz+1; y: capacity num_rows+1. */
+int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x,
+               const float *mask, glb_idx_val_t *y);
+/* SpMSpVModule::get_results_nnz (spmspv_module.h:239-242): blocking read of list[0].index. */
+int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count);
+/* convert_sparse_vec_to_dense_vec (global.h:153-164) done on the device (the reference does it
+ * on the host at the push->pull switch, bfs.h:195-201). dense[0..len) = zero, then scatter. */
+int glb_sparse_to_dense(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, uint32_t len, float zero);
+
+/* ------------------------------------------------------------------ overlay mode 3
+ * kernel_add_scalar_vector_dense_impl.h:6-27: out[i] = in[i] + val. in may equal out. */
+int glb_ewise_add(glb_ctx_t ctx, const float *in, float *out, uint32_t len, float val);
+
+/* ------------------------------------------------------------------ overlay mode 4
+ * kernel_assign_vector_dense_impl.h:8-47: WRITE_TO_ZERO: mask[i]==0 -> inout[i]=val;
+ * WRITE_TO_ONE: mask[i]!=0 -> inout[i]=val; GLB_MASK_NONE -> GLB_EINVAL. */
+int glb_assign_dense(glb_ctx_t ctx, const float *mask, float *inout, uint32_t len, float val, int mask_type);
+
+/* ------------------------------------------------------------------ overlay mode 5
+ * kernel_assign_vector_sparse_no_new_frontier_impl.h:4-55:
+ * inout[list[i+1].index] = val for i < list[0].index. */
+int glb_assign_sparse(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, float val);
+
+/* ------------------------------------------------------------------ overlay mode 6
+ * kernel_assign_vector_sparse_new_frontier_impl.h:4-78: for each list entry {i, v}:
+ * if inout[i] > v { inout[i] = v; emit {i, v} }; new_frontier[0] = {count, 0}.
+ * `capacity` = number of glb_idx_val_t slots in new_frontier (>= list count + 1).
+ * Indices in `list` are unique (it is an SpMSpV result), so the emitted SET equals the
+ * reference's; order is unspecified. new_frontier must not alias list. */
+int glb_assign_sparse_relax(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout,
+                            glb_idx_val_t *new_frontier);
+
+/* ------------------------------------------------------------------ multi-GPU ------
+ * Row-range sharding: one process per GPU, each holding glb_csr_create(..., row_begin, row_end)
+ * and a full-length x.  After glb_spmv every rank owns y[row_begin:row_end); one allgather
+ * makes the next x.  The host may do that exchange with its own communicator on the same
+ * stream (torch.distributed in bench.py), or use the built-in NCCL binding below. */
+#define GLB_NCCL_UNIQUE_ID_BYTES 128
+int glb_nccl_available(void);
+int glb_nccl_unique_id(void *id128);
+int glb_comm_init(glb_ctx_t ctx, const void *id128, int rank, int nranks);
+int glb_comm_destroy(glb_ctx_t ctx);
+/* In-place allgather: every rank contributed buf[rank*count_per_rank .. +count_per_rank). */
+int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHLILY_B200_H_ */

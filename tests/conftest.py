@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The parity oracle (test infrastructure): C restatement + compiled reference if present."""
+    import oracle as o
+    return o
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One glb context on cuda:0 for the -m gpu tests; the CUDA path must be the one that runs."""
+    from graphlily_b200 import capi
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests need a B200 (there is no CPU fallback)")
+    c = capi.Context(0)
+    yield c
+    c.close()
