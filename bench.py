@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- SpMV GTEPS on the BASELINE.json configs[1] workload (bench_spmv).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: synthetic power-law CSR, 4 194 304 x 4 194 304, 134 217 728 nnz
+(32 / row), fp32 plus-times, A[:] = 1/N, x in {0, 1} -- the shape of the reference's
+benchmark/bench_spmv.cpp:37-113 (GTEPS = nnz / seconds / 1e9, :106-112).
+
+One step = one SpMV over the whole matrix.  With N > 1 the CSR is row-range sharded (equal
+row counts), every rank computes its slice of y straight into the gather buffer and one NCCL
+allgather per step makes it the next x (strong scaling: total work fixed).
+
+Reported on one JSON line by rank 0:
+  value        device-timed GTEPS, inputs resident in HBM (matrix 1.07 GB >> 126 MB L2, so every
+               step streams it from HBM; the 16 MB x is meant to live in L2)
+  e2e          GTEPS through glb_spmv_host with pinned HOST x / y: H2D x, kernels, D2H y per step
+  roofline     spmv_ws_kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline the reference's own compute_reference_results (oracle/_ref) on one host thread,
+               on a bounded row sample of the same matrix (N = 1 only)
+`--impl reference` runs only that CPU path (the reference has no threading: 1 thread).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS = 4_194_304
+NNZ = 134_217_728
+SEED = 42
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons through NVML while the measurement runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            log("NVML unavailable:", e)
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.thread:
+            self.thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_matrix(device):
+    from graphlily_b200 import datasets
+    t0 = time.time()
+    m = datasets.powerlaw_csr(ROWS, ROWS, NNZ, seed=SEED, device=device)
+    log(f"generated power-law CSR {m.num_rows} x {m.num_cols}, nnz {m.nnz} on {device} in {time.time() - t0:.1f}s")
+    return m
+
+
+def row_sample(m, rows):
+    from graphlily_b200.io import CSRMatrix
+    end = int(m.indptr[rows])
+    return CSRMatrix(rows, m.num_cols, m.data[:end], m.indices[:end], m.indptr[:rows + 1].copy())
+
+
+def cpu_reference_backend():
+    import oracle  # the ONLY use of oracle/ here: as the timed CPU baseline / reference arm
+    if oracle.ref is not None:
+        return oracle.ref, "reference"
+    return oracle.port, "port"
+
+
+def workload_config(n_gpus):
+    return {"workload": "bench_spmv: synthetic power-law CSR 4194304 x 4194304, 134217728 nnz (32/row), "
+                        "fp32 plus-times SpMV, A=1/N, x in {0,1}",
+            "generator": f"graphlily_b200.datasets.powerlaw_csr(seed={SEED}): Pareto(2.1) row degrees 1..2^20, "
+                         "Zipf(0.9) column popularity, random column labels",
+            "rows": ROWS, "nnz": NNZ, "semiring": "plus-times",
+            "sharding": f"row-range x{n_gpus}, one NCCL allgather of y per step" if n_gpus > 1 else "none",
+            "l2": "matrix streams (1.07 GB) exceed the 126 MB L2 every step; no flush needed"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU SpMV on a bounded row sample, 1 thread."""
+    if rank != 0:
+        return
+    import torch
+    backend, kind = cpu_reference_backend()
+    m = make_matrix("cuda" if torch.cuda.is_available() else "cpu")
+    x = np.random.default_rng(SEED).integers(0, 2, m.num_cols).astype(np.float32)
+    probe = row_sample(m, 65536)
+    t_probe, _ = backend.spmv_timed(probe, 0, 0.0, x, reps=2)
+    per_nnz = t_probe / max(probe.nnz, 1)
+    budget = 60.0 / max(args.steps + args.warmup, 1)               # seconds per step
+    rows = 65536
+    while rows < 1_048_576 and per_nnz * int(m.indptr[rows * 2]) * 2.0 < budget:
+        rows *= 2
+    s = row_sample(m, rows)
+    for _ in range(args.warmup):
+        backend.spmv_timed(s, 0, 0.0, x, reps=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        backend.spmv_timed(s, 0, 0.0, x, reps=1)
+    dt = (time.perf_counter() - t0) / args.steps
+    gteps = s.nnz / dt / 1e9
+    sample = f"rows [0, {rows}) of the same matrix ({s.nnz} nnz) per step, 1 thread (the reference has no threading)"
+    line = {"impl": "reference", "metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": gteps, "unit": "GTEPS", "cores": 1, "kind": kind, "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": gteps, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS, help=argparse.SUPPRESS)   # debugging only
+    args = ap.parse_args()
+    if args.rows != ROWS:   # scaled-down debugging run, never a bench line of record
+        globals().update(ROWS=args.rows, NNZ=args.rows * 32)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from graphlily_b200 import capi  # fails loudly if the CUDA library is missing
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: graphlily_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = make_matrix(dev)
+    n = m.num_rows
+    assert n % (32 * world) == 0
+    slot = n // world
+    rb, re = rank * slot, (rank + 1) * slot
+
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+    t0 = time.time()
+    A = capi.CsrMatrix(ctx, m, rb, re)
+    info = A.info()
+    log(f"rank {rank}: rows [{rb},{re}) nnz {info['nnz']} chunks {info['chunks']} fixups {info['fixups']} "
+        f"layout {info['device_bytes'] / 1e9:.3f} GB, format+upload {time.time() - t0:.1f}s")
+
+    if world > 1:
+        uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+
+    x_host = np.random.default_rng(SEED).integers(0, 2, n).astype(np.float32)
+    xa = torch.from_numpy(x_host).to(dev)
+    xb = torch.zeros_like(xa)
+
+    def step(src, dst):
+        A.spmv(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.data_ptr(), None, dst.data_ptr())
+        if world > 1:
+            ctx.allgather_f32(dst.data_ptr(), slot)
+
+    def run_steps(k, src, dst):
+        for _ in range(k):
+            step(src, dst)
+            src, dst = dst, src
+        return src, dst
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident timing ------------------------------------------------------------
+    src, dst = run_steps(args.warmup, xa, xb)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    src, dst = run_steps(args.steps, src, dst)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    gteps = m.nnz / (ms_step * 1e-3) / 1e9
+
+    # ---- dominant kernel alone (events inside the C ABI, same stream) --------------------------
+    xa.copy_(torch.from_numpy(x_host))
+    ctx.kernel_timing(True)
+    run_steps(args.steps, xa, xb)
+    ms_main, ms_fix, launches = ctx.kernel_timing_read()
+    ctx.kernel_timing(False)
+    ms_kernel = ms_main / max(launches, 1)
+    rows_s = re - rb
+    alg_bytes = 8 * info["nnz"] + 4 * (rows_s + 1) + 4 * m.num_cols + 4 * rows_s
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:  # noqa: BLE001
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": "spmv_ws_kernel<plus-times>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fix / max(launches, 1)}
+
+    # ---- end to end through the host-buffer entry point ----------------------------------------
+    xh = torch.from_numpy(x_host).pin_memory()
+    yh = torch.zeros(n, dtype=torch.float32).pin_memory()
+    e2e_steps = max(10, min(args.steps, 50))
+    for _ in range(3):
+        A.spmv_host(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xh.data_ptr(), None, yh.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        A.spmv_host(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xh.data_ptr(), None, yh.data_ptr())
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / e2e_steps
+    e2e = {"value": m.nnz / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 4 * n,
+           "d2h_bytes_per_step": 4 * rows_s, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "glb_spmv_host (pinned host x -> device, SpMV, y slice -> pinned host)"}
+    clocks = sampler.stop()
+    checksum = float(yh[rb:re].double().sum())
+
+    # ---- CPU baseline beside it (rank 0, N = 1) ----------------------------------------------
+    cpu = None
+    if world == 1:
+        backend, kind = cpu_reference_backend()
+        rows_c = 1_048_576 if args.rows == ROWS else min(args.rows, 65536)
+        s = row_sample(m, rows_c)
+        sec, y_ref = backend.spmv_timed(s, 0, 0.0, x_host, reps=3)
+        got = yh[:rows_c].numpy()
+        err = np.abs(got - y_ref) / np.maximum(np.abs(y_ref), 1e-30)
+        ok = bool(((err <= 1e-5) | (np.abs(got - y_ref) < 1e-12)).all())
+        cpu = {"value": s.nnz / sec / 1e9, "unit": "GTEPS", "cores": 1, "kind": kind,
+               "sample": f"rows [0, {rows_c}) of the same matrix ({s.nnz} nnz), best of 3, 1 thread "
+                         "(the reference has no threading)",
+               "host_cpus": os.cpu_count(), "gpu_result_matches_on_sample_1e-5_rel": ok}
+        if not ok:
+            log("WARNING: GPU result differs from the CPU reference on the sample")
+
+    if rank == 0:
+        line = {"metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline,
+                "cpu_baseline": cpu, "y_checksum": checksum, "nnz": m.nnz}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

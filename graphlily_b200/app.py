@@ -1,0 +1,319 @@
+"""Graph algorithms: the Python mirror of ``graphlily::app`` (BFS, PageRank, SSSP).
+
+Follows ``/root/reference/graphlily/app/{module_collection,bfs,pagerank,sssp}.h``: same class
+and method names, same pre-processing, same buffer aliasing, same results.  Two execution
+modes per pull loop:
+
+* ``fused=False`` -- the reference's launch sequence literally (``SpMV.run(); eWiseAdd.run();
+  DenseAssign.run()`` per iteration, ``bfs.h:117-124``);
+* ``fused=True`` (default) -- one ``glb_spmv_fused`` launch per iteration: the eWiseAdd and the
+  dense assign ride in the SpMV write-back and the results / vector buffers ping-pong instead
+  of being copied.
+
+The push->pull switch of ``pull_push`` converts the sparse frontier to a dense vector on the
+device (``glb_sparse_to_dense``) instead of the reference's host round trip (``bfs.h:195-201``).
+``load_and_format_matrix`` takes an ``.npz`` path like the reference, or a ``CSRMatrix``.
+"""
+import copy
+
+import numpy as np
+
+from . import capi, io
+from .capi import Epilogue
+from .module import (AssignVectorDenseModule, AssignVectorSparseModule, SpMSpVModule, SpMVModule, eWiseAddModule)
+
+ArithmeticSemiring = (capi.OP_MUL_ADD, 1.0, 0.0)
+LogicalSemiring = (capi.OP_LOGICAL_AND_OR, 1.0, 0.0)
+TropicalSemiring = (capi.OP_ADD_MIN, 0.0, 255.0)
+PACK = 8  # graphlily::pack_size, global.h:57
+
+
+class ModuleCollection:
+    """module_collection.h:15-114"""
+
+    def __init__(self):
+        self.modules_ = []
+        self.target_ = "hw"
+        self.ctx = None
+
+    def add_module(self, module):
+        self.modules_.append(module)
+
+    def set_target(self, target):
+        assert target in ("sw_emu", "hw_emu", "hw")
+        self.target_ = target
+
+    def set_up_runtime(self, xclbin_file_path=None, device=0, ctx=None):
+        """One context (device + stream) shared by all modules; the bitstream path is ignored."""
+        self.ctx = ctx or capi.Context(device)
+        for m in self.modules_:
+            m.set_context(self.ctx)
+
+
+def _load(path_or_csr):
+    if isinstance(path_or_csr, str):
+        return io.load_csr_matrix_from_float_npz(path_or_csr)
+    return copy.deepcopy(path_or_csr)
+
+
+class BFS(ModuleCollection):
+    """bfs.h:20-360"""
+
+    def __init__(self, num_channels=16, spmv_out_buf_len=0, spmspv_out_buf_len=0, vec_buf_len=0):
+        super().__init__()
+        self.num_channels_ = num_channels
+        self.semiring_ = LogicalSemiring
+        self.SpMV_ = SpMVModule(num_channels, spmv_out_buf_len, vec_buf_len)
+        self.SpMV_.set_semiring(self.semiring_)
+        self.SpMV_.set_mask_type(capi.MASK_WRITE_TO_ZERO)
+        self.add_module(self.SpMV_)
+        self.DenseAssign_ = AssignVectorDenseModule()
+        self.DenseAssign_.set_mask_type(capi.MASK_WRITE_TO_ONE)
+        self.add_module(self.DenseAssign_)
+        self.SpMSpV_ = SpMSpVModule(spmspv_out_buf_len)
+        self.SpMSpV_.set_semiring(self.semiring_)
+        self.SpMSpV_.set_mask_type(capi.MASK_WRITE_TO_ZERO)
+        self.add_module(self.SpMSpV_)
+        self.SparseAssign_ = AssignVectorSparseModule(False)
+        self.add_module(self.SparseAssign_)
+        self.eWiseAdd_ = eWiseAddModule()
+        self.add_module(self.eWiseAdd_)
+
+    def get_nnz(self):
+        return self.SpMV_.get_nnz()
+
+    def load_and_format_matrix(self, csr_float_npz_path, skip_empty_rows=True):
+        """bfs.h:84-97: round dims to 128, all values 1, CSC for the push direction."""
+        m = _load(csr_float_npz_path)
+        io.util_round_csr_matrix_dim(m, self.num_channels_ * PACK, self.num_channels_ * PACK)
+        m.data = np.ones(m.nnz, np.float32)
+        self.csr_matrix_ = m
+        self.SpMV_.load_and_format_matrix(m, skip_empty_rows)
+        self.SpMSpV_.load_and_format_matrix(io.csr2csc(m))
+        self.matrix_num_rows_, self.matrix_num_cols_ = m.num_rows, m.num_cols
+        assert m.num_rows == m.num_cols
+
+    def send_matrix_host_to_device(self):
+        self.SpMV_.send_matrix_host_to_device()
+        self.SpMSpV_.send_matrix_host_to_device()
+
+    # -- pull ------------------------------------------------------------------------
+    def _pull_loop(self, first_iter, num_iterations, fused):
+        n = self.matrix_num_rows_
+        if fused:
+            for it in range(first_iter, num_iterations + 1):
+                ep = Epilogue(0, 0.0, self.SpMV_.mask_buf.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE)
+                self.SpMV_.run(ep)
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+        else:
+            self.DenseAssign_.bind_mask_buf(self.SpMV_.vector_buf)
+            self.DenseAssign_.bind_inout_buf(self.SpMV_.mask_buf)
+            self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
+            self.eWiseAdd_.bind_out_buf(self.SpMV_.vector_buf)
+            for it in range(first_iter, num_iterations + 1):
+                self.SpMV_.run()
+                self.eWiseAdd_.run(n, 0.0)
+                self.DenseAssign_.run(n, float(it + 1))
+
+    def pull(self, source, num_iterations, fused=True):
+        """bfs.h:106-126"""
+        n = self.matrix_num_rows_
+        inp = np.full(n, self.semiring_[2], np.float32)
+        distance = np.zeros(n, np.float32)
+        inp[source] = 1
+        distance[source] = 1
+        self.SpMV_.send_vector_host_to_device(inp)
+        self.SpMV_.send_mask_host_to_device(distance)
+        self._pull_loop(1, num_iterations, fused)
+        return self.SpMV_.send_mask_device_to_host()
+
+    # -- push ------------------------------------------------------------------------
+    def _push_setup(self, source):
+        n = self.matrix_num_rows_
+        distance = np.zeros(n, np.float32)
+        distance[source] = 1
+        self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [1.0]))
+        self.SpMSpV_.send_mask_host_to_device(distance)
+        self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
+
+    def _push_step(self, it):
+        # SpMSpV.run(); results -> vector (the reference copies 1+nnz entries, bfs.h:147-151;
+        # here the two list buffers swap roles); SparseAssign.run(iter + 1)
+        self.SpMSpV_.run()
+        self.SpMSpV_.vector_buf, self.SpMSpV_.results_buf = self.SpMSpV_.results_buf, self.SpMSpV_.vector_buf
+        self.SparseAssign_.bind_mask_buf(self.SpMSpV_.vector_buf)
+        self.SparseAssign_.run(float(it + 1))
+
+    def push(self, source, num_iterations):
+        """bfs.h:129-157"""
+        self._push_setup(source)
+        for it in range(1, num_iterations + 1):
+            self._push_step(it)
+        return self.SpMSpV_.send_mask_device_to_host()
+
+    def pull_push(self, source, num_iterations, threshold=0.05, fused=True):
+        """bfs.h:160-219: push while the frontier is sparse, then pull."""
+        n = self.matrix_num_rows_
+        self._push_setup(source)
+        it = 1
+        while True:
+            self._push_step(it)
+            vector_nnz = capi.sparse_count(self.ctx, self.SpMSpV_.vector_buf)
+            it += 1
+            if not (it < num_iterations and float(vector_nnz) / n < threshold):
+                break
+        self.push_iterations_ = it - 1
+        # switch: the last frontier becomes the dense SpMV input, on the device
+        self.SpMV_.bind_mask_buf(self.SpMSpV_.mask_buf)
+        if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
+            self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
+        capi.sparse_to_dense(self.ctx, self.SpMSpV_.vector_buf, self.SpMV_.vector_buf, n, LogicalSemiring[2])
+        self._pull_loop(it, num_iterations, fused)
+        return self.SpMSpV_.send_mask_device_to_host()
+
+
+class PageRank(ModuleCollection):
+    """pagerank.h:17-159"""
+
+    def __init__(self, num_channels=16, spmv_out_buf_len=0, vec_buf_len=0):
+        super().__init__()
+        self.num_channels_ = num_channels
+        self.semiring_ = ArithmeticSemiring
+        self.SpMV_ = SpMVModule(num_channels, spmv_out_buf_len, vec_buf_len)
+        self.SpMV_.set_semiring(self.semiring_)
+        self.SpMV_.set_mask_type(capi.MASK_NONE)
+        self.add_module(self.SpMV_)
+        self.eWiseAdd_ = eWiseAddModule()
+        self.add_module(self.eWiseAdd_)
+
+    def get_nnz(self):
+        return self.SpMV_.get_nnz()
+
+    def load_and_format_matrix(self, csr_float_npz_path, damping, skip_empty_rows=True):
+        """pagerank.h:60-73: round dims, 1/colcount (double divide -> float), * damping in float."""
+        m = _load(csr_float_npz_path)
+        io.util_round_csr_matrix_dim(m, self.num_channels_ * PACK, self.num_channels_ * PACK)
+        io.util_normalize_csr_matrix_by_outdegree(m)
+        m.data = (m.data * np.float32(damping)).astype(np.float32)
+        self.csr_matrix_ = m
+        self.SpMV_.load_and_format_matrix(m, skip_empty_rows)
+        self.matrix_num_rows_, self.matrix_num_cols_ = m.num_rows, m.num_cols
+        assert m.num_rows == m.num_cols
+
+    def send_matrix_host_to_device(self, row_begin=0, row_end=None):
+        self.SpMV_.send_matrix_host_to_device(row_begin, row_end)
+
+    def pull(self, damping, num_iterations, fused=True):
+        """pagerank.h:80-90"""
+        n = self.matrix_num_rows_
+        rank = np.full(n, np.float32(1.0 / n), np.float32)
+        teleport = float((np.float32(1) - np.float32(damping)) / np.float32(n))
+        self.SpMV_.send_vector_host_to_device(rank)
+        if fused:
+            for _ in range(num_iterations):
+                self.SpMV_.run(Epilogue(1, teleport, None, 0.0, 0))
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+        else:
+            self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
+            self.eWiseAdd_.bind_out_buf(self.SpMV_.vector_buf)
+            for _ in range(num_iterations):
+                self.SpMV_.run()
+                self.eWiseAdd_.run(n, teleport)
+        return self.SpMV_.send_vector_device_to_host()
+
+
+class SSSP(ModuleCollection):
+    """sssp.h:68-253"""
+
+    def __init__(self, num_channels=16, spmv_out_buf_len=0, spmspv_out_buf_len=0, vec_buf_len=0):
+        super().__init__()
+        self.num_channels_ = num_channels
+        self.semiring_ = TropicalSemiring
+        self.SpMV_ = SpMVModule(num_channels, spmv_out_buf_len, vec_buf_len)
+        self.SpMV_.set_semiring(self.semiring_)
+        self.SpMV_.set_mask_type(capi.MASK_NONE)
+        self.add_module(self.SpMV_)
+        self.SpMSpV_ = SpMSpVModule(spmspv_out_buf_len)
+        self.SpMSpV_.set_semiring(self.semiring_)
+        self.SpMSpV_.set_mask_type(capi.MASK_NONE)
+        self.add_module(self.SpMSpV_)
+        self.SparseAssign_ = AssignVectorSparseModule(True)
+        self.add_module(self.SparseAssign_)
+        self.eWiseAdd_ = eWiseAddModule()
+        self.add_module(self.eWiseAdd_)
+
+    def get_nnz(self):
+        return self.SpMV_.get_nnz()
+
+    def load_and_format_matrix(self, csr_float_npz_path, skip_empty_rows=True):
+        """sssp.h:128-143: _preprocess (weights 1, zero diagonal) THEN round dims, CSC for push."""
+        m = _load(csr_float_npz_path)
+        io.sssp_preprocess(m)
+        io.util_round_csr_matrix_dim(m, self.num_channels_ * PACK, self.num_channels_ * PACK)
+        self.csr_matrix_ = m
+        self.SpMV_.load_and_format_matrix(m, skip_empty_rows)
+        self.SpMSpV_.load_and_format_matrix(io.csr2csc(m))
+        self.matrix_num_rows_, self.matrix_num_cols_ = m.num_rows, m.num_cols
+        assert m.num_rows == m.num_cols
+
+    def send_matrix_host_to_device(self):
+        self.SpMV_.send_matrix_host_to_device()
+        self.SpMSpV_.send_matrix_host_to_device()
+
+    def _pull_loop(self, first_iter, num_iterations, fused):
+        n = self.matrix_num_rows_
+        if fused:
+            for _ in range(first_iter, num_iterations + 1):
+                self.SpMV_.run()
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+        else:
+            self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
+            self.eWiseAdd_.bind_out_buf(self.SpMV_.vector_buf)
+            for _ in range(first_iter, num_iterations + 1):
+                self.SpMV_.run()
+                self.eWiseAdd_.run(n, 0.0)
+
+    def pull(self, source, num_iterations, fused=True):
+        """sssp.h:152-166"""
+        inp = np.full(self.matrix_num_rows_, self.semiring_[2], np.float32)
+        inp[source] = 0
+        self.SpMV_.send_vector_host_to_device(inp)
+        self._pull_loop(1, num_iterations, fused)
+        return self.SpMV_.send_vector_device_to_host()
+
+    def _push_setup(self, source):
+        distance = np.full(self.matrix_num_rows_, self.semiring_[2], np.float32)
+        distance[source] = 0
+        self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [0.0]))
+        self.SpMSpV_.send_mask_host_to_device(distance)
+        self.SparseAssign_.bind_mask_buf(self.SpMSpV_.results_buf)
+        self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
+        self.SparseAssign_.bind_new_frontier_buf(self.SpMSpV_.vector_buf)
+
+    def push(self, source, num_iterations):
+        """sssp.h:169-194"""
+        self._push_setup(source)
+        for _ in range(num_iterations):
+            self.SpMSpV_.run()
+            self.SparseAssign_.run()
+        return self.SpMSpV_.send_mask_device_to_host()
+
+    def pull_push(self, source, num_iterations, threshold=0.05, fused=True):
+        """sssp.h:197-243"""
+        n = self.matrix_num_rows_
+        self._push_setup(source)
+        it = 1
+        while True:
+            self.SpMSpV_.run()
+            self.SparseAssign_.run()
+            vector_nnz = self.SpMSpV_.get_results_nnz()
+            it += 1
+            if not (it < num_iterations and float(vector_nnz) / n < threshold):
+                break
+        self.push_iterations_ = it - 1
+        # switch: the distance vector becomes the SpMV input (device copy, no host round trip)
+        if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
+            self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
+        capi.d2d(self.ctx, self.SpMV_.vector_buf, self.SpMSpV_.mask_buf, 4 * n)
+        self._pull_loop(it, num_iterations, fused)
+        return self.SpMV_.send_vector_device_to_host()

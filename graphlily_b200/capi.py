@@ -48,6 +48,8 @@ SIGNATURES = {
     "glb_ctx_destroy": (C.c_int, [_vp]),
     "glb_ctx_sync": (C.c_int, [_vp]),
     "glb_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "glb_ctx_kernel_timing": (C.c_int, [_vp, C.c_int]),
+    "glb_ctx_kernel_timing_read": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "glb_buffer_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "glb_buffer_free": (C.c_int, [_vp, _vp]),
     "glb_buffer_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -137,6 +139,28 @@ class Context:
         if self.handle:
             lib.glb_ctx_destroy(self.handle)
             self.handle = None
+
+    def kernel_timing(self, enable):
+        check(lib.glb_ctx_kernel_timing(self.handle, int(enable)))
+
+    def kernel_timing_read(self):
+        """(ms in SpMV main kernel, ms in fix-up kernel, launches) since the last read."""
+        out = (C.c_double * 3)()
+        check(lib.glb_ctx_kernel_timing_read(self.handle, out))
+        return out[0], out[1], int(out[2])
+
+    # ---- multi-GPU (NCCL resolved with dlopen inside the library) -------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        check(lib.glb_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, nranks):
+        check(lib.glb_comm_init(self.handle, C.c_char_p(unique_id), rank, nranks))
+
+    def allgather_f32(self, buf, count_per_rank):
+        check(lib.glb_allgather_f32(self.handle, _ptr(buf), count_per_rank))
 
     # ---- buffers ------------------------------------------------------------------
     def alloc(self, nbytes):

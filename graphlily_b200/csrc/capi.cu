@@ -70,9 +70,7 @@ int glb_ctx_destroy(glb_ctx_t ctx) {
     if (!ctx) return GLB_OK;
     cudaSetDevice(ctx->device);
     glb_comm_destroy(ctx);
-    if (ctx->hx) cudaFreeHost(ctx->hx);
-    if (ctx->hmask) cudaFreeHost(ctx->hmask);
-    if (ctx->hy) cudaFreeHost(ctx->hy);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GLB_OK;
@@ -87,6 +85,29 @@ int glb_ctx_sync(glb_ctx_t ctx) {
 int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream) {
     GLB_REQUIRE(ctx && cuda_stream, "NULL argument");
     *cuda_stream = ctx->stream;
+    return GLB_OK;
+}
+
+int glb_ctx_kernel_timing(glb_ctx_t ctx, int enable) {
+    GLB_REQUIRE(ctx, "ctx is NULL");
+    ctx->timing = enable != 0;
+    return GLB_OK;
+}
+
+int glb_ctx_kernel_timing_read(glb_ctx_t ctx, double out[3]) {
+    GLB_REQUIRE(ctx && out, "NULL argument");
+    out[0] = out[1] = out[2] = 0.0;
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 2 < ctx->timing_events.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        GLB_CUDA(cudaEventElapsedTime(&a, ctx->timing_events[i], ctx->timing_events[i + 1]));
+        GLB_CUDA(cudaEventElapsedTime(&b, ctx->timing_events[i + 1], ctx->timing_events[i + 2]));
+        out[0] += a;
+        out[1] += b;
+        out[2] += 1.0;
+    }
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    ctx->timing_events.clear();
     return GLB_OK;
 }
 

@@ -38,9 +38,9 @@ struct glb_ctx_s {
     bool owns_stream = false;
     void *nccl_comm = nullptr;  // ncclComm_t when built with GLB_WITH_NCCL
     int nccl_rank = 0, nccl_nranks = 1;
-    // scratch for glb_spmv_host (grown on demand)
-    float *hx = nullptr, *hmask = nullptr, *hy = nullptr;
-    size_t hx_n = 0, hmask_n = 0, hy_n = 0;
+    // optional per-kernel timing (glb_ctx_kernel_timing): event triples of timed launches
+    bool timing = false;
+    std::vector<cudaEvent_t> timing_events;  // 3 per launch: before main, after main, after fix-up
 };
 
 // ---------------------------------------------------------------- warp-segment CSR (SpMV)

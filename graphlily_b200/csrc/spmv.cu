@@ -215,15 +215,25 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
 
 template <int OP>
 int launch_op(glb_ctx_t ctx, const SpmvParams &P) {
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (ctx->timing) {
+        for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
+        GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
+    }
     if (P.n_chunks) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
         spmv_ws_kernel<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
     }
+    if (ctx->timing) GLB_CUDA(cudaEventRecord(ev[1], ctx->stream));
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
     const uint32_t nb_long = (P.n_fix_long + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const uint32_t nb_empty = (P.n_empty + kThreads - 1) / kThreads;
     if (nb_short + nb_long + nb_empty)
         spmv_fixup_kernel<OP><<<nb_short + nb_long + nb_empty, kThreads, 0, ctx->stream>>>(P, nb_short, nb_long);
+    if (ctx->timing) {
+        GLB_CUDA(cudaEventRecord(ev[2], ctx->stream));
+        for (auto e : ev) ctx->timing_events.push_back(e);
+    }
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }

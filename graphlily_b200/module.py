@@ -1,0 +1,294 @@
+"""Operator modules: the Python mirror of ``graphlily::module`` over the C ABI.
+
+Same class names, method names, argument meaning and error behaviour as
+``/root/reference/graphlily/module/*.h`` (the C++ mirror with identical signatures is in
+``include/graphlily/module``).  ``cl::Buffer`` members become :class:`capi.DeviceBuffer`
+handles with the same public names (``vector_buf``, ``mask_buf``, ``results_buf`` ...), so the
+apps alias them across modules exactly as the reference does (``bfs.h:113-116``).
+``run()`` enqueues on the context's stream; every ``send_*_device_to_host`` synchronises.
+Tuning arguments of the FPGA build (``num_channels``, ``*_buf_len``) are accepted and ignored.
+"""
+import numpy as np
+
+from . import capi
+from .io import CSRMatrix
+
+
+class BaseModule:
+    """base_module.h:10-103"""
+    _shared_ctx = None
+
+    def __init__(self, kernel_name="overlay"):
+        self.kernel_name_ = kernel_name
+        self.target_ = "hw"
+        self.ctx = None
+
+    def get_kernel_name(self):
+        return self.kernel_name_
+
+    def set_target(self, target):
+        assert target in ("sw_emu", "hw_emu", "hw")   # base_module.h:75
+        self.target_ = target
+
+    def set_context(self, ctx):
+        self.ctx = ctx
+
+    def set_up_runtime(self, xclbin_file_path=None, device=0):
+        """base_module.h:106-133; the bitstream path is ignored (kernels are in the library)."""
+        if self.ctx is None:
+            self.ctx = capi.Context(device)
+
+    def copy_buffer_device_to_device(self, src, dst, nbytes):
+        """base_module.h:82-85 (enqueueCopyBuffer + finish)"""
+        capi.d2d(self.ctx, dst, src, nbytes)
+        self.ctx.sync()
+
+    def _dense_to_device(self, vec):
+        return self.ctx.to_device(np.ascontiguousarray(vec, np.float32))
+
+
+class SpMVModule(BaseModule):
+    """spmv_module.h:26-272"""
+
+    def __init__(self, num_channels=16, out_buf_len=0, vec_buf_len=0):
+        super().__init__()
+        self.semiring_ = (capi.OP_MUL_ADD, 1.0, 0.0)
+        self.mask_type_ = capi.MASK_NONE
+        self.csr_matrix_float_ = None
+        self.matrix = None
+        self.vector_buf = self.mask_buf = self.results_buf = None
+
+    def set_semiring(self, semiring):
+        self.semiring_ = semiring
+
+    def set_mask_type(self, mask_type):
+        self.mask_type_ = mask_type
+
+    def get_num_rows(self):
+        return self.csr_matrix_float_.num_rows
+
+    def get_num_cols(self):
+        return self.csr_matrix_float_.num_cols
+
+    def get_nnz(self):
+        return self.csr_matrix_float_.nnz
+
+    def load_and_format_matrix(self, csr_matrix_float, skip_empty_rows=True):
+        """spmv_module.h:282-370; the device layout itself is built at upload time."""
+        self.csr_matrix_float_ = csr_matrix_float
+
+    def send_matrix_host_to_device(self, row_begin=0, row_end=None):
+        """spmv_module.h:374-420 (+ allocation of the results buffer)."""
+        self.matrix = capi.CsrMatrix(self.ctx, self.csr_matrix_float_, row_begin, row_end)
+        self.results_buf = self.ctx.zeros_f32(self.get_num_rows())
+
+    def send_vector_host_to_device(self, vector):
+        self.vector_buf = self._dense_to_device(vector)      # spmv_module.h:424-440
+
+    def send_mask_host_to_device(self, mask):
+        self.mask_buf = self._dense_to_device(mask)          # spmv_module.h:444-459
+
+    def bind_mask_buf(self, src_buf):
+        self.mask_buf = src_buf                              # spmv_module.h:463-467
+
+    def run(self, epilogue=None):
+        """spmv_module.h:471-475"""
+        op, _one, zero = self.semiring_
+        self.matrix.spmv(op, zero, self.mask_type_, self.vector_buf,
+                         self.mask_buf if self.mask_type_ != capi.MASK_NONE else None, self.results_buf, epilogue)
+
+    def send_vector_device_to_host(self):
+        return self.vector_buf.read(np.float32, self.get_num_cols())
+
+    def send_mask_device_to_host(self):
+        return self.mask_buf.read(np.float32, self.get_num_rows())
+
+    def send_results_device_to_host(self):
+        return self.results_buf.read(np.float32, self.get_num_rows())
+
+
+class SpMSpVModule(BaseModule):
+    """spmspv_module.h:26-254"""
+
+    def __init__(self, out_buf_len=0):
+        super().__init__()
+        self.semiring_ = (capi.OP_MUL_ADD, 1.0, 0.0)
+        self.mask_type_ = capi.MASK_NONE
+        self.csc_matrix_float_ = None
+        self.matrix = None
+        self.vector_buf = self.mask_buf = self.results_buf = None
+
+    def set_semiring(self, semiring):
+        self.semiring_ = semiring
+
+    def set_mask_type(self, mask_type):
+        self.mask_type_ = mask_type
+
+    def get_num_rows(self):
+        return self.csc_matrix_float_.num_rows
+
+    def get_num_cols(self):
+        return self.csc_matrix_float_.num_cols
+
+    def get_nnz(self):
+        return self.csc_matrix_float_.nnz
+
+    def load_and_format_matrix(self, csc_matrix_float):
+        self.csc_matrix_float_ = csc_matrix_float             # spmspv_module.h:264-286
+
+    def send_matrix_host_to_device(self):
+        """spmspv_module.h:290-370: matrix upload + results (rows+1) and vector (cols+1) lists."""
+        self.matrix = capi.CscMatrix(self.ctx, self.csc_matrix_float_)
+        self.results_buf = self.ctx.to_device(np.zeros(self.get_num_rows() + 1, capi.IDX_VAL))
+        self.vector_buf = self.ctx.to_device(np.zeros(self.get_num_cols() + 1, capi.IDX_VAL))
+
+    def send_vector_host_to_device(self, vector):
+        """``vector``: idx_val_t array with the {nnz, -} head (spmspv_module.h:374-399)."""
+        self.vector_buf.write(np.ascontiguousarray(vector, capi.IDX_VAL))
+
+    def send_mask_host_to_device(self, mask):
+        self.mask_buf = self._dense_to_device(mask)          # spmspv_module.h:403-433
+
+    def bind_mask_buf(self, src_buf):
+        self.mask_buf = src_buf
+
+    def run(self):
+        """spmspv_module.h:437-441"""
+        op, _one, zero = self.semiring_
+        self.matrix.spmspv(op, zero, self.mask_type_, self.vector_buf,
+                           self.mask_buf if self.mask_type_ != capi.MASK_NONE else None, self.results_buf)
+
+    def send_vector_device_to_host(self):
+        n = capi.sparse_count(self.ctx, self.vector_buf)
+        return self.vector_buf.read(capi.IDX_VAL, n + 1)
+
+    def send_mask_device_to_host(self):
+        return self.mask_buf.read(np.float32, self.get_num_rows())
+
+    def send_results_device_to_host(self):
+        n = capi.sparse_count(self.ctx, self.results_buf)
+        return self.results_buf.read(capi.IDX_VAL, n + 1)
+
+    def get_results_nnz(self):
+        return capi.sparse_count(self.ctx, self.results_buf)  # spmspv_module.h:239-242
+
+
+class eWiseAddModule(BaseModule):
+    """add_scalar_vector_dense_module.h:17-138"""
+
+    def __init__(self):
+        super().__init__()
+        self.in_buf = self.out_buf = None
+        self._out_len = 0
+
+    def send_in_host_to_device(self, vec):
+        self.in_buf = self._dense_to_device(vec)
+        self._in_len = len(vec)
+
+    def allocate_out_buf(self, length):
+        self.out_buf = self.ctx.zeros_f32(length)
+        self._out_len = length
+
+    def bind_in_buf(self, src_buf):
+        self.in_buf = src_buf
+
+    def bind_out_buf(self, src_buf):
+        self.out_buf = src_buf
+
+    def run(self, length, val):
+        capi.ewise_add(self.ctx, self.in_buf, self.out_buf, length, val)
+
+    def send_out_device_to_host(self):
+        return self.out_buf.read(np.float32, self.out_buf.nbytes // 4)
+
+
+class AssignVectorDenseModule(BaseModule):
+    """assign_vector_dense_module.h:17-164"""
+
+    def __init__(self):
+        super().__init__()
+        self.mask_type_ = None
+        self.mask_buf = self.inout_buf = None
+
+    def set_mask_type(self, mask_type):
+        if mask_type == capi.MASK_NONE:   # assign_vector_dense_module.h:88-95: print + exit(EXIT_FAILURE)
+            print("Please set the mask type")
+            raise SystemExit(1)
+        self.mask_type_ = mask_type
+
+    def send_mask_host_to_device(self, mask):
+        self.mask_buf = self._dense_to_device(mask)
+
+    def send_inout_host_to_device(self, inout):
+        self.inout_buf = self._dense_to_device(inout)
+
+    def bind_mask_buf(self, src_buf):
+        self.mask_buf = src_buf
+
+    def bind_inout_buf(self, src_buf):
+        self.inout_buf = src_buf
+
+    def run(self, length, val):
+        capi.assign_dense(self.ctx, self.mask_buf, self.inout_buf, length, val, self.mask_type_)
+
+    def send_mask_device_to_host(self):
+        return self.mask_buf.read(np.float32, self.mask_buf.nbytes // 4)
+
+    def send_inout_device_to_host(self):
+        return self.inout_buf.read(np.float32, self.inout_buf.nbytes // 4)
+
+
+class AssignVectorSparseModule(BaseModule):
+    """assign_vector_sparse_module.h:17-210"""
+
+    def __init__(self, generate_new_frontier):
+        super().__init__()
+        self.generate_new_frontier_ = generate_new_frontier
+        self.mask_buf = self.inout_buf = self.new_frontier_buf = None
+
+    def send_mask_host_to_device(self, mask):
+        mask = np.ascontiguousarray(mask, capi.IDX_VAL)
+        self.mask_buf = self.ctx.to_device(mask)
+        if self.generate_new_frontier_:   # assign_vector_sparse_module.h:232-247
+            self.new_frontier_buf = self.ctx.to_device(np.zeros(len(mask), capi.IDX_VAL))
+
+    def send_inout_host_to_device(self, inout):
+        self.inout_buf = self._dense_to_device(inout)
+
+    def bind_mask_buf(self, src_buf):
+        self.mask_buf = src_buf
+
+    def bind_inout_buf(self, src_buf):
+        self.inout_buf = src_buf
+
+    def bind_new_frontier_buf(self, src_buf):
+        if not self.generate_new_frontier_:
+            print("[ERROR]: this->generate_new_frontier_ should be true")
+            raise SystemExit(1)
+        self.new_frontier_buf = src_buf
+
+    def run(self, val=None):
+        if val is not None:
+            if self.generate_new_frontier_:
+                print("[ERROR]: this->generate_new_frontier_ should be false")
+                raise SystemExit(1)
+            capi.assign_sparse(self.ctx, self.mask_buf, self.inout_buf, val)
+        else:
+            if not self.generate_new_frontier_:
+                print("[ERROR]: this->generate_new_frontier_ should be true")
+                raise SystemExit(1)
+            capi.assign_sparse_relax(self.ctx, self.mask_buf, self.inout_buf, self.new_frontier_buf)
+
+    def send_mask_device_to_host(self):
+        n = capi.sparse_count(self.ctx, self.mask_buf)
+        return self.mask_buf.read(capi.IDX_VAL, n + 1)
+
+    def send_inout_device_to_host(self):
+        return self.inout_buf.read(np.float32, self.inout_buf.nbytes // 4)
+
+    def send_new_frontier_device_to_host(self):
+        if not self.generate_new_frontier_:
+            print("[ERROR]: this->generate_new_frontier_ should be true")
+            raise SystemExit(1)
+        n = capi.sparse_count(self.ctx, self.new_frontier_buf)
+        return self.new_frontier_buf.read(capi.IDX_VAL, n + 1)

@@ -82,6 +82,13 @@ int glb_ctx_create(int device, void *cuda_stream, glb_ctx_t *out);
 int glb_ctx_destroy(glb_ctx_t ctx);
 int glb_ctx_sync(glb_ctx_t ctx); /* command_queue_.finish() */
 int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream);
+/* Per-kernel device timing for roofline accounting (the queues of the reference are created
+ * with CL_QUEUE_PROFILING_ENABLE, base_module.h:127).  While enabled, glb_spmv / glb_spmv_fused
+ * bracket the main kernel and the fix-up kernel with CUDA events on the context's stream.
+ * glb_ctx_kernel_timing_read synchronises and returns, summed since the last read:
+ * out[0] = ms in the SpMV main kernel, out[1] = ms in the fix-up kernel, out[2] = launches timed. */
+int glb_ctx_kernel_timing(glb_ctx_t ctx, int enable);
+int glb_ctx_kernel_timing_read(glb_ctx_t ctx, double out[3]);
 
 /* ------------------------------------------------------------------ buffers -------
  * cl::Buffer + enqueueMigrateMemObjects (e.g. spmv_module.h:424-459, 229-253). */

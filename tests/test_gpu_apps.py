@@ -1,0 +1,105 @@
+"""BFS / PageRank / SSSP through the module + app mirror (graphlily_b200.module / .app) against the
+oracle -- the shape of /root/reference/tests/test_app.cpp:51-135 (uniform_10K_10, source 0, 10
+iterations) plus power-law graphs and the committed reference-produced fixture.
+BFS and SSSP must be bit-exact; PageRank within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from golden_util import golden, golden_csr
+from graphlily_b200 import app, datasets
+from graphlily_b200.io import CSRMatrix
+from util import assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def prep_bfs(oracle, m):
+    nr, nc, ip = oracle.port.round_dim(m.num_rows, m.num_cols, m.indptr, 128, 128)
+    return CSRMatrix(nr, nc, np.ones(m.nnz, np.float32), m.indices, ip)
+
+
+def prep_pagerank(oracle, m, damping):
+    nr, nc, ip = oracle.port.round_dim(m.num_rows, m.num_cols, m.indptr, 128, 128)
+    r = CSRMatrix(nr, nc, m.data, m.indices, ip)
+    r.data = oracle.port.normalize_outdegree(r) * np.float32(damping)
+    return r
+
+
+def prep_sssp(oracle, m):
+    sip, six, sd = oracle.port.sssp_preprocess(m)
+    nr, nc, ip = oracle.port.round_dim(m.num_rows, m.num_cols, sip, 128, 128)
+    return CSRMatrix(nr, nc, sd, six, ip)
+
+
+GRAPHS = {
+    "uniform_10K_10": lambda: datasets.uniform_csr(10000, 10000, 10, seed=0, value=1.0),
+    "powerlaw_20k": lambda: datasets.powerlaw_graph(20000, 400000, seed=5, diagonal=True),
+    "line_8": lambda: datasets.line_graph(8),
+}
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
+def test_bfs(ctx, oracle, name):
+    g = GRAPHS[name]()
+    ref = oracle.port.bfs(prep_bfs(oracle, g), 0, 10)
+    bfs = app.BFS(16, 1024, 512, 256)
+    bfs.set_target("hw")
+    bfs.set_up_runtime("ignored.xclbin", ctx=ctx)
+    bfs.load_and_format_matrix(g, True)
+    bfs.send_matrix_host_to_device()
+    for fused in (True, False):
+        assert bfs.pull(0, 10, fused=fused).tobytes() == ref.tobytes()
+    assert bfs.push(0, 10).tobytes() == ref.tobytes()
+    for thr in (0.1, 0.001, 1.1):
+        for fused in (True, False):
+            assert bfs.pull_push(0, 10, thr, fused=fused).tobytes() == ref.tobytes(), (thr, fused)
+    if name != "line_8":
+        assert ref.max() >= 3 and (ref > 0).sum() > 100
+
+
+@pytest.mark.parametrize("name", ["uniform_10K_10", "powerlaw_20k"])
+def test_pagerank(ctx, oracle, name):
+    g = GRAPHS[name]()
+    ref = oracle.port.pagerank(prep_pagerank(oracle, g, 0.9), 0.9, 10)
+    pr = app.PageRank(16, 1024, 256)
+    pr.set_up_runtime(None, ctx=ctx)
+    pr.load_and_format_matrix(g, 0.9, True)
+    pr.send_matrix_host_to_device()
+    for fused in (True, False):
+        assert_close_rel(pr.pull(0.9, 10, fused=fused), ref, 1e-5)
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
+def test_sssp(ctx, oracle, name):
+    g = GRAPHS[name]()
+    ref = oracle.port.sssp(prep_sssp(oracle, g), 0, 10)
+    s = app.SSSP(16, 1024, 512, 256)
+    s.set_up_runtime(None, ctx=ctx)
+    s.load_and_format_matrix(g, True)
+    s.send_matrix_host_to_device()
+    for fused in (True, False):
+        assert s.pull(0, 10, fused=fused).tobytes() == ref.tobytes()
+    assert s.push(0, 10).tobytes() == ref.tobytes()
+    for thr in (0.1, 0.001, 1.1):
+        assert s.pull_push(0, 10, thr).tobytes() == ref.tobytes(), thr
+
+
+def test_apps_against_reference_fixture(ctx):
+    z, g = golden(), golden_csr("app")
+    bfs = app.BFS()
+    bfs.set_up_runtime(None, ctx=ctx)
+    bfs.load_and_format_matrix(g)
+    bfs.send_matrix_host_to_device()
+    assert bfs.pull(0, 10).tobytes() == z["app_bfs"].tobytes()
+    assert bfs.pull_push(0, 10, 0.05).tobytes() == z["app_bfs"].tobytes()
+    pr = app.PageRank()
+    pr.set_up_runtime(None, ctx=ctx)
+    pr.load_and_format_matrix(g, 0.9)
+    pr.send_matrix_host_to_device()
+    assert_close_rel(pr.pull(0.9, 10), z["app_pagerank"], 1e-5)
+    s = app.SSSP()
+    s.set_up_runtime(None, ctx=ctx)
+    s.load_and_format_matrix(g)
+    s.send_matrix_host_to_device()
+    assert s.pull(0, 10).tobytes() == z["app_sssp"].tobytes()
+    assert s.pull_push(0, 10, 0.05).tobytes() == z["app_sssp"].tobytes()

@@ -1,0 +1,275 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes -> libgraphlily_b200.so).
+
+Bars (north_star): or-and and min-plus results bit-exact; fp32 plus-times within 1e-5 relative
+(the kernel reduces a row in a different order than the sequential reference loop).
+Shapes follow tests/test_module_spmv_spmspv.cpp / test_module_apply.cpp of the reference plus the
+edge cases of a warp-segment layout: empty rows, rows longer than a chunk, rows ending on a chunk
+boundary, empty matrices, row shards."""
+import numpy as np
+import pytest
+
+from golden_util import golden, golden_csr
+from graphlily_b200 import capi, datasets, io
+from graphlily_b200.capi import Epilogue
+from graphlily_b200.io import CSRMatrix
+from util import MASKS, SEMIRINGS, assert_close_rel, densify, random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def check_vec(got, ref, op):
+    if op == capi.OP_MUL_ADD:
+        assert_close_rel(got, ref, 1e-5)
+    else:
+        assert got.tobytes() == ref.tobytes(), f"mismatch at {np.nonzero(got != ref)[0][:8]}"
+
+
+def gpu_spmv(ctx, m, op, zero, mt, x, mask, rb=0, re=None, epilogue=None, y_init=np.nan):
+    A = capi.CsrMatrix(ctx, m, rb, re)
+    dx, dy = ctx.to_device(np.asarray(x, np.float32)), ctx.to_device(np.full(m.num_rows, y_init, np.float32))
+    dm = ctx.to_device(np.asarray(mask, np.float32)) if mask is not None else None
+    A.spmv(op, zero, mt, dx, dm, dy, epilogue)
+    y = dy.read(np.float32, m.num_rows)
+    A.close()
+    return y
+
+
+# ------------------------------------------------------------------------------ SpMV
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+@pytest.mark.parametrize("mt", MASKS)
+def test_spmv_golden_fixture(ctx, op, zero, mt):
+    z, m = golden(), golden_csr("spmv")
+    y = gpu_spmv(ctx, m, op, zero, mt, z["spmv_x"], z["spmv_mask"])
+    check_vec(y, z[f"spmv_y_op{op}_m{mt}"], op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmv_golden_powerlaw(ctx, op, zero):
+    z, m = golden(), golden_csr("pl")
+    check_vec(gpu_spmv(ctx, m, op, zero, 0, z["pl_x"], None), z[f"pl_y_op{op}"], op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+@pytest.mark.parametrize("mt", MASKS)
+def test_spmv_c1_uniform_10k(ctx, oracle, op, zero, mt):
+    # BASELINE configs[0]: 10k x 10k, 10 nnz/row, A = 1/N, x = rand % 2, mask = rand % 2
+    rng = np.random.default_rng(1)
+    m = datasets.uniform_csr(10000, 10000, 10, seed=0)
+    x, mask = rng.integers(0, 2, 10000).astype(np.float32), rng.integers(0, 2, 10000).astype(np.float32)
+    check_vec(gpu_spmv(ctx, m, op, zero, mt, x, mask), oracle.port.spmv(m, op, zero, mt, x, mask), op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmv_random_shapes_with_empty_rows(ctx, oracle, op, zero):
+    rng = np.random.default_rng(10 + op)
+    for shape in [(1, 1), (5, 9), (33, 70), (257, 129), (2000, 1500)]:
+        m = random_csr(rng, *shape, 0.1, values="rand" if op == 0 else "small", empty_frac=0.3)
+        x = (rng.integers(0, 3, shape[1]) * rng.random(shape[1])).astype(np.float32)
+        mask = rng.integers(0, 2, shape[0]).astype(np.float32)
+        for mt in MASKS:
+            check_vec(gpu_spmv(ctx, m, op, zero, mt, x, mask), oracle.port.spmv(m, op, zero, mt, x, mask), op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmv_chunk_boundaries_and_long_rows(ctx, oracle, op, zero):
+    rng = np.random.default_rng(20 + op)
+    ip = [0]
+    for d in [1024, 0, 0, 2048, 1, 1023, 5000, 0, 1024, 3, 0, 70000, 7, 0]:
+        ip.append(ip[-1] + d)
+    nnz = ip[-1]
+    m = CSRMatrix(len(ip) - 1, 9000, (rng.random(nnz) if op == 0 else rng.integers(0, 3, nnz)).astype(np.float32),
+                  rng.integers(0, 9000, nnz).astype(np.uint32), np.array(ip, np.uint32))
+    x = rng.integers(0, 4, 9000).astype(np.float32)
+    check_vec(gpu_spmv(ctx, m, op, zero, 0, x, None), oracle.port.spmv(m, op, zero, 0, x), op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmv_powerlaw_1m_nnz(ctx, oracle, op, zero):
+    rng = np.random.default_rng(30 + op)
+    m = datasets.powerlaw_csr(1 << 15, 1 << 15, 1 << 20, seed=11, max_degree=1 << 14)
+    if op == 2:
+        m.data = rng.integers(0, 3, m.nnz).astype(np.float32)
+    x = rng.integers(0, 2, m.num_cols).astype(np.float32) if op != 2 else rng.integers(0, 200, m.num_cols).astype(np.float32)
+    check_vec(gpu_spmv(ctx, m, op, zero, 0, x, None), oracle.port.spmv(m, op, zero, 0, x), op)
+
+
+def test_spmv_empty_matrix_and_zero_value(ctx, oracle):
+    m = CSRMatrix(6, 4, np.zeros(0, np.float32), np.zeros(0, np.uint32), np.zeros(7, np.uint32))
+    x = np.ones(4, np.float32)
+    for op, zero in SEMIRINGS + [(0, 2.5), (2, 7.0)]:   # `zero` is a runtime value
+        check_vec(gpu_spmv(ctx, m, op, zero, 0, x, None), oracle.port.spmv(m, op, zero, 0, x), op)
+    rng = np.random.default_rng(3)
+    m = random_csr(rng, 300, 300, 0.05, values="small")
+    x = rng.integers(0, 6, 300).astype(np.float32)
+    for op, zero in [(0, 2.5), (2, 3.0), (1, 1.0)]:
+        check_vec(gpu_spmv(ctx, m, op, zero, 0, x, None), oracle.port.spmv(m, op, zero, 0, x), op)
+
+
+def test_spmv_row_shards_cover_disjoint_slices(ctx, oracle):
+    rng = np.random.default_rng(4)
+    m = datasets.powerlaw_csr(4096, 4096, 1 << 17, seed=12, max_degree=3000)
+    x = rng.random(4096).astype(np.float32)
+    ref = oracle.port.spmv(m, 0, 0.0, 0, x)
+    bounds = [0, 1024, 1031, 3000, 4096]
+    for rb, re in zip(bounds[:-1], bounds[1:]):
+        y = gpu_spmv(ctx, m, 0, 0.0, 0, x, None, rb, re, y_init=-7.0)
+        assert_close_rel(y[rb:re], ref[rb:re])
+        assert (y[:rb] == -7.0).all() and (y[re:] == -7.0).all()   # rows outside the shard untouched
+
+
+def test_spmv_fused_epilogues(ctx, oracle):
+    rng = np.random.default_rng(5)
+    g = datasets.powerlaw_graph(2048, 30000, seed=6)
+    # PageRank step: y = A x + c
+    gp = CSRMatrix(g.num_rows, g.num_cols, oracle.port.normalize_outdegree(g) * np.float32(0.9), g.indices, g.indptr)
+    x = rng.random(2048).astype(np.float32)
+    c = float(np.float32(0.1) / np.float32(2048))
+    y = gpu_spmv(ctx, gp, 0, 0.0, 0, x, None, epilogue=Epilogue(1, c, None, 0.0, 0))
+    assert_close_rel(y, oracle.port.ewise_add(oracle.port.spmv(gp, 0, 0.0, 0, x), c))
+    # BFS step: y = mask-to-zero(A or.and x); distance[y != 0] = level
+    dist = np.zeros(2048, np.float32)
+    frontier = np.zeros(2048, np.float32)
+    seen = rng.choice(2048, 200, replace=False)
+    dist[seen] = 1
+    frontier[seen[:50]] = 1
+    A = capi.CsrMatrix(ctx, g)
+    dx, dd, dy = ctx.to_device(frontier), ctx.to_device(dist), ctx.zeros_f32(2048)
+    A.spmv(1, 0.0, 1, dx, dd, dy, Epilogue(0, 0.0, dd.ptr, 5.0, 2))
+    ref_y = oracle.port.spmv(g, 1, 0.0, 1, frontier, dist)
+    _, ref_d = oracle.port.assign_dense(ref_y, dist, 5.0, 2)
+    assert dy.read(np.float32, 2048).tobytes() == ref_y.tobytes()
+    assert dd.read(np.float32, 2048).tobytes() == ref_d.tobytes()
+
+
+def test_spmv_host_entry_point(ctx, oracle):
+    rng = np.random.default_rng(6)
+    m = datasets.uniform_csr(5000, 5000, 10, seed=2)
+    x, mask = rng.integers(0, 2, 5000).astype(np.float32), rng.integers(0, 2, 5000).astype(np.float32)
+    A = capi.CsrMatrix(ctx, m)
+    y = np.zeros(5000, np.float32)
+    A.spmv_host(0, 0.0, 2, x, mask, y)
+    assert_close_rel(y, oracle.port.spmv(m, 0, 0.0, 2, x, mask))
+
+
+def test_spmv_argument_errors(ctx):
+    m = datasets.eye(8)
+    A = capi.CsrMatrix(ctx, m)
+    d = ctx.zeros_f32(8)
+    e = ctx.zeros_f32(8)
+    with pytest.raises(capi.GlbError):
+        A.spmv(0, 0.0, 1, d, None, e)       # mask required
+    with pytest.raises(capi.GlbError):
+        A.spmv(0, 0.0, 0, d, None, d)       # y aliases x
+    with pytest.raises(capi.GlbError):
+        A.spmv(7, 0.0, 0, d, None, e)       # bad semiring
+    with pytest.raises(capi.GlbError):
+        capi.assign_dense(ctx, d, e, 8, 1.0, capi.MASK_NONE)   # assign_vector_dense_module.h:88-95
+
+
+# ---------------------------------------------------------------------------- SpMSpV
+def gpu_spmspv(ctx, csc, op, zero, mt, idx, val, mask, runs=1):
+    A = capi.CscMatrix(ctx, csc)
+    dx = ctx.to_device(capi.sparse_to_numpy(idx, val, csc.num_cols + 1))
+    dy = ctx.to_device(np.zeros(csc.num_rows + 1, capi.IDX_VAL))
+    dm = ctx.to_device(np.asarray(mask, np.float32)) if mask is not None else None
+    for _ in range(runs):
+        A.spmspv(op, zero, mt, dx, dm, dy)
+    head = dy.read(capi.IDX_VAL, 1)
+    oi, ov = dy.read_sparse()
+    assert len(np.unique(oi)) == len(oi)
+    assert head["val"][0] == np.float32(zero)           # head = {nnz, Zero}, kernel_spmspv_impl.h:551-555
+    assert capi.sparse_count(ctx, dy) == len(oi)
+    assert not (ov == np.float32(zero)).any()           # only entries != zero are listed
+    A.close()
+    return densify(oi, ov, csc.num_rows, zero)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+@pytest.mark.parametrize("mt", MASKS)
+def test_spmspv_golden_fixture(ctx, op, zero, mt):
+    z, m = golden(), golden_csr("spmspv_csc")
+    y = gpu_spmspv(ctx, m, op, zero, mt, z["spmspv_x_idx"], z["spmspv_x_val"], z[f"spmspv_mask_op{op}"])
+    check_vec(y, z[f"spmspv_y_op{op}_m{mt}"], op)
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmspv_sparsity_sweep_heavy_columns_and_reuse(ctx, oracle, op, zero):
+    # vector sparsity 0 / 0.5 / 0.99 as tests/test_module_spmv_spmspv.cpp:286-313; a power-law matrix
+    # has columns above the heavy-column threshold; runs=2 checks the accumulator is left clean
+    rng = np.random.default_rng(40 + op)
+    g = datasets.powerlaw_csr(1 << 14, 1 << 14, 1 << 19, seed=13, max_degree=1 << 13)
+    ip, ix, d = oracle.port.csr2csc(g)
+    csc = CSRMatrix(g.num_rows, g.num_cols, np.ones_like(d) if op else rng.random(len(d)).astype(np.float32), ix, ip)
+    assert np.diff(ip.astype(np.int64)).max() > 2048
+    n = g.num_cols
+    mask = np.where(rng.random(n) < 0.5, np.float32(zero), np.float32(1)).astype(np.float32)
+    for sparsity in (0.0, 0.5, 0.99):
+        k = max(1, int(n * (1 - sparsity)))
+        idx = (np.arange(k) * (n // k)).astype(np.uint32)
+        val = ((rng.integers(0, 10, k)) / 10).astype(np.float32)
+        for mt in MASKS:
+            y = gpu_spmspv(ctx, csc, op, zero, mt, idx, val, mask, runs=2)
+            check_vec(y, oracle.port.spmspv(csc, op, zero, mt, idx, val, mask), op)
+
+
+def test_spmspv_empty_frontier_and_rectangular(ctx, oracle):
+    rng = np.random.default_rng(50)
+    m = random_csr(rng, 70, 40, 0.2, values="small")           # as CSC: 40 rows, 70 columns
+    csc = CSRMatrix(40, 70, m.data, m.indices, m.indptr)
+    y = gpu_spmspv(ctx, csc, 0, 0.0, 0, [], [], None)
+    assert (y == 0).all()
+    idx = np.array([0, 69, 13], np.uint32)
+    val = np.array([1.0, 2.0, 0.5], np.float32)
+    check_vec(gpu_spmspv(ctx, csc, 2, 255.0, 0, idx, val, None), oracle.port.spmspv(csc, 2, 255.0, 0, idx, val, None), 2)
+
+
+# ----------------------------------------------------------------------------- apply
+def test_apply_golden_fixture(ctx):
+    z = golden()
+    n = len(z["apply_in"])
+    din, dout = ctx.to_device(z["apply_in"]), ctx.zeros_f32(n)
+    capi.ewise_add(ctx, din, dout, n, 0.25)
+    assert dout.read(np.float32, n).tobytes() == z["apply_ewise_add"].tobytes()
+    for mt in (1, 2):
+        dm, dio = ctx.to_device(z["apply_mask"]), ctx.to_device(z["apply_in"])
+        capi.assign_dense(ctx, dm, dio, n, 23.0, mt)
+        assert dio.read(np.float32, n).tobytes() == z[f"apply_assign_dense_m{mt}"].tobytes()
+    dl = ctx.to_device(capi.sparse_to_numpy(z["apply_sparse_idx"], z["apply_sparse_val"]))
+    dio = ctx.to_device(z["apply_in"])
+    capi.assign_sparse(ctx, dl, dio, 7.0)
+    assert dio.read(np.float32, n).tobytes() == z["apply_assign_sparse"].tobytes()
+    dio = ctx.to_device(z["apply_in"])
+    dnf = ctx.to_device(np.zeros(len(z["apply_sparse_idx"]) + 1, capi.IDX_VAL))
+    capi.assign_sparse_relax(ctx, dl, dio, dnf)
+    assert dio.read(np.float32, n).tobytes() == z["apply_relax_inout"].tobytes()
+    fi, fv = dnf.read_sparse()
+    order, ref_order = np.argsort(fi), np.argsort(z["apply_relax_idx"])
+    assert fi[order].tolist() == z["apply_relax_idx"][ref_order].tolist()      # same set, order unspecified
+    assert fv[order].tobytes() == z["apply_relax_val"][ref_order].tobytes()
+    assert dnf.read(capi.IDX_VAL, 1)["val"][0] == 0.0                           # head {count, 0}
+
+
+def test_apply_shapes_of_reference_tests(ctx, oracle):
+    # tests/test_module_apply.cpp: eWiseAdd len 128 (:54-75), dense assign val 23 (:78-103),
+    # unaligned / odd lengths, in-place eWiseAdd, device copy + aliasing (:209-261)
+    rng = np.random.default_rng(60)
+    for n in (1, 3, 128, 1000, 8192, 100003):
+        v = rng.random(n).astype(np.float32)
+        d = ctx.to_device(v)
+        capi.ewise_add(ctx, d, d, n, 1.5)
+        assert d.read(np.float32, n).tobytes() == oracle.port.ewise_add(v, 1.5).tobytes()
+    v = rng.random(4096).astype(np.float32)
+    a, b = ctx.to_device(v), ctx.zeros_f32(4096)
+    capi.d2d(ctx, b, a, 4096 * 4)
+    assert b.read(np.float32, 4096).tobytes() == v.tobytes()
+    lst = ctx.to_device(capi.sparse_to_numpy([3, 100, 4095], [1.0, 2.0, 3.0]))
+    dense = ctx.zeros_f32(4096)
+    capi.sparse_to_dense(ctx, lst, dense, 4096, 255.0)
+    ref = np.full(4096, 255.0, np.float32)
+    ref[[3, 100, 4095]] = [1, 2, 3]
+    assert dense.read(np.float32, 4096).tobytes() == ref.tobytes()
+    empty = ctx.to_device(capi.sparse_to_numpy([], []))
+    capi.assign_sparse(ctx, empty, dense, 9.0)
+    nf = ctx.to_device(np.zeros(4, capi.IDX_VAL))
+    capi.assign_sparse_relax(ctx, empty, dense, nf)
+    assert capi.sparse_count(ctx, nf) == 0 and dense.read(np.float32, 4096).tobytes() == ref.tobytes()

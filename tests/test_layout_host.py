@@ -1,0 +1,82 @@
+"""The warp-segment formatter (glb_csr_format_host, the counterpart of the reference's csr2cpsr,
+data_formatter.h:457-534) checked on the CPU: a sequential model of the kernel schedule
+(tests/layout_model.py) run over the produced arrays must reproduce the oracle's SpMV."""
+import numpy as np
+import pytest
+
+from graphlily_b200 import capi, datasets, io
+from layout_model import FLAG, run_model
+from util import SEMIRINGS, random_csr
+
+
+def check(oracle, m, rb=0, re=None, seed=0):
+    rng = np.random.default_rng(seed)
+    re = m.num_rows if re is None else re
+    L = capi.format_host(m, rb, re)
+    assert L["nnz"] == int(m.indptr[re]) - int(m.indptr[rb])
+    assert L["n_chunks"] == -(-L["nnz"] // L["chunk"])
+    # invariants: one flag per non-empty row that does not start a chunk; none at chunk starts
+    starts = m.indptr[rb:re][np.diff(m.indptr[rb:re + 1].astype(np.int64)) > 0].astype(np.int64) - int(m.indptr[rb])
+    flags = np.nonzero(L["cols"] & FLAG)[0]
+    assert sorted(flags.tolist()) == sorted(s for s in starts.tolist() if s % L["chunk"] != 0)
+    assert len(L["nz_rows"]) + len(L["empty_rows"]) == re - rb
+    for op, zero in SEMIRINGS:
+        x = rng.integers(0, 2, m.num_cols).astype(np.float32) if op != 2 else rng.integers(0, 5, m.num_cols).astype(np.float32)
+        y, written = run_model(L, m.data, x, op, zero, m.num_rows, int(m.indptr[rb]))
+        ref = oracle.port.spmv(m, op, zero, 0, x)
+        assert (written[rb:re] == 1).all() and written[:rb].sum() == 0 and written[re:].sum() == 0
+        if op == 0:
+            assert np.allclose(y[rb:re], ref[rb:re], rtol=1e-5, atol=1e-7)
+        else:
+            assert np.array_equal(y[rb:re], ref[rb:re])
+    return L
+
+
+def test_powerlaw_and_shards(oracle):
+    rng = np.random.default_rng(1)
+    m = datasets.powerlaw_csr(3000, 3000, 60000, seed=5, max_degree=5000)
+    m.data = rng.random(m.nnz).astype(np.float32)
+    L = check(oracle, m)
+    assert L["n_chunks"] == 59 and len(L["fixups"]) <= L["n_chunks"]
+    check(oracle, m, 1000, 2000)
+    check(oracle, m, 0, 1)
+    check(oracle, m, 2999, 3000)
+    check(oracle, m, 1500, 1500)   # empty shard
+
+
+def test_boundary_cases(oracle):
+    # rows that are exactly one chunk, span several, end on a boundary, or are empty
+    rng = np.random.default_rng(2)
+    ip = [0]
+    for d in [1024, 0, 0, 2048, 1, 1023, 5000, 0, 1024, 3, 0]:
+        ip.append(ip[-1] + d)
+    nnz = ip[-1]
+    m = io.CSRMatrix(len(ip) - 1, 7000, rng.random(nnz).astype(np.float32),
+                     rng.integers(0, 7000, nnz).astype(np.uint32), np.array(ip, np.uint32))
+    L = check(oracle, m)
+    assert L["empty_rows"].tolist() == [1, 2, 7, 10]
+    for a, b in [(0, 3), (3, 4), (1, 2), (4, 11), (6, 7)]:
+        check(oracle, m, a, b)
+    one_long = io.CSRMatrix(1, 50, np.ones(40000, np.float32), rng.integers(0, 50, 40000).astype(np.uint32),
+                            np.array([0, 40000], np.uint32))
+    L = check(oracle, one_long)
+    assert len(L["fixups"]) == 1 and L["fixups"][0].tolist() == [0, 0, 39]
+
+
+def test_empty_and_tiny(oracle):
+    check(oracle, io.CSRMatrix(5, 5, np.zeros(0, np.float32), np.zeros(0, np.uint32), np.zeros(6, np.uint32)))
+    check(oracle, datasets.eye(10))
+    check(oracle, datasets.line_graph(8))
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 31, 33, 1025):
+        check(oracle, random_csr(rng, n, n + 3, 0.3), seed=n)
+
+
+def test_invalid_inputs_rejected():
+    m = datasets.eye(4)
+    bad = io.CSRMatrix(4, 4, m.data, np.array([0, 1, 2, 9], np.uint32), m.indptr)
+    with pytest.raises(capi.GlbError):
+        capi.format_host(bad)
+    bad2 = io.CSRMatrix(4, 4, m.data, m.indices, np.array([0, 2, 1, 3, 4], np.uint32))
+    with pytest.raises(capi.GlbError):
+        capi.format_host(bad2)
