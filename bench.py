@@ -197,7 +197,10 @@ def main():
     slot = n // world
     rb, re = rank * slot, (rank + 1) * slot
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the C ABI, so torch.cuda.Event brackets our kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = capi.Context(local_rank, stream.cuda_stream)
     t0 = time.time()
     A = capi.CsrMatrix(ctx, m, rb, re)
