@@ -81,6 +81,11 @@ struct glb_csr_s {
     glb_fixup_t *fix_long = nullptr;   // longer spans: one warp each
     uint32_t *empty_rows = nullptr;
     float *head_carry = nullptr, *tail_carry = nullptr;  // per chunk
+    // column relabelling (formatter option): cols[] hold popularity ranks, col_perm[rank] = column
+    uint32_t *col_perm = nullptr;  // padded to a multiple of 4 entries
+    float *xp = nullptr;           // x in relabelled order, rebuilt by every SpMV launch
+    uint32_t tile_k = 0;           // hot columns staged in shared memory by the tile kernel
+    uint32_t tile_threads = 1024;
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
     size_t device_bytes = 0;

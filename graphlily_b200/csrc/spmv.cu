@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "glb_internal.h"
@@ -39,7 +40,7 @@ struct SpmvParams {
     const float *__restrict__ vals;
     const uint32_t *__restrict__ nz_rows;
     const uint32_t *__restrict__ chunk_first;
-    const float *__restrict__ x;
+    const float *__restrict__ x;   // gather source: the caller's x, or its relabelled copy xp
     const float *mask;  // may alias assign_inout
     float *y;
     float *head_carry;
@@ -58,6 +59,7 @@ struct SpmvParams {
     const glb_fixup_t *fix_long;
     const uint32_t *empty_rows;
     uint32_t n_fix_short, n_fix_long, n_empty;
+    uint32_t tile_k;  // columns [0, tile_k) of the relabelled x live in shared memory (0 = none)
 };
 
 // Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
@@ -78,14 +80,11 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
     }
 }
 
-template <int OP>
-__global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
-    __shared__ float stage[kWarpsPerBlock][kStep];
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned wib = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
-
+// One chunk (GLB_CHUNK non-zeros) by one warp.  TILE: columns below P.tile_k are read from the
+// shared-memory copy of the hot end of the relabelled vector, the rest through L1/L2.
+template <int OP, bool TILE>
+__device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
+                                              float *my_stage, const float *tile) {
     const uint32_t cf = P.chunk_first[chunk];
     const uint32_t ord0 = cf & ~GLB_FLAG;
     const bool fresh = (cf & GLB_FLAG) != 0;
@@ -95,7 +94,6 @@ __global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
 
     uint32_t ord_base = ord0;  // ordinal of the row open at the start of the step
     float wcarry = Semi<OP>::ident();
-    float *my_stage = stage[wib];
 
 #pragma unroll 2
     for (int it = 0; it < int(GLB_CHUNK / kStep); ++it) {
@@ -113,7 +111,10 @@ __global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             f[j] = (c[j] & GLB_FLAG) != 0;
-            const float xv = __ldg(P.x + (c[j] & ~GLB_FLAG));
+            const uint32_t col = c[j] & ~GLB_FLAG;
+            float xv;
+            if (TILE) xv = (col < P.tile_k) ? tile[col] : __ldg(P.x + col);
+            else xv = __ldg(P.x + col);
             prod[j] = (j < rem) ? Semi<OP>::mul(a[j], xv) : Semi<OP>::ident();
         }
 
@@ -176,6 +177,92 @@ __global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
     if (lane == 0) P.tail_carry[chunk] = wcarry;
 }
 
+// Variant A: one chunk per warp, x gathered through L1/L2 only.
+template <int OP>
+__global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
+    __shared__ float stage[kWarpsPerBlock][kStep];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
+    if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
+    process_chunk<OP, false>(P, chunk, lane, stage[wib], nullptr);
+}
+
+// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!done);
+}
+
+// Variant B: persistent CTAs, one per SM.  Each CTA pulls the hot end of the relabelled vector
+// (columns [0, tile_k), the most referenced ones) into shared memory with TMA bulk copies
+// once, then its warps walk the chunk list; hot gathers become bank-parallel LDS instead of
+// one L1 wavefront + one 32-byte L2 sector per lane.
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) spmv_ws_tile_kernel(const SpmvParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    const unsigned n_warps = blockDim.x >> 5;
+    float *stage = tile + P.tile_k;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + n_warps * kStep);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = P.tile_k * 4u;
+        mbar_expect_tx(bar, bytes);
+        constexpr uint32_t kPiece = 32768;
+        for (uint32_t off = 0; off < bytes; off += kPiece) {
+            const uint32_t nb = (bytes - off < kPiece) ? (bytes - off) : kPiece;
+            bulk_g2s(reinterpret_cast<unsigned char *>(tile) + off, reinterpret_cast<const unsigned char *>(P.x) + off,
+                     nb, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    const uint32_t total_warps = gridDim.x * n_warps;
+    for (uint32_t chunk = blockIdx.x * n_warps + wib; chunk < P.n_chunks; chunk += total_warps)
+        process_chunk<OP, true>(P, chunk, lane, stage + wib * kStep, tile);
+}
+
+// xp[i] = x[perm[i]]: the caller's vector in the matrix's relabelled column order.
+__global__ void __launch_bounds__(kThreads) permute_x_kernel(const float *__restrict__ x,
+                                                           const uint32_t *__restrict__ perm, float *__restrict__ xp,
+                                                           uint32_t n4) {
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(perm) + i);
+        float4 o;
+        o.x = __ldg(x + q.x);
+        o.y = __ldg(x + q.y);
+        o.z = __ldg(x + q.z);
+        o.w = __ldg(x + q.w);
+        reinterpret_cast<float4 *>(xp)[i] = o;
+    }
+}
+
 // Rows touching a chunk boundary: total = tail[c_begin .. c_last] (+) head[c_end].
 template <int OP>
 __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P, uint32_t nb_short, uint32_t nb_long) {
@@ -214,13 +301,24 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
 }
 
 template <int OP>
-int launch_op(glb_ctx_t ctx, const SpmvParams &P) {
+int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (ctx->timing) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
         GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
     }
-    if (P.n_chunks) {
+    if (P.n_chunks && P.tile_k) {
+        const uint32_t n_warps = m->tile_threads / 32;
+        const size_t smem = size_t(P.tile_k) * 4 + size_t(n_warps) * kStep * 4 + 16;
+        static thread_local size_t attr_set[3] = {0, 0, 0};
+        if (attr_set[OP] < smem) {
+            GLB_CUDA(cudaFuncSetAttribute(spmv_ws_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            attr_set[OP] = smem;
+        }
+        uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
+        if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
+        spmv_ws_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
+    } else if (P.n_chunks) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
         spmv_ws_kernel<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
     }
@@ -264,6 +362,15 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.nz_rows = m->nz_rows;
     P.chunk_first = m->chunk_first;
     P.x = x;
+    if (m->col_perm) {  // relabelled columns: gather from the permuted copy of x
+        const uint32_t n4 = (m->num_cols + 3) / 4;
+        uint32_t blocks = (n4 + kThreads - 1) / kThreads;
+        const uint32_t cap = uint32_t(ctx->num_sms) * 8;
+        if (blocks > cap) blocks = cap;
+        permute_x_kernel<<<blocks, kThreads, 0, ctx->stream>>>(x, m->col_perm, m->xp, n4);
+        P.x = m->xp;
+    }
+    P.tile_k = m->tile_k;
     P.mask = mask;
     P.y = y;
     P.head_carry = m->head_carry;
@@ -286,9 +393,9 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
     switch (op) {
-        case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, P);
-        case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, P);
-        case GLB_OP_ADD_MIN: return launch_op<GLB_OP_ADD_MIN>(ctx, P);
+        case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, m, P);
+        case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);
+        case GLB_OP_ADD_MIN: return launch_op<GLB_OP_ADD_MIN>(ctx, m, P);
     }
     glb_set_error("glb_spmv: invalid semiring op %d", op);
     return GLB_EINVAL;
@@ -298,6 +405,7 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
 // the host-only glb_csr_format_host (which lets the layout be checked without a GPU).
 struct HostLayout {
     uint32_t *cols = nullptr;  // malloc'd, nnz entries (padding is added on the device)
+    std::vector<uint32_t> col_perm;  // relabelled column -> original column (empty = identity)
     std::vector<uint32_t> nz_rows, empty_rows, chunk_first;
     std::vector<glb_fixup_t> fix_short, fix_long;
     uint64_t nnz = 0, sb = 0;
@@ -306,7 +414,7 @@ struct HostLayout {
 };
 
 static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
-                       uint32_t row_begin, uint32_t row_end, HostLayout &L) {
+                       uint32_t row_begin, uint32_t row_end, HostLayout &L, bool relabel = false) {
     GLB_REQUIRE(indptr, "NULL indptr");
     GLB_REQUIRE(row_begin <= row_end && row_end <= num_rows, "bad row range");
     GLB_REQUIRE(num_cols >= 1 && num_cols < GLB_FLAG, "num_cols must be in [1, 2^31)");
@@ -326,6 +434,20 @@ static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *ind
                           (unsigned long long)(sb + i));
             return GLB_EINVAL;
         }
+    }
+    if (relabel && nnz) {
+        // Columns renumbered by descending reference count inside this shard (ties by id): the hot
+        // end of the vector becomes one contiguous block -- a TMA-loadable shared-memory tile -- and
+        // equally warm columns share 32-byte sectors.  col_perm[new] = old.
+        std::vector<uint32_t> count(num_cols, 0);
+        for (uint64_t i = 0; i < nnz; ++i) count[L.cols[i]]++;
+        L.col_perm.resize(num_cols);
+        for (uint32_t c = 0; c < num_cols; ++c) L.col_perm[c] = c;
+        std::stable_sort(L.col_perm.begin(), L.col_perm.end(),
+                         [&](uint32_t a, uint32_t b) { return count[a] > count[b]; });
+        std::vector<uint32_t> &rank = count;  // reuse: rank[old] = new
+        for (uint32_t n = 0; n < num_cols; ++n) rank[L.col_perm[n]] = n;
+        for (uint64_t i = 0; i < nnz; ++i) L.cols[i] = rank[L.cols[i]];
     }
     L.chunk_first.assign(L.n_chunks, 0);
     L.nz_rows.reserve(row_end - row_begin);
@@ -396,8 +518,26 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
                    const float *data, uint32_t row_begin, uint32_t row_end, glb_csr_t *out) {
     GLB_REQUIRE(ctx && out, "NULL argument");
     *out = nullptr;
+    // Tuning knobs (defaults chosen by measurement on B200):
+    //   GLB_SPMV_RELABEL=0|1       renumber columns by popularity (needs one x-permute pass per SpMV)
+    //   GLB_SPMV_TILE_K=<floats>   hot columns kept in shared memory (0 = gather everything via L1/L2)
+    //   GLB_SPMV_TILE_THREADS=<n>  threads of the persistent tile kernel
+    auto env_u32 = [](const char *name, uint32_t dflt) {
+        const char *v = getenv(name);
+        return v ? uint32_t(strtoul(v, nullptr, 10)) : dflt;
+    };
+    const bool relabel = env_u32("GLB_SPMV_RELABEL", 1) != 0 && num_cols >= 4096;
+    uint32_t tile_k = relabel ? env_u32("GLB_SPMV_TILE_K", 49152) : 0;
+    uint32_t tile_threads = env_u32("GLB_SPMV_TILE_THREADS", 1024);
+    if (tile_threads < 32 || tile_threads > 1024 || tile_threads % 32) tile_threads = 1024;
+    const uint32_t cols_pad = (num_cols + 3u) & ~3u;
+    if (tile_k > cols_pad) tile_k = cols_pad;
+    tile_k &= ~3u;
+    if (size_t(tile_k) * 4 + size_t(tile_threads / 32) * kStep * 4 + 16 > 227 * 1024)
+        tile_k = uint32_t((227 * 1024 - size_t(tile_threads / 32) * kStep * 4 - 16) / 4) & ~3u;
+
     HostLayout L;
-    int rc = format_host(num_rows, num_cols, indptr, indices, row_begin, row_end, L);
+    int rc = format_host(num_rows, num_cols, indptr, indices, row_begin, row_end, L, relabel);
     if (rc) return rc;
     const uint64_t nnz = L.nnz, sb = L.sb;
     GLB_REQUIRE(nnz == 0 || data, "NULL data");
@@ -426,6 +566,12 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     if (!rc) rc = upload(ctx, &m->fix_short, L.fix_short.data(), L.fix_short.size(), L.fix_short.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->fix_long, L.fix_long.data(), L.fix_long.size(), L.fix_long.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->empty_rows, L.empty_rows.data(), L.empty_rows.size(), L.empty_rows.size(), &bytes);
+    if (!rc && !L.col_perm.empty()) {
+        rc = upload(ctx, &m->col_perm, L.col_perm.data(), L.col_perm.size(), size_t(cols_pad), &bytes);
+        if (!rc) rc = upload<float>(ctx, &m->xp, nullptr, 0, size_t(cols_pad), &bytes);
+        m->tile_k = tile_k;
+        m->tile_threads = tile_threads;
+    }
     if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, n_chunks, &bytes);
     if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, n_chunks, &bytes);
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -444,7 +590,7 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->cols); cudaFree(m->vals); cudaFree(m->nz_rows); cudaFree(m->chunk_first);
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
-    cudaFree(m->head_carry); cudaFree(m->tail_carry);
+    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->col_perm); cudaFree(m->xp);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
     delete m;
     return GLB_OK;
