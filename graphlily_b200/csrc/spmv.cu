@@ -527,7 +527,7 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
         return v ? uint32_t(strtoul(v, nullptr, 10)) : dflt;
     };
     const bool relabel = env_u32("GLB_SPMV_RELABEL", 1) != 0 && num_cols >= 4096;
-    uint32_t tile_k = relabel ? env_u32("GLB_SPMV_TILE_K", 49152) : 0;
+    uint32_t tile_k = relabel ? env_u32("GLB_SPMV_TILE_K", 0) : 0;  // measured: the 1-CTA/SM tile kernel loses (profiles/r1_sweep_v1.txt)
     uint32_t tile_threads = env_u32("GLB_SPMV_TILE_THREADS", 1024);
     if (tile_threads < 32 || tile_threads > 1024 || tile_threads % 32) tile_threads = 1024;
     const uint32_t cols_pad = (num_cols + 3u) & ~3u;
