@@ -34,9 +34,11 @@ class Epilogue(C.Structure):
 
 class HostLayout(C.Structure):
     """glb_host_layout_t"""
-    _fields_ = [("chunk", C.c_uint32), ("nnz", C.c_uint64), ("n_chunks", C.c_uint32), ("n_nz_rows", C.c_uint32),
-                ("n_empty", C.c_uint32), ("n_fixups", C.c_uint32), ("cols", _u32p), ("nz_rows", _u32p),
-                ("empty_rows", _u32p), ("chunk_first", _u32p), ("fixups", _u32p)]
+    _fields_ = [("group", C.c_uint32), ("max_groups", C.c_uint32), ("row_cap", C.c_uint32), ("nnz", C.c_uint64),
+                ("n_chunks", C.c_uint32), ("n_groups", C.c_uint32), ("n_nz_rows", C.c_uint32), ("n_empty", C.c_uint32),
+                ("n_fixups", C.c_uint32), ("tile_k", C.c_uint32), ("n_hot", C.c_uint32),
+                ("stream", _u32p), ("flags", _u32p), ("chunk_goff", _u32p), ("chunk_first", _u32p),
+                ("nz_rows", _u32p), ("empty_rows", _u32p), ("fixups", _u32p), ("hot_cols", _u32p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/graphlily_b200.h declares.
@@ -63,7 +65,8 @@ SIGNATURES = {
     "glb_csr_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "glb_csr_destroy": (C.c_int, [_vp]),
     "glb_csr_info": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
-    "glb_csr_format_host": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(HostLayout)]),
+    "glb_csr_format_host": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.POINTER(HostLayout)]),
     "glb_host_layout_free": (C.c_int, [C.POINTER(HostLayout)]),
     "glb_csc_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
     "glb_csc_destroy": (C.c_int, [_vp]),
@@ -228,7 +231,7 @@ def sparse_to_numpy(idx, val, capacity=None):
 
 
 class CsrMatrix:
-    """Device-resident CSR row shard in warp-segment layout (glb_csr_t)."""
+    """Device-resident CSR row shard in lane-segment layout (glb_csr_t)."""
 
     def __init__(self, ctx, m, row_begin=0, row_end=None):
         row_end = int(m.num_rows) if row_end is None else row_end
@@ -245,7 +248,7 @@ class CsrMatrix:
     def info(self):
         a = (C.c_uint64 * 8)()
         check(lib.glb_csr_info(self.handle, a))
-        keys = ("rows", "cols", "nnz", "chunks", "fixups", "empty_rows", "device_bytes", "chunk_nnz")
+        keys = ("rows", "cols", "nnz", "chunks", "fixups", "empty_rows", "device_bytes", "tile_k")
         return dict(zip(keys, (int(v) for v in a)))
 
     def spmv(self, op, zero, mask_type, x, mask, y, epilogue=None):
@@ -329,19 +332,23 @@ def d2d(ctx, dst, src, nbytes):
     check(lib.glb_buffer_d2d(ctx.handle, _ptr(dst), _ptr(src), nbytes))
 
 
-def format_host(m, row_begin=0, row_end=None):
-    """Host-only view of the warp-segment layout (no GPU needed); returns a dict of numpy arrays."""
+def format_host(m, row_begin=0, row_end=None, tile_k=0, with_data=True):
+    """Host-only view of the lane-segment layout (no GPU needed); returns a dict of numpy arrays."""
     row_end = int(m.num_rows) if row_end is None else row_end
     ip, ix = np.ascontiguousarray(m.indptr, np.uint32), np.ascontiguousarray(m.indices, np.uint32)
+    d = np.ascontiguousarray(m.data, np.float32) if with_data else None
     L = HostLayout()
-    check(lib.glb_csr_format_host(int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data, row_begin, row_end,
-                                  C.byref(L)))
+    check(lib.glb_csr_format_host(int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data,
+                                  d.ctypes.data if d is not None else None, row_begin, row_end, int(tile_k), C.byref(L)))
 
     def arr(p, n):
         return np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
 
-    out = dict(chunk=L.chunk, nnz=int(L.nnz), n_chunks=L.n_chunks, cols=arr(L.cols, int(L.nnz)),
-               nz_rows=arr(L.nz_rows, L.n_nz_rows), empty_rows=arr(L.empty_rows, L.n_empty),
-               chunk_first=arr(L.chunk_first, L.n_chunks), fixups=arr(L.fixups, 3 * L.n_fixups).reshape(-1, 3))
+    out = dict(group=L.group, max_groups=L.max_groups, row_cap=L.row_cap, nnz=int(L.nnz), n_chunks=L.n_chunks,
+               n_groups=L.n_groups, tile_k=L.tile_k, stream=arr(L.stream, 256 * L.n_groups),
+               flags=arr(L.flags, 32 * L.n_chunks).reshape(-1, 32), chunk_goff=arr(L.chunk_goff, L.n_chunks + 1),
+               chunk_first=arr(L.chunk_first, L.n_chunks), nz_rows=arr(L.nz_rows, L.n_nz_rows),
+               empty_rows=arr(L.empty_rows, L.n_empty), fixups=arr(L.fixups, 3 * L.n_fixups).reshape(-1, 3),
+               hot_cols=arr(L.hot_cols, L.n_hot))
     lib.glb_host_layout_free(C.byref(L))
     return out

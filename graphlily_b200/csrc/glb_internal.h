@@ -43,20 +43,29 @@ struct glb_ctx_s {
     std::vector<cudaEvent_t> timing_events;  // 3 per launch: before main, after main, after fix-up
 };
 
-// ---------------------------------------------------------------- warp-segment CSR (SpMV)
+// ---------------------------------------------------------------- lane-segment CSR (SpMV)
 //
-// The nnz stream of the row shard is cut into fixed chunks of GLB_CHUNK non-zeros; one warp
-// owns one chunk and reads it with 128-bit loads, four consecutive non-zeros per lane.
-//   cols[p]  bit31 = "p is the first non-zero of its row" (cleared at chunk position 0,
-//            where chunk_first carries the information instead); bits 0..30 = column
-//   vals[p]  fp32 value
-//   nz_rows[k]      row id of the k-th non-empty row of the shard
-//   chunk_first[c]  ordinal k of the row holding the chunk's first non-zero,
-//                   bit31 = that row starts exactly at the chunk start
-// Rows that cross a chunk boundary (or end exactly on one) are finished by the fix-up
-// kernel from per-chunk carries: see spmv.cu.
-#define GLB_CHUNK 1024u
+// The nnz stream of the row shard is cut into chunks of up to GLB_MAX_GROUPS groups of GLB_GROUP
+// non-zeros; one warp owns one chunk.  In a chunk of n groups lane l owns the 4n consecutive
+// non-zeros [4n*l, 4n*(l+1)) (positions past the chunk's real length are padding); storage is
+// transposed so that group g holds elements 4g..4g+3 of every lane:
+//   stream[256*G + 4*l + e]        encoded column of element 4g+e of lane l   (G = chunk_goff[c] + g)
+//   stream[256*G + 128 + 4*l + e]  its fp32 value
+//   encoded column                 rank (< tile_k) of a hot column in hot_cols, else tile_k + column
+//   flags[32*c + l]                bit r = "element r of lane l starts a row" (never set for the chunk's
+//                                  first non-zero; the first padding element, if any, is flagged)
+//   chunk_goff[c]                  first group of chunk c (n_chunks + 1 entries)
+//   chunk_first[c]                 ordinal k into nz_rows of the row open at the chunk start,
+//                                  bit31 = that row starts exactly there
+//   nz_rows[k]                     row id of the k-th non-empty row of the shard
+// A chunk holds at most GLB_ROW_CAP flags.  Rows that cross a chunk boundary (or end exactly on
+// one) are finished by the fix-up kernel from per-chunk carries: see spmv.cu.
+#define GLB_GROUP 128u
+#define GLB_MAX_GROUPS 8
+#define GLB_ROW_CAP 256u
 #define GLB_FLAG 0x80000000u
+#define GLB_DEFAULT_TILE_K 40960u
+#define GLB_DEFAULT_CARVEOUT_PCT 20u
 
 struct glb_fixup_t {
     uint32_t row;    // global row id
@@ -69,23 +78,25 @@ struct glb_csr_s {
     uint32_t num_rows = 0, num_cols = 0;  // global dims
     uint32_t row_begin = 0, row_end = 0;  // shard
     uint64_t nnz = 0;                     // in shard
-    uint32_t n_chunks = 0;
+    uint32_t n_chunks = 0, n_groups = 0;
     uint32_t n_nz_rows = 0;
     uint32_t n_fix_short = 0, n_fix_long = 0, n_empty = 0;
     // device arrays
-    uint32_t *cols = nullptr;
-    float *vals = nullptr;
-    uint32_t *nz_rows = nullptr;
+    uint32_t *stream = nullptr;
+    uint32_t *flags = nullptr;
+    uint32_t *chunk_goff = nullptr;
     uint32_t *chunk_first = nullptr;
+    uint32_t *nz_rows = nullptr;
     glb_fixup_t *fix_short = nullptr;  // span <= 32 chunks: one thread each
     glb_fixup_t *fix_long = nullptr;   // longer spans: one warp each
     uint32_t *empty_rows = nullptr;
     float *head_carry = nullptr, *tail_carry = nullptr;  // per chunk
-    // column relabelling (formatter option): cols[] hold popularity ranks, col_perm[rank] = column
-    uint32_t *col_perm = nullptr;  // padded to a multiple of 4 entries
-    float *xp = nullptr;           // x in relabelled order, rebuilt by every SpMV launch
-    uint32_t tile_k = 0;           // hot columns staged in shared memory by the tile kernel
-    uint32_t tile_threads = 1024;
+    // hot columns: the tile_k most referenced columns of the shard, renumbered 0 .. tile_k-1
+    uint32_t tile_k = 0;           // encoded columns below it are hot
+    uint32_t n_hot = 0;            // entries of hot_cols (0 when tile_k == 0 or tile_k == num_cols: identity)
+    uint32_t *hot_cols = nullptr;  // rank -> column
+    float *hot_x = nullptr;        // x[hot_cols[.]], rebuilt by every SpMV launch
+    int smem_carveout_pct = 20;
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
     size_t device_bytes = 0;

@@ -1,28 +1,46 @@
-// SpMV: y = A (+).(x) x over a row shard in warp-segment layout (overlay mode 1).
+// SpMV: y = A (+).(x) x over a row shard in lane-segment layout (overlay mode 1).
 //
 // Replaces kernel_spmv (/root/reference/graphlily/hw/kernel_spmv_impl.h:392-819) and the
 // CPSR formatter that feeds it (graphlily/io/data_formatter.h:457-534).  Semantics are those of
 // SpMVModule::compute_reference_results (graphlily/module/spmv_module.h:478-532).
 //
-// Layout and schedule (see glb_internal.h for the arrays):
-//   * the shard's nnz stream is cut into chunks of GLB_CHUNK = 1024 non-zeros, one warp each --
-//     perfect nnz balance whatever the row-length distribution (power-law rows of 1 .. 2^20);
-//   * per step a warp streams 128 non-zeros: lane l loads cols/vals [4l, 4l+4) with one
-//     128-bit streaming load each (fully coalesced 512-B rows), gathers x, multiplies;
-//   * row boundaries travel in bit 31 of the column word; a ballot/popc prefix gives every
-//     row end its ordinal, a 5-step shuffle segmented scan gives the carry into each lane;
-//   * finished rows are staged in shared memory by ordinal and written back by consecutive
-//     lanes (coalesced mask reads / y writes), with the mask and the fused eWiseAdd / dense
-//     assign epilogues applied in the same pass;
+// What bounds this kernel on B200 (tools/gather_bench.cu, profiles/r1_gather_microbench*.txt):
+// a 4-byte gather that misses L1 costs one L1 miss request = one 32-byte L2 sector, and an SM
+// sustains ~1.0 of those per clock whatever the path (ld / ld.cg / texture): 128 M random
+// gathers take 464 us, 2.7x the 172 us the 1.12 GB of matrix stream needs from HBM.  Gathers
+// that HIT L1 run 3x faster.  So the layout is built around keeping the gathers out of L2:
+//
+//   * hot columns: the formatter ranks the columns of the shard by reference count; the
+//     tile_k most referenced ones are renumbered 0..tile_k-1 and every SpMV first packs their x
+//     values into one contiguous `hot_x` array (a 200 KB gather) that the main kernel reads
+//     with L1-allocating loads, so it stays L1-resident in every SM; all other columns keep
+//     their id (stored as tile_k + column) and are read with ld.global.nc.L1::no_allocate, as
+//     is the matrix stream, so they never evict the hot lines;
+//   * lane-segment chunks: the nnz stream is cut into chunks of up to 8 groups of 128
+//     non-zeros, one warp per chunk.  Inside a chunk lane l owns the 4n CONSECUTIVE non-zeros
+//     [4n*l, 4n*(l+1)) and storage is transposed so that every load is still a coalesced
+//     128-bit access (group g holds elements 4g..4g+3 of all 32 lanes: 512 B of column words
+//     followed by 512 B of values).  A lane therefore reduces its run serially in registers --
+//     no per-element shuffles or ballots -- and row boundaries come from one 32-bit flag word
+//     per lane.  Row sums that close inside a lane go straight to a per-warp staging array in
+//     shared memory indexed by row ordinal; one segmented shuffle scan per CHUNK (not per 128
+//     non-zeros) stitches rows that cross lanes; then consecutive lanes write consecutive rows
+//     (coalesced mask reads / y writes) with the mask and the fused eWiseAdd / dense-assign
+//     epilogues applied in the same pass;
+//   * a chunk never holds more than GLB_ROW_CAP row ends (the formatter cuts it early at a
+//     row boundary and pads the last group; padding is flagged as a row of its own whose sum
+//     is discarded), so the staging array is bounded;
 //   * rows that cross or touch a chunk boundary leave per-chunk head / tail carries that the
 //     fix-up kernel combines (deterministic -- no float atomics); it also writes empty rows.
 //
 // Algorithmic HBM bytes per launch: 8*nnz (cols+vals) + 4*nonempty_rows (nz_rows) + 4*ncols (x)
-// + 4*rows (y) [+ 4*rows mask], i.e. the CSR figure of SURVEY.md section 8d.
+// + 4*rows (y) [+ 4*rows mask], i.e. the CSR figure of SURVEY.md section 8d; the flag words add
+// 4 bytes per 32 non-zeros (1.6 %).
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "glb_internal.h"
@@ -32,21 +50,23 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kStep = 128;  // non-zeros per warp step
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPrefetch = 2;  // groups of the matrix stream in flight ahead of the one being reduced
 
 struct SpmvParams {
-    const uint32_t *__restrict__ cols;
-    const float *__restrict__ vals;
+    const uint32_t *__restrict__ stream;       // 256 words per group: 128 encoded columns, 128 fp32 values
+    const uint32_t *__restrict__ flags;        // 32 per chunk: bit r of word l = "element r of lane l starts a row"
+    const uint32_t *__restrict__ chunk_goff;   // n_chunks + 1: first group of every chunk
+    const uint32_t *__restrict__ chunk_first;  // ordinal of the row open at the chunk start | GLB_FLAG if it starts there
     const uint32_t *__restrict__ nz_rows;
-    const uint32_t *__restrict__ chunk_first;
-    const float *__restrict__ x;   // gather source: the caller's x, or its relabelled copy xp
-    const float *mask;  // may alias assign_inout
+    const float *hot_x;   // x values of the hot columns, packed (or x itself when every column is hot)
+    const float *x_cold;  // x - tile_k: cold column words index it directly
+    const float *mask;    // may alias assign_inout
     float *y;
     float *head_carry;
     float *tail_carry;
-    uint64_t nnz;
     uint32_t n_chunks;
+    uint32_t tile_k;
     float zero;
     int mask_type;
     int add_enable;
@@ -59,7 +79,6 @@ struct SpmvParams {
     const glb_fixup_t *fix_long;
     const uint32_t *empty_rows;
     uint32_t n_fix_short, n_fix_long, n_empty;
-    uint32_t tile_k;  // columns [0, tile_k) of the relabelled x live in shared memory (0 = none)
 };
 
 // Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
@@ -80,187 +99,136 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
     }
 }
 
-// One chunk (GLB_CHUNK non-zeros) by one warp.  TILE: columns below P.tile_k are read from the
-// shared-memory copy of the hot end of the relabelled vector, the rest through L1/L2.
-template <int OP, bool TILE>
-__device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
-                                              float *my_stage, const float *tile) {
-    const uint32_t cf = P.chunk_first[chunk];
-    const uint32_t ord0 = cf & ~GLB_FLAG;
-    const bool fresh = (cf & GLB_FLAG) != 0;
-    const uint64_t base = uint64_t(chunk) * GLB_CHUNK;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned le_mask = lt_mask | (1u << lane);
-
-    uint32_t ord_base = ord0;  // ordinal of the row open at the start of the step
-    float wcarry = Semi<OP>::ident();
-
-#pragma unroll 2
-    for (int it = 0; it < int(GLB_CHUNK / kStep); ++it) {
-        const uint64_t p = base + uint64_t(it) * kStep + lane * 4u;
-        const uint4 c4 = __ldcs(reinterpret_cast<const uint4 *>(P.cols + p));
-        const float4 a4 = __ldcs(reinterpret_cast<const float4 *>(P.vals + p));
-        const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        // padding beyond nnz (last chunk only) contributes the identity
-        const uint64_t left = (P.nnz > p) ? (P.nnz - p) : 0;
-        const int rem = left > 4 ? 4 : int(left);
-
-        bool f[4];
-        float prod[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            f[j] = (c[j] & GLB_FLAG) != 0;
-            const uint32_t col = c[j] & ~GLB_FLAG;
-            float xv;
-            if (TILE) xv = (col < P.tile_k) ? tile[col] : __ldg(P.x + col);
-            else xv = __ldg(P.x + col);
-            prod[j] = (j < rem) ? Semi<OP>::mul(a[j], xv) : Semi<OP>::ident();
-        }
-
-        // pass 1: value of the lane's open tail segment, flag census
-        float tail = Semi<OP>::ident();
-        bool hasf = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (f[j]) { tail = Semi<OP>::ident(); hasf = true; }
-            tail = Semi<OP>::add(tail, prod[j]);
-        }
-        unsigned excl = 0, total = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned b = __ballot_sync(kFull, f[j]);
-            excl += __popc(b & lt_mask);
-            total += __popc(b);
-        }
-        const unsigned hb = __ballot_sync(kFull, hasf);
-
-        // segmented inclusive scan of the tails across lanes (segments start at flagged lanes)
-        if (lane == 0 && !hasf) tail = Semi<OP>::add(wcarry, tail);
-        int start = 31 - __clz(int(hb & le_mask));
-        if (start < 0) start = 0;
-        float v = tail;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const float tv = __shfl_up_sync(kFull, v, d);
-            if (int(lane) - d >= start) v = Semi<OP>::add(tv, v);
-        }
-        float carry_in = __shfl_up_sync(kFull, v, 1);
-        if (lane == 0) carry_in = wcarry;
-        wcarry = __shfl_sync(kFull, v, 31);
-
-        // pass 2: close rows; the k-th row end of this step goes to stage[k]
-        float acc = carry_in;
-        unsigned k = excl;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (f[j]) {
-                my_stage[k] = acc;
-                ++k;
-                acc = Semi<OP>::ident();
-            }
-            acc = Semi<OP>::add(acc, prod[j]);
-        }
-        __syncwarp();
-        for (unsigned k2 = lane; k2 < total; k2 += 32) {
-            const float val = my_stage[k2];
-            const uint32_t ord = ord_base + k2;
-            if (ord == ord0 && !fresh) {
-                P.head_carry[chunk] = val;  // row began in an earlier chunk
-            } else {
-                finish_row<OP>(P, P.nz_rows[ord], val);
-            }
-        }
-        __syncwarp();
-        ord_base += total;
-    }
-    if (lane == 0) P.tail_carry[chunk] = wcarry;
+// Matrix stream: read once, kept out of L1 so it cannot evict the hot x lines.
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
-// Variant A: one chunk per warp, x gathered through L1/L2 only.
+// x gather: hot column words (< tile_k) index the packed hot vector through L1 (allocating),
+// cold ones index x itself around L1.  Both addresses are formed, one load issues.
+__device__ __forceinline__ float gather_x(const float *hot_x, const float *x_cold, uint32_t tile_k, uint32_t c) {
+    float v;
+    asm("{\n"
+        " .reg .pred p;\n"
+        " setp.lt.u32 p, %3, %4;\n"
+        " @p ld.global.nc.L1::evict_last.f32 %0, [%1];\n"
+        " @!p ld.global.nc.L1::no_allocate.f32 %0, [%2];\n"
+        "}"
+        : "=f"(v)
+        : "l"(hot_x + c), "l"(x_cold + c), "r"(c), "r"(tile_k));
+    return v;
+}
+
+// One chunk (up to 8 groups of 128 non-zeros) by one warp.
 template <int OP>
-__global__ void __launch_bounds__(kThreads) spmv_ws_kernel(const SpmvParams P) {
-    __shared__ float stage[kWarpsPerBlock][kStep];
+__global__ void __launch_bounds__(kThreads) spmv_lane_kernel(const SpmvParams P) {
+    __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
     if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
-    process_chunk<OP, false>(P, chunk, lane, stage[wib], nullptr);
-}
+    float *const stage = stage_all[wib];
 
-// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    } while (!done);
-}
-
-// Variant B: persistent CTAs, one per SM.  Each CTA pulls the hot end of the relabelled vector
-// (columns [0, tile_k), the most referenced ones) into shared memory with TMA bulk copies
-// once, then its warps walk the chunk list; hot gathers become bank-parallel LDS instead of
-// one L1 wavefront + one 32-byte L2 sector per lane.
-template <int OP>
-__global__ void __launch_bounds__(1024, 1) spmv_ws_tile_kernel(const SpmvParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);
-    const unsigned n_warps = blockDim.x >> 5;
-    float *stage = tile + P.tile_k;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + n_warps * kStep);
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned wib = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = P.tile_k * 4u;
-        mbar_expect_tx(bar, bytes);
-        constexpr uint32_t kPiece = 32768;
-        for (uint32_t off = 0; off < bytes; off += kPiece) {
-            const uint32_t nb = (bytes - off < kPiece) ? (bytes - off) : kPiece;
-            bulk_g2s(reinterpret_cast<unsigned char *>(tile) + off, reinterpret_cast<const unsigned char *>(P.x) + off,
-                     nb, bar);
+    const uint32_t g0 = __ldg(P.chunk_goff + chunk);
+    const int n = int(__ldg(P.chunk_goff + chunk + 1) - g0);  // 1 .. GLB_MAX_GROUPS, warp-uniform
+    const uint4 *gp = reinterpret_cast<const uint4 *>(P.stream) + size_t(g0) * 64 + lane;
+    uint4 cq[kPrefetch + 1], aq[kPrefetch + 1];
+#pragma unroll
+    for (int g = 0; g < kPrefetch; ++g) {
+        if (g < n) {
+            cq[g] = ld_stream_v4(gp + g * 64);
+            aq[g] = ld_stream_v4(gp + g * 64 + 32);
         }
     }
-    mbar_wait(bar, 0);
+    const uint32_t fw = ld_stream_u32(P.flags + size_t(chunk) * 32 + lane);
+    const uint32_t cf = __ldg(P.chunk_first + chunk);
 
-    const uint32_t total_warps = gridDim.x * n_warps;
-    for (uint32_t chunk = blockIdx.x * n_warps + wib; chunk < P.n_chunks; chunk += total_warps)
-        process_chunk<OP, true>(P, chunk, lane, stage + wib * kStep, tile);
+    // ordinal of this lane's first row end = number of row ends in the lanes below
+    const uint32_t cnt = __popc(fw);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (int(lane) >= d) incl += t;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+
+    // the lane's run: serial reduction in registers; every flagged element closes the open row
+    float *sp = stage + excl;
+    float acc = Semi<OP>::ident();
+#pragma unroll
+    for (int g = 0; g < GLB_MAX_GROUPS; ++g) {
+        if (g < n) {
+            if (g + kPrefetch < GLB_MAX_GROUPS && g + kPrefetch < n) {
+                cq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64);
+                aq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64 + 32);
+            }
+            const uint4 c4 = cq[g % (kPrefetch + 1)], a4 = aq[g % (kPrefetch + 1)];
+            const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
+            const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float xv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xv[e] = gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float prod = Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
+                if (fw & (1u << (4 * g + e))) {
+                    *sp++ = acc;
+                    acc = Semi<OP>::ident();
+                }
+                acc = Semi<OP>::add(acc, prod);
+            }
+        }
+    }
+
+    // stitch rows that cross lanes: segmented inclusive scan of the lane tails (a lane holding a
+    // row start begins a new segment with what follows its last flag)
+    const bool hasf = fw != 0;
+    const unsigned hb = __ballot_sync(kFull, hasf);
+    const unsigned le_mask = 0xffffffffu >> (31u - lane);
+    int start = 31 - __clz(int(hb & le_mask));
+    if (start < 0) start = 0;
+    float v = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float tv = __shfl_up_sync(kFull, v, d);
+        if (int(lane) - d >= start) v = Semi<OP>::add(tv, v);
+    }
+    float carry_in = __shfl_up_sync(kFull, v, 1);
+    if (lane == 0) carry_in = Semi<OP>::ident();
+    if (hasf) stage[excl] = Semi<OP>::add(carry_in, stage[excl]);  // the lane's first row end began in lower lanes
+    if (lane == 31) P.tail_carry[chunk] = v;
+    __syncwarp();
+
+    // write back: the k-th row end of the chunk closes row ordinal ord0 + k
+    const uint32_t ord0 = cf & ~GLB_FLAG;
+    const bool fresh = (cf & GLB_FLAG) != 0;
+    for (uint32_t k = lane; k < total; k += 32) {
+        const float val = stage[k];
+        if (k == 0 && !fresh) {
+            P.head_carry[chunk] = val;  // row began in an earlier chunk
+        } else {
+            finish_row<OP>(P, __ldg(P.nz_rows + ord0 + k), val);
+        }
+    }
 }
 
-// xp[i] = x[perm[i]]: the caller's vector in the matrix's relabelled column order.
-__global__ void __launch_bounds__(kThreads) permute_x_kernel(const float *__restrict__ x,
-                                                           const uint32_t *__restrict__ perm, float *__restrict__ xp,
-                                                           uint32_t n4) {
-    const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
-        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(perm) + i);
-        float4 o;
-        o.x = __ldg(x + q.x);
-        o.y = __ldg(x + q.y);
-        o.z = __ldg(x + q.z);
-        o.w = __ldg(x + q.w);
-        reinterpret_cast<float4 *>(xp)[i] = o;
-    }
+// hot_x[i] = x[hot_cols[i]]: the x values of the most referenced columns, packed.
+__global__ void __launch_bounds__(kThreads) gather_hot_kernel(const float *__restrict__ x,
+                                                            const uint32_t *__restrict__ hot_cols,
+                                                            float *__restrict__ hot_x, uint32_t n) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) hot_x[i] = __ldg(x + __ldg(hot_cols + i));
 }
 
 // Rows touching a chunk boundary: total = tail[c_begin .. c_last] (+) head[c_end].
@@ -307,20 +275,16 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
         GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
     }
-    if (P.n_chunks && P.tile_k) {
-        const uint32_t n_warps = m->tile_threads / 32;
-        const size_t smem = size_t(P.tile_k) * 4 + size_t(n_warps) * kStep * 4 + 16;
-        static thread_local size_t attr_set[3] = {0, 0, 0};
-        if (attr_set[OP] < smem) {
-            GLB_CUDA(cudaFuncSetAttribute(spmv_ws_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            attr_set[OP] = smem;
+    if (P.n_chunks) {
+        // leave everything but the staging arrays to L1: that is where the hot x lines live
+        static thread_local int carveout_set[3] = {-1, -1, -1};
+        if (carveout_set[OP] != m->smem_carveout_pct) {
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          m->smem_carveout_pct));
+            carveout_set[OP] = m->smem_carveout_pct;
         }
-        uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
-        if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
-        spmv_ws_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
-    } else if (P.n_chunks) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        spmv_ws_kernel<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+        spmv_lane_kernel<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
     }
     if (ctx->timing) GLB_CUDA(cudaEventRecord(ev[1], ctx->stream));
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
@@ -357,25 +321,24 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
                     float *y, const glb_spmv_epilogue_t *ep) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
-    P.cols = m->cols;
-    P.vals = m->vals;
-    P.nz_rows = m->nz_rows;
+    P.stream = m->stream;
+    P.flags = m->flags;
+    P.chunk_goff = m->chunk_goff;
     P.chunk_first = m->chunk_first;
-    P.x = x;
-    if (m->col_perm) {  // relabelled columns: gather from the permuted copy of x
-        const uint32_t n4 = (m->num_cols + 3) / 4;
-        uint32_t blocks = (n4 + kThreads - 1) / kThreads;
-        const uint32_t cap = uint32_t(ctx->num_sms) * 8;
-        if (blocks > cap) blocks = cap;
-        permute_x_kernel<<<blocks, kThreads, 0, ctx->stream>>>(x, m->col_perm, m->xp, n4);
-        P.x = m->xp;
-    }
+    P.nz_rows = m->nz_rows;
     P.tile_k = m->tile_k;
+    if (m->n_hot && m->n_chunks) {  // pack the x values of the hot columns
+        gather_hot_kernel<<<(m->n_hot + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->hot_x,
+                                                                                            m->n_hot);
+        P.hot_x = m->hot_x;
+    } else {
+        P.hot_x = x;  // tile_k == num_cols (every column hot, identity numbering) or tile_k == 0
+    }
+    P.x_cold = x - m->tile_k;
     P.mask = mask;
     P.y = y;
     P.head_carry = m->head_carry;
     P.tail_carry = m->tail_carry;
-    P.nnz = m->nnz;
     P.n_chunks = m->n_chunks;
     P.zero = zero;
     P.mask_type = mask_type;
@@ -401,20 +364,36 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     return GLB_EINVAL;
 }
 
-// Host side of the formatter: O(nnz) copy + O(rows) flagging.  Shared by glb_csr_create and
-// the host-only glb_csr_format_host (which lets the layout be checked without a GPU).
+// ------------------------------------------------------------------------------------------
+// Host side of the formatter (the counterpart of csr2cpsr, data_formatter.h:457-534).  Shared by
+// glb_csr_create and the host-only glb_csr_format_host, which lets the layout be checked
+// without a GPU.  O(nnz) work; the stream transposition is spread over the host cores.
 struct HostLayout {
-    uint32_t *cols = nullptr;  // malloc'd, nnz entries (padding is added on the device)
-    std::vector<uint32_t> col_perm;  // relabelled column -> original column (empty = identity)
-    std::vector<uint32_t> nz_rows, empty_rows, chunk_first;
+    uint32_t *stream = nullptr;  // malloc'd, 256 * n_groups words
+    std::vector<uint32_t> flags, chunk_goff, chunk_first, nz_rows, empty_rows, hot_cols;
     std::vector<glb_fixup_t> fix_short, fix_long;
     uint64_t nnz = 0, sb = 0;
-    uint32_t n_chunks = 0;
-    ~HostLayout() { free(cols); }
+    uint32_t n_chunks = 0, n_groups = 0, tile_k = 0;
+    ~HostLayout() { free(stream); }
 };
 
+template <typename F>
+static void parallel_for(size_t n, size_t grain, F &&body) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t workers = std::min<size_t>(hw ? hw : 1, (n + grain - 1) / grain);
+    if (workers <= 1) { body(size_t(0), n); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (n + workers - 1) / workers;
+    for (size_t w = 0; w < workers; ++w) {
+        const size_t b = w * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        pool.emplace_back([&body, b, e] { body(b, e); });
+    }
+    for (auto &t : pool) t.join();
+}
+
 static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
-                       uint32_t row_begin, uint32_t row_end, HostLayout &L, bool relabel = false) {
+                       const float *data, uint32_t row_begin, uint32_t row_end, uint32_t tile_k_req, HostLayout &L) {
     GLB_REQUIRE(indptr, "NULL indptr");
     GLB_REQUIRE(row_begin <= row_end && row_end <= num_rows, "bad row range");
     GLB_REQUIRE(num_cols >= 1 && num_cols < GLB_FLAG, "num_cols must be in [1, 2^31)");
@@ -424,54 +403,135 @@ static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *ind
     GLB_REQUIRE(nnz == 0 || indices, "NULL indices");
     L.nnz = nnz;
     L.sb = sb;
-    L.n_chunks = uint32_t((nnz + GLB_CHUNK - 1) / GLB_CHUNK);
-    L.cols = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (nnz ? nnz : 1)));
-    if (!L.cols) { glb_set_error("glb_csr_create: host allocation failed"); return GLB_ENOMEM; }
-    if (nnz) memcpy(L.cols, indices + sb, sizeof(uint32_t) * nnz);
-    for (uint64_t i = 0; i < nnz; ++i) {
-        if (L.cols[i] >= num_cols) {
-            glb_set_error("glb_csr_create: column index %u out of range at nnz %llu", L.cols[i],
-                          (unsigned long long)(sb + i));
-            return GLB_EINVAL;
-        }
-    }
-    if (relabel && nnz) {
-        // Columns renumbered by descending reference count inside this shard (ties by id): the hot
-        // end of the vector becomes one contiguous block -- a TMA-loadable shared-memory tile -- and
-        // equally warm columns share 32-byte sectors.  col_perm[new] = old.
-        std::vector<uint32_t> count(num_cols, 0);
-        for (uint64_t i = 0; i < nnz; ++i) count[L.cols[i]]++;
-        L.col_perm.resize(num_cols);
-        for (uint32_t c = 0; c < num_cols; ++c) L.col_perm[c] = c;
-        std::stable_sort(L.col_perm.begin(), L.col_perm.end(),
-                         [&](uint32_t a, uint32_t b) { return count[a] > count[b]; });
-        std::vector<uint32_t> &rank = count;  // reuse: rank[old] = new
-        for (uint32_t n = 0; n < num_cols; ++n) rank[L.col_perm[n]] = n;
-        for (uint64_t i = 0; i < nnz; ++i) L.cols[i] = rank[L.cols[i]];
-    }
-    L.chunk_first.assign(L.n_chunks, 0);
+    const uint32_t *ix = indices + sb;
+
+    // rows: non-empty (ordinal order) and empty ones
     L.nz_rows.reserve(row_end - row_begin);
     for (uint32_t r = row_begin; r < row_end; ++r) {
         if (indptr[r + 1] < indptr[r]) {
             glb_set_error("glb_csr_create: indptr not monotone at row %u", r);
             return GLB_EINVAL;
         }
-        const uint64_t p0 = uint64_t(indptr[r]) - sb, p1 = uint64_t(indptr[r + 1]) - sb;
-        if (p0 == p1) { L.empty_rows.push_back(r); continue; }
-        const uint32_t ord = uint32_t(L.nz_rows.size());
-        L.nz_rows.push_back(r);
-        const uint32_t c_s = uint32_t(p0 / GLB_CHUNK), c_e = uint32_t((p1 - 1) / GLB_CHUNK);
-        if (p0 % GLB_CHUNK == 0) L.chunk_first[c_s] = ord | GLB_FLAG;  // row starts with the chunk
-        else L.cols[p0] |= GLB_FLAG;
-        for (uint32_t c = c_s + 1; c <= c_e; ++c) L.chunk_first[c] = ord;  // chunks starting inside this row
-        const bool ends_on_boundary = (p1 % GLB_CHUNK == 0) || (p1 == nnz);
-        if (c_s == c_e && !ends_on_boundary) continue;  // interior row: the main kernel finishes it
-        glb_fixup_t e;
-        e.row = r;
-        e.c_begin = c_s;
-        e.c_end = ends_on_boundary ? c_e : (c_e | GLB_FLAG);
-        ((c_e - c_s) <= 32 ? L.fix_short : L.fix_long).push_back(e);
+        if (indptr[r + 1] == indptr[r]) L.empty_rows.push_back(r);
+        else L.nz_rows.push_back(r);
     }
+    const uint32_t n_nz = uint32_t(L.nz_rows.size());
+
+    // ---- hot columns: the tile_k most referenced ones get the low numbers ------------------
+    std::vector<uint32_t> count(num_cols, 0);
+    for (uint64_t i = 0; i < nnz; ++i) {
+        if (ix[i] >= num_cols) {
+            glb_set_error("glb_csr_create: column index %u out of range at nnz %llu", ix[i], (unsigned long long)(sb + i));
+            return GLB_EINVAL;
+        }
+        count[ix[i]]++;
+    }
+    std::vector<uint32_t> enc;  // column -> stored word (empty = identity)
+    if (tile_k_req >= num_cols) {
+        L.tile_k = num_cols;  // every column hot, identity numbering: hot_x is x itself
+    } else if (tile_k_req == 0 || nnz == 0) {
+        L.tile_k = 0;
+    } else {
+        L.tile_k = tile_k_req;
+        std::vector<uint32_t> order(num_cols);
+        for (uint32_t c = 0; c < num_cols; ++c) order[c] = c;
+        auto hotter = [&](uint32_t a, uint32_t b) { return count[a] != count[b] ? count[a] > count[b] : a < b; };
+        std::nth_element(order.begin(), order.begin() + L.tile_k, order.end(), hotter);
+        std::sort(order.begin(), order.begin() + L.tile_k, hotter);
+        L.hot_cols.assign(order.begin(), order.begin() + L.tile_k);
+        enc.resize(num_cols);
+        for (uint32_t c = 0; c < num_cols; ++c) enc[c] = L.tile_k + c;
+        for (uint32_t k = 0; k < L.tile_k; ++k) enc[L.hot_cols[k]] = k;
+    }
+    count.clear();
+    count.shrink_to_fit();
+
+    // ---- chunking: up to 8 groups of 128 non-zeros, at most GLB_ROW_CAP row ends ---------------
+    constexpr uint64_t kChunkMax = uint64_t(GLB_GROUP) * GLB_MAX_GROUPS;
+    std::vector<uint64_t> cs;  // chunk start positions (shard-local), plus the end sentinel
+    {
+        uint64_t cur = 0;
+        uint32_t flags_in = 0;
+        for (uint32_t k = 0; k < n_nz; ++k) {
+            const uint64_t p0 = uint64_t(indptr[L.nz_rows[k]]) - sb;
+            while (p0 >= cur + kChunkMax) { cs.push_back(cur); cur += kChunkMax; flags_in = 0; }
+            if (p0 == cur) continue;  // the row opens the chunk: no flag
+            if (flags_in == GLB_ROW_CAP - 1) {  // keep one slot for the padding flag: cut here, at a row start
+                cs.push_back(cur);
+                cur = p0;
+                flags_in = 0;
+                continue;
+            }
+            ++flags_in;
+        }
+        while (cur < nnz) { cs.push_back(cur); cur = std::min(nnz, cur + kChunkMax); }
+        cs.push_back(nnz);
+    }
+    const uint32_t n_chunks = uint32_t(cs.size() - 1);
+    L.n_chunks = n_chunks;
+    L.chunk_goff.assign(n_chunks + 1, 0);
+    for (uint32_t c = 0; c < n_chunks; ++c)
+        L.chunk_goff[c + 1] = L.chunk_goff[c] + uint32_t((cs[c + 1] - cs[c] + GLB_GROUP - 1) / GLB_GROUP);
+    L.n_groups = L.chunk_goff[n_chunks];
+    auto padded = [&](uint32_t c) { return ((cs[c + 1] - cs[c]) % GLB_GROUP) != 0; };
+    auto n_of = [&](uint32_t c) { return L.chunk_goff[c + 1] - L.chunk_goff[c]; };
+
+    // ---- flags, chunk_first, fix-up list -----------------------------------------------------
+    L.flags.assign(size_t(n_chunks) * 32, 0);
+    L.chunk_first.assign(n_chunks, 0);
+    auto set_flag = [&](uint32_t c, uint64_t i) {  // position i of chunk c -> lane word, bit
+        const uint32_t run = 4 * n_of(c);
+        L.flags[size_t(c) * 32 + i / run] |= 1u << (i % run);
+    };
+    {
+        uint32_t c = 0;
+        for (uint32_t k = 0; k < n_nz; ++k) {
+            const uint32_t r = L.nz_rows[k];
+            const uint64_t p0 = uint64_t(indptr[r]) - sb, p1 = uint64_t(indptr[r + 1]) - sb;
+            while (cs[c + 1] <= p0) ++c;
+            const uint32_t c_s = c;
+            if (p0 == cs[c_s]) L.chunk_first[c_s] = k | GLB_FLAG;  // row starts with the chunk
+            else set_flag(c_s, p0 - cs[c_s]);
+            uint32_t c_e = c_s;
+            while (cs[c_e + 1] < p1) { ++c_e; L.chunk_first[c_e] = k; }  // chunks starting inside this row
+            const bool closed = (p1 < cs[c_e + 1]) || padded(c_e);  // a later flag of chunk c_e ends the row
+            if (c_s == c_e && closed) continue;  // interior row: the main kernel finishes it
+            glb_fixup_t e;
+            e.row = r;
+            e.c_begin = c_s;
+            e.c_end = closed ? (c_e | GLB_FLAG) : c_e;
+            ((c_e - c_s) <= 32 ? L.fix_short : L.fix_long).push_back(e);
+        }
+        for (uint32_t c2 = 0; c2 < n_chunks; ++c2)
+            if (padded(c2)) set_flag(c2, cs[c2 + 1] - cs[c2]);  // padding is a row of its own, never written back
+    }
+
+    // ---- the transposed stream -----------------------------------------------------------------
+    L.stream = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * 256 * size_t(L.n_groups ? L.n_groups : 1)));
+    if (!L.stream) { glb_set_error("glb_csr_create: host allocation failed"); return GLB_ENOMEM; }
+    const uint32_t *dbits = reinterpret_cast<const uint32_t *>(data ? data + sb : nullptr);
+    const uint32_t *encp = enc.empty() ? nullptr : enc.data();
+    parallel_for(n_chunks, 256, [&](size_t cb, size_t ce) {
+        for (size_t c = cb; c < ce; ++c) {
+            const uint32_t n = L.chunk_goff[c + 1] - L.chunk_goff[c], run = 4 * n;
+            uint32_t *out = L.stream + size_t(L.chunk_goff[c]) * 256;
+            const uint64_t s = cs[c], len = cs[c + 1] - cs[c];
+            uint64_t i = 0;
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                for (uint32_t r = 0; r < run; ++r, ++i) {
+                    const uint32_t w = (r >> 2) * 256 + lane * 4 + (r & 3);
+                    if (i < len) {
+                        const uint32_t col = ix[s + i];
+                        out[w] = encp ? encp[col] : col;
+                        out[w + 128] = dbits ? dbits[s + i] : 0u;
+                    } else {
+                        out[w] = 0;  // padding: a valid (hot) address, value irrelevant
+                        out[w + 128] = 0;
+                    }
+                }
+            }
+        }
+    });
     return GLB_OK;
 }
 
@@ -480,36 +540,46 @@ extern "C" {
 // Host-only view of the layout for tests (no CUDA call).  Arrays are malloc'd copies the
 // caller releases with glb_host_layout_free.
 int glb_csr_format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
-                        uint32_t row_begin, uint32_t row_end, glb_host_layout_t *out) {
+                        const float *data, uint32_t row_begin, uint32_t row_end, uint32_t tile_k,
+                        glb_host_layout_t *out) {
     GLB_REQUIRE(out, "out is NULL");
     memset(out, 0, sizeof(*out));
     HostLayout L;
-    int rc = format_host(num_rows, num_cols, indptr, indices, row_begin, row_end, L);
+    int rc = format_host(num_rows, num_cols, indptr, indices, data, row_begin, row_end, tile_k, L);
     if (rc) return rc;
     auto dup = [](const void *src, size_t bytes) {
         void *p = malloc(bytes ? bytes : 1);
         if (p && bytes) memcpy(p, src, bytes);
-        return p;
+        return static_cast<uint32_t *>(p);
     };
     std::vector<glb_fixup_t> fix(L.fix_short);
     fix.insert(fix.end(), L.fix_long.begin(), L.fix_long.end());
-    out->chunk = GLB_CHUNK;
+    out->group = GLB_GROUP;
+    out->max_groups = GLB_MAX_GROUPS;
+    out->row_cap = GLB_ROW_CAP;
     out->nnz = L.nnz;
     out->n_chunks = L.n_chunks;
+    out->n_groups = L.n_groups;
     out->n_nz_rows = uint32_t(L.nz_rows.size());
     out->n_empty = uint32_t(L.empty_rows.size());
     out->n_fixups = uint32_t(fix.size());
-    out->cols = static_cast<uint32_t *>(dup(L.cols, sizeof(uint32_t) * L.nnz));
-    out->nz_rows = static_cast<uint32_t *>(dup(L.nz_rows.data(), sizeof(uint32_t) * L.nz_rows.size()));
-    out->empty_rows = static_cast<uint32_t *>(dup(L.empty_rows.data(), sizeof(uint32_t) * L.empty_rows.size()));
-    out->chunk_first = static_cast<uint32_t *>(dup(L.chunk_first.data(), sizeof(uint32_t) * L.chunk_first.size()));
-    out->fixups = static_cast<uint32_t *>(dup(fix.data(), sizeof(glb_fixup_t) * fix.size()));
+    out->tile_k = L.tile_k;
+    out->n_hot = uint32_t(L.hot_cols.size());
+    out->stream = dup(L.stream, sizeof(uint32_t) * 256 * size_t(L.n_groups));
+    out->flags = dup(L.flags.data(), sizeof(uint32_t) * L.flags.size());
+    out->chunk_goff = dup(L.chunk_goff.data(), sizeof(uint32_t) * L.chunk_goff.size());
+    out->chunk_first = dup(L.chunk_first.data(), sizeof(uint32_t) * L.chunk_first.size());
+    out->nz_rows = dup(L.nz_rows.data(), sizeof(uint32_t) * L.nz_rows.size());
+    out->empty_rows = dup(L.empty_rows.data(), sizeof(uint32_t) * L.empty_rows.size());
+    out->fixups = dup(fix.data(), sizeof(glb_fixup_t) * fix.size());
+    out->hot_cols = dup(L.hot_cols.data(), sizeof(uint32_t) * L.hot_cols.size());
     return GLB_OK;
 }
 
 int glb_host_layout_free(glb_host_layout_t *l) {
     if (!l) return GLB_OK;
-    free(l->cols); free(l->nz_rows); free(l->empty_rows); free(l->chunk_first); free(l->fixups);
+    free(l->stream); free(l->flags); free(l->chunk_goff); free(l->chunk_first);
+    free(l->nz_rows); free(l->empty_rows); free(l->fixups); free(l->hot_cols);
     memset(l, 0, sizeof(*l));
     return GLB_OK;
 }
@@ -519,31 +589,20 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     GLB_REQUIRE(ctx && out, "NULL argument");
     *out = nullptr;
     // Tuning knobs (defaults chosen by measurement on B200):
-    //   GLB_SPMV_RELABEL=0|1       renumber columns by popularity (needs one x-permute pass per SpMV)
-    //   GLB_SPMV_TILE_K=<floats>   hot columns kept in shared memory (0 = gather everything via L1/L2)
-    //   GLB_SPMV_TILE_THREADS=<n>  threads of the persistent tile kernel
+    //   GLB_SPMV_TILE_K=<floats>     hot columns packed into the L1-resident hot_x (0 = none)
+    //   GLB_SPMV_CARVEOUT=<percent>  shared-memory carve-out hint of the main kernel
     auto env_u32 = [](const char *name, uint32_t dflt) {
         const char *v = getenv(name);
         return v ? uint32_t(strtoul(v, nullptr, 10)) : dflt;
     };
-    const bool relabel = env_u32("GLB_SPMV_RELABEL", 1) != 0 && num_cols >= 4096;
-    uint32_t tile_k = relabel ? env_u32("GLB_SPMV_TILE_K", 0) : 0;  // measured: the 1-CTA/SM tile kernel loses (profiles/r1_sweep_v1.txt)
-    uint32_t tile_threads = env_u32("GLB_SPMV_TILE_THREADS", 1024);
-    if (tile_threads < 32 || tile_threads > 1024 || tile_threads % 32) tile_threads = 1024;
-    const uint32_t cols_pad = (num_cols + 3u) & ~3u;
-    if (tile_k > cols_pad) tile_k = cols_pad;
-    tile_k &= ~3u;
-    if (size_t(tile_k) * 4 + size_t(tile_threads / 32) * kStep * 4 + 16 > 227 * 1024)
-        tile_k = uint32_t((227 * 1024 - size_t(tile_threads / 32) * kStep * 4 - 16) / 4) & ~3u;
+    const uint32_t tile_k = env_u32("GLB_SPMV_TILE_K", GLB_DEFAULT_TILE_K);
+    const uint32_t carveout = env_u32("GLB_SPMV_CARVEOUT", GLB_DEFAULT_CARVEOUT_PCT);
 
     HostLayout L;
-    int rc = format_host(num_rows, num_cols, indptr, indices, row_begin, row_end, L, relabel);
+    int rc = format_host(num_rows, num_cols, indptr, indices, data, row_begin, row_end, tile_k, L);
     if (rc) return rc;
-    const uint64_t nnz = L.nnz, sb = L.sb;
-    GLB_REQUIRE(nnz == 0 || data, "NULL data");
+    GLB_REQUIRE(L.nnz == 0 || data, "NULL data");
     GLB_CUDA(cudaSetDevice(ctx->device));
-    const uint32_t n_chunks = L.n_chunks;
-    const uint64_t nnz_pad = uint64_t(n_chunks) * GLB_CHUNK;
 
     glb_csr_t m = new glb_csr_s();
     m->ctx = ctx;
@@ -551,29 +610,33 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     m->num_cols = num_cols;
     m->row_begin = row_begin;
     m->row_end = row_end;
-    m->nnz = nnz;
-    m->n_chunks = n_chunks;
+    m->nnz = L.nnz;
+    m->n_chunks = L.n_chunks;
+    m->n_groups = L.n_groups;
     m->n_nz_rows = uint32_t(L.nz_rows.size());
     m->n_fix_short = uint32_t(L.fix_short.size());
     m->n_fix_long = uint32_t(L.fix_long.size());
     m->n_empty = uint32_t(L.empty_rows.size());
+    m->tile_k = L.tile_k;
+    m->n_hot = uint32_t(L.hot_cols.size());
+    m->smem_carveout_pct = int(carveout > 100 ? 100 : carveout);
 
     size_t bytes = 0;
-    if (!rc) rc = upload(ctx, &m->cols, L.cols, size_t(nnz), size_t(nnz_pad), &bytes);
-    if (!rc) rc = upload(ctx, &m->vals, nnz ? data + sb : nullptr, size_t(nnz), size_t(nnz_pad), &bytes);
-    if (!rc) rc = upload(ctx, &m->nz_rows, L.nz_rows.data(), L.nz_rows.size(), L.nz_rows.size(), &bytes);
+    const size_t words = size_t(L.n_groups) * 256;
+    if (!rc) rc = upload(ctx, &m->stream, L.stream, words, words, &bytes);
+    if (!rc) rc = upload(ctx, &m->flags, L.flags.data(), L.flags.size(), L.flags.size(), &bytes);
+    if (!rc) rc = upload(ctx, &m->chunk_goff, L.chunk_goff.data(), L.chunk_goff.size(), L.chunk_goff.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->chunk_first, L.chunk_first.data(), L.chunk_first.size(), L.chunk_first.size(), &bytes);
+    if (!rc) rc = upload(ctx, &m->nz_rows, L.nz_rows.data(), L.nz_rows.size(), L.nz_rows.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->fix_short, L.fix_short.data(), L.fix_short.size(), L.fix_short.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->fix_long, L.fix_long.data(), L.fix_long.size(), L.fix_long.size(), &bytes);
     if (!rc) rc = upload(ctx, &m->empty_rows, L.empty_rows.data(), L.empty_rows.size(), L.empty_rows.size(), &bytes);
-    if (!rc && !L.col_perm.empty()) {
-        rc = upload(ctx, &m->col_perm, L.col_perm.data(), L.col_perm.size(), size_t(cols_pad), &bytes);
-        if (!rc) rc = upload<float>(ctx, &m->xp, nullptr, 0, size_t(cols_pad), &bytes);
-        m->tile_k = tile_k;
-        m->tile_threads = tile_threads;
+    if (!rc && m->n_hot) {
+        rc = upload(ctx, &m->hot_cols, L.hot_cols.data(), L.hot_cols.size(), L.hot_cols.size(), &bytes);
+        if (!rc) rc = upload<float>(ctx, &m->hot_x, nullptr, 0, m->n_hot, &bytes);
     }
-    if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, n_chunks, &bytes);
-    if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, n_chunks, &bytes);
+    if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, L.n_chunks, &bytes);
+    if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         glb_set_error("glb_csr_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = GLB_ECUDA;
@@ -588,9 +651,9 @@ int glb_csr_destroy(glb_csr_t m) {
     if (!m) return GLB_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->cols); cudaFree(m->vals); cudaFree(m->nz_rows); cudaFree(m->chunk_first);
+    cudaFree(m->stream); cudaFree(m->flags); cudaFree(m->chunk_goff); cudaFree(m->chunk_first); cudaFree(m->nz_rows);
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
-    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->col_perm); cudaFree(m->xp);
+    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
     delete m;
     return GLB_OK;
@@ -605,7 +668,7 @@ int glb_csr_info(glb_csr_t m, uint64_t info[8]) {
     info[4] = uint64_t(m->n_fix_short) + m->n_fix_long;
     info[5] = m->n_empty;
     info[6] = m->device_bytes;
-    info[7] = GLB_CHUNK;
+    info[7] = m->tile_k;
     return GLB_OK;
 }
 

@@ -18,7 +18,7 @@
  * base_module.h:106-133), buffers (cl::Buffer + enqueueMigrateMemObjects), device-to-device
  * copies (base_module.h:82-85) and the matrix upload (send_matrix_host_to_device,
  * spmv_module.h:374-420, spmspv_module.h:290-370) -- which is where the device layout is built
- * (CPSR / formatCSC in the reference, the warp-segment layout here).
+ * (CPSR / formatCSC in the reference, the lane-segment layout here).
  *
  * Conventions
  *  - every function returns 0 on success, a GLB_E* code otherwise; glb_last_error() gives the
@@ -67,7 +67,7 @@ typedef struct glb_idx_val {
 } glb_idx_val_t;
 
 typedef struct glb_ctx_s *glb_ctx_t; /* one CUDA device + one stream (cl::Context + cl::CommandQueue)  */
-typedef struct glb_csr_s *glb_csr_t; /* device-resident CSR row shard in warp-segment layout (SpMV)    */
+typedef struct glb_csr_s *glb_csr_t; /* device-resident CSR row shard in lane-segment layout (SpMV)    */
 typedef struct glb_csc_s *glb_csc_t; /* device-resident CSC (SpMSpV)                                    */
 
 /* ------------------------------------------------------------------ runtime ------- */
@@ -107,7 +107,7 @@ int glb_host_free(void *hptr);
 
 /* ------------------------------------------------------------------ matrices ------
  * SpMVModule::load_and_format_matrix + send_matrix_host_to_device (spmv_module.h:282-420):
- * takes a host CSR (CSRMatrix<float>, data_loader.h:19-31), builds the warp-segment layout
+ * takes a host CSR (CSRMatrix<float>, data_loader.h:19-31), builds the lane-segment layout
  * for rows [row_begin, row_end) and uploads it.  Row ids stay GLOBAL: glb_spmv writes
  * y[r] for r in the shard only, so ranks of a row-sharded run fill disjoint slices of one
  * full-length vector.  Pass row_begin = 0, row_end = num_rows for the whole matrix. */
@@ -116,28 +116,42 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
                    glb_csr_t *out);
 int glb_csr_destroy(glb_csr_t m);
 /* info[0]=rows in shard, [1]=num_cols, [2]=nnz in shard, [3]=chunks, [4]=fix-up rows,
- * [5]=empty rows in shard, [6]=device bytes of the layout, [7]=nnz per chunk. */
+ * [5]=empty rows in shard, [6]=device bytes of the layout, [7]=hot columns (tile_k). */
 int glb_csr_info(glb_csr_t m, uint64_t info[8]);
 
-/* Host-only view of the warp-segment layout glb_csr_create builds (no CUDA call), so the
+/* Host-only view of the lane-segment layout glb_csr_create builds (no CUDA call), so the
  * formatter -- the counterpart of csr2cpsr, data_formatter.h:457-534 -- can be checked on a
- * machine without a GPU.  cols[p] bit31 = "p starts a row" (never set at a chunk start);
- * chunk_first[c] = ordinal into nz_rows of the row holding the chunk's first non-zero,
- * bit31 = that row starts exactly there; fixups = n_fixups x {row, c_begin, c_end}: the row's
- * value is tail_carry[c_begin .. c_last] (+) head_carry[c_end] when bit31 of c_end is set
- * (c_last = c_end - 1), else tail_carry[c_begin .. c_end]. */
+ * machine without a GPU.  The nnz stream is cut into chunks of up to `max_groups` groups of
+ * `group` non-zeros (one warp per chunk); in a chunk of n groups lane l owns the 4n consecutive
+ * non-zeros [4n*l, 4n*(l+1)), stored transposed:
+ *   stream[256*G + 4*l + e]        encoded column of element 4g+e of lane l (G = chunk_goff[c] + g)
+ *   stream[256*G + 128 + 4*l + e]  bit pattern of its fp32 value (0 when `data` was NULL)
+ *   encoded column                 rank (< tile_k) in hot_cols of a hot column, else tile_k + column;
+ *                                  with tile_k == num_cols (n_hot == 0) the numbering is the identity
+ *   flags[32*c + l]                bit r = element r of lane l starts a row (never the chunk's first
+ *                                  non-zero); the first padding element of a chunk is flagged too
+ *   chunk_first[c]                 ordinal into nz_rows of the row open at the chunk start,
+ *                                  bit31 = that row starts exactly there
+ *   fixups                         n_fixups x {row, c_begin, c_end}: the row's value is
+ *                                  tail_carry[c_begin .. c_end - 1] (+) head_carry[c_end] when bit31 of
+ *                                  c_end is set, else tail_carry[c_begin .. c_end]
+ * A chunk holds at most row_cap flags. */
 typedef struct glb_host_layout {
-    uint32_t chunk;      /* non-zeros per chunk (one warp each) */
+    uint32_t group, max_groups, row_cap;
     uint64_t nnz;
-    uint32_t n_chunks, n_nz_rows, n_empty, n_fixups;
-    uint32_t *cols;        /* nnz */
+    uint32_t n_chunks, n_groups, n_nz_rows, n_empty, n_fixups, tile_k, n_hot;
+    uint32_t *stream;      /* 256 * n_groups */
+    uint32_t *flags;       /* 32 * n_chunks */
+    uint32_t *chunk_goff;  /* n_chunks + 1 */
+    uint32_t *chunk_first; /* n_chunks */
     uint32_t *nz_rows;     /* n_nz_rows */
     uint32_t *empty_rows;  /* n_empty */
-    uint32_t *chunk_first; /* n_chunks */
     uint32_t *fixups;      /* 3 * n_fixups */
+    uint32_t *hot_cols;    /* n_hot */
 } glb_host_layout_t;
 int glb_csr_format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
-                        uint32_t row_begin, uint32_t row_end, glb_host_layout_t *out);
+                        const float *data, uint32_t row_begin, uint32_t row_end, uint32_t tile_k,
+                        glb_host_layout_t *out);
 int glb_host_layout_free(glb_host_layout_t *layout);
 
 /* SpMSpVModule::load_and_format_matrix + send_matrix_host_to_device (spmspv_module.h:264-370):

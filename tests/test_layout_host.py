@@ -1,4 +1,4 @@
-"""The warp-segment formatter (glb_csr_format_host, the counterpart of the reference's csr2cpsr,
+"""The lane-segment formatter (glb_csr_format_host, the counterpart of the reference's csr2cpsr,
 data_formatter.h:457-534) checked on the CPU: a sequential model of the kernel schedule
 (tests/layout_model.py) run over the produced arrays must reproduce the oracle's SpMV."""
 import numpy as np
@@ -9,20 +9,28 @@ from layout_model import FLAG, run_model
 from util import SEMIRINGS, random_csr
 
 
-def check(oracle, m, rb=0, re=None, seed=0):
+def check(oracle, m, rb=0, re=None, seed=0, tile_k=0):
     rng = np.random.default_rng(seed)
     re = m.num_rows if re is None else re
-    L = capi.format_host(m, rb, re)
-    assert L["nnz"] == int(m.indptr[re]) - int(m.indptr[rb])
-    assert L["n_chunks"] == -(-L["nnz"] // L["chunk"])
-    # invariants: one flag per non-empty row that does not start a chunk; none at chunk starts
-    starts = m.indptr[rb:re][np.diff(m.indptr[rb:re + 1].astype(np.int64)) > 0].astype(np.int64) - int(m.indptr[rb])
-    flags = np.nonzero(L["cols"] & FLAG)[0]
-    assert sorted(flags.tolist()) == sorted(s for s in starts.tolist() if s % L["chunk"] != 0)
+    L = capi.format_host(m, rb, re, tile_k)
+    nnz = int(m.indptr[re]) - int(m.indptr[rb])
+    assert L["nnz"] == nnz
+    # invariants: chunks tile the group stream, hold 1..8 groups and at most row_cap flags;
+    # one flag per non-empty row that does not open a chunk, plus one per padded chunk
+    n_groups = np.diff(L["chunk_goff"].astype(np.int64))
+    assert L["n_chunks"] == 0 or (n_groups.min() >= 1 and n_groups.max() <= L["max_groups"])
+    assert int(L["chunk_goff"][-1]) == L["n_groups"] and L["n_groups"] * L["group"] - nnz < L["group"] * max(L["n_chunks"], 1)
+    n_flags = sum(bin(int(w)).count("1") for w in L["flags"].ravel())
+    n_fresh = int((L["chunk_first"] & FLAG != 0).sum())
     assert len(L["nz_rows"]) + len(L["empty_rows"]) == re - rb
+    assert len(L["nz_rows"]) <= n_flags + n_fresh <= len(L["nz_rows"]) + L["n_chunks"]
+    if L["n_chunks"]:
+        assert max(sum(bin(int(w)).count("1") for w in row) for row in L["flags"]) <= L["row_cap"]
+    if len(L["hot_cols"]):
+        assert L["tile_k"] == len(L["hot_cols"]) == len(set(L["hot_cols"].tolist()))
     for op, zero in SEMIRINGS:
         x = rng.integers(0, 2, m.num_cols).astype(np.float32) if op != 2 else rng.integers(0, 5, m.num_cols).astype(np.float32)
-        y, written = run_model(L, m.data, x, op, zero, m.num_rows, int(m.indptr[rb]))
+        y, written = run_model(L, x, op, zero, m.num_rows)
         ref = oracle.port.spmv(m, op, zero, 0, x)
         assert (written[rb:re] == 1).all() and written[:rb].sum() == 0 and written[re:].sum() == 0
         if op == 0:
@@ -37,7 +45,13 @@ def test_powerlaw_and_shards(oracle):
     m = datasets.powerlaw_csr(3000, 3000, 60000, seed=5, max_degree=5000)
     m.data = rng.random(m.nnz).astype(np.float32)
     L = check(oracle, m)
-    assert L["n_chunks"] == 59 and len(L["fixups"]) <= L["n_chunks"]
+    assert L["n_chunks"] >= 59 and len(L["fixups"]) <= 2 * L["n_chunks"]
+    L = check(oracle, m, tile_k=64)          # hot columns renumbered
+    assert len(L["hot_cols"]) == 64
+    counts = np.bincount(m.indices, minlength=m.num_cols)
+    assert counts[L["hot_cols"]].min() >= np.sort(counts)[-64]
+    check(oracle, m, tile_k=1 << 20)         # every column hot: identity numbering
+    check(oracle, m, 1000, 2000, tile_k=100)
     check(oracle, m, 1000, 2000)
     check(oracle, m, 0, 1)
     check(oracle, m, 2999, 3000)
@@ -60,7 +74,23 @@ def test_boundary_cases(oracle):
     one_long = io.CSRMatrix(1, 50, np.ones(40000, np.float32), rng.integers(0, 50, 40000).astype(np.uint32),
                             np.array([0, 40000], np.uint32))
     L = check(oracle, one_long)
-    assert len(L["fixups"]) == 1 and L["fixups"][0].tolist() == [0, 0, 39]
+    assert len(L["fixups"]) == 1 and L["fixups"][0].tolist()[:2] == [0, 0] and (L["fixups"][0][2] & 0x7fffffff) == 39
+
+
+def test_row_cap_cuts_chunks(oracle):
+    # many very short rows: more row ends per 1024 non-zeros than a chunk may hold
+    rng = np.random.default_rng(7)
+    deg = rng.integers(0, 4, 6000)
+    deg[100:110] = 700
+    ip = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint32)
+    nnz = int(ip[-1])
+    m = io.CSRMatrix(len(deg), 900, rng.random(nnz).astype(np.float32), rng.integers(0, 900, nnz).astype(np.uint32), ip)
+    L = check(oracle, m, tile_k=50)
+    assert (np.diff(L["chunk_goff"].astype(np.int64)) < L["max_groups"]).any()   # some chunk was cut early
+    check(oracle, m, 17, 5000, tile_k=0)
+    ones = io.CSRMatrix(5000, 5000, np.ones(5000, np.float32), np.arange(5000, dtype=np.uint32),
+                        np.arange(5001, dtype=np.uint32))
+    check(oracle, ones, tile_k=128)
 
 
 def test_empty_and_tiny(oracle):

@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     return x;
 }
 
-enum { M_LDG = 0, M_LDG_NC_NOALLOC, M_LDG_CG, M_TEX, M_SMEM, M_MIX, M_LDG_IDX, M_MIX_IDX };
+enum { M_LDG = 0, M_LDG_NC_NOALLOC, M_LDG_CG, M_TEX, M_SMEM, M_MIX, M_LDG_IDX, M_MIX_IDX, M_L1MIX_IDX, M_L1MIX2_IDX };
 
 // Each thread performs `per_thread` gathers; the index is a hash (ALU only, no index stream), or
 // read from a coalesced uint4 stream (IDX modes: the real SpMV shape, 4 per lane per step).
@@ -31,13 +31,22 @@ __global__ void __launch_bounds__(1024) gather_kernel(const float *__restrict__ 
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nthreads = gridDim.x * blockDim.x;
     float acc = 0.f;
-    if (MODE == M_LDG_IDX || MODE == M_MIX_IDX) {
+    if (MODE == M_LDG_IDX || MODE == M_MIX_IDX || MODE == M_L1MIX_IDX || MODE == M_L1MIX2_IDX) {
         for (uint32_t it = 0; it < per_thread / 4; ++it) {
             const uint4 c = __ldcs(idx + size_t(it) * nthreads + tid);
             const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (MODE == M_MIX_IDX) acc += (cc[j] < tile_k) ? tile[cc[j]] : __ldg(x + cc[j]);
+                else if (MODE == M_L1MIX_IDX || MODE == M_L1MIX2_IDX) {
+                    // hot prefix through L1 (allocating, evict_last), cold around it (no_allocate)
+                    float v;
+                    if (cc[j] < tile_k) {
+                        if (MODE == M_L1MIX2_IDX) asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(x + cc[j]));
+                        else v = __ldg(x + cc[j]);
+                    } else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(x + cc[j]));
+                    acc += v;
+                }
                 else acc += __ldg(x + cc[j]);
             }
         }
@@ -131,12 +140,14 @@ int main(int argc, char **argv) {
     run<M_SMEM>("smem tile 48K floats", x, tex, n, tile_k, nullptr, gathers, out, 1024, 1, 0, sms);
     for (uint32_t hot : {0u, 300u, 540u, 700u, 850u})
         run<M_MIX>("mix smem/ldg (hash idx)", x, tex, n, tile_k, nullptr, gathers, out, 1024, 1, hot, sms);
-    for (uint32_t hot : {0u, 540u, 850u}) {
+    for (uint32_t hot : {0u, 460u, 540u, 850u}) {
         fill_idx<<<sms * 8, 256>>>(idx, gathers, n, tile_k, hot);
         CK(cudaDeviceSynchronize());
         run<M_LDG_IDX>("ldg, idx stream (uint4/lane)", x, tex, n, tile_k, reinterpret_cast<const uint4 *>(idx), gathers, out, 1024, 2, hot, sms);
         run<M_MIX_IDX>("mix smem/ldg, idx stream", x, tex, n, tile_k, reinterpret_cast<const uint4 *>(idx), gathers, out, 1024, 1, hot, sms);
         run<M_MIX_IDX>("mix smem/ldg, idx stream", x, tex, n, tile_k, reinterpret_cast<const uint4 *>(idx), gathers, out, 512, 1, hot, sms);
+        run<M_L1MIX_IDX>("L1 hot(ldg)/cold(no_alloc), idx", x, tex, n, tile_k, reinterpret_cast<const uint4 *>(idx), gathers, out, 1024, 2, hot, sms);
+        run<M_L1MIX2_IDX>("L1 hot(evict_last)/cold(no_alloc)", x, tex, n, tile_k, reinterpret_cast<const uint4 *>(idx), gathers, out, 1024, 2, hot, sms);
     }
     return 0;
 }

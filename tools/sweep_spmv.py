@@ -22,9 +22,9 @@ x = torch.from_numpy(x_host).to(dev)
 y = torch.zeros_like(x)
 alg_bytes = 8 * m.nnz + 4 * (rows + 1) + 4 * rows + 4 * rows
 
-configs = [dict(GLB_SPMV_RELABEL=0)] + [dict(GLB_SPMV_RELABEL=1, GLB_SPMV_TILE_K=k, GLB_SPMV_TILE_THREADS=t)
-                                         for k, t in [(0, 1024), (16384, 1024), (32768, 1024), (49152, 1024),
-                                                      (53248, 1024), (49152, 512), (49152, 768), (32768, 512)]]
+configs = [dict(GLB_SPMV_TILE_K=k, GLB_SPMV_CARVEOUT=c)
+           for k, c in [(0, 20), (16384, 20), (32768, 20), (40960, 20), (49152, 20), (40960, 10), (40960, 30), (49152, 10),
+                        (57344, 10)]]
 if len(sys.argv) > 2:
     configs = [eval(sys.argv[2])]
 ref = None
