@@ -16,7 +16,7 @@ Reported on one JSON line by rank 0:
   value        device-timed GTEPS, inputs resident in HBM (matrix 1.07 GB >> 126 MB L2, so every
                step streams it from HBM; the 16 MB x is meant to live in L2)
   e2e          GTEPS through glb_spmv_host with pinned HOST x / y: H2D x, kernels, D2H y per step
-  roofline     spmv_ws_kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  roofline     spmv_lane_kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline the reference's own compute_reference_results (oracle/_ref) on one host thread,
                on a bounded row sample of the same matrix (N = 1 only)
 `--impl reference` runs only that CPU path (the reference has no threading: 1 thread).
@@ -122,7 +122,8 @@ def workload_config(n_gpus):
                          "Zipf(0.9) column popularity, random column labels",
             "rows": ROWS, "nnz": NNZ, "semiring": "plus-times",
             "sharding": f"row-range x{n_gpus}, one NCCL allgather of y per step" if n_gpus > 1 else "none",
-            "l2": "matrix streams (1.07 GB) exceed the 126 MB L2 every step; no flush needed"}
+            "l2": "matrix streams (1.07 GB) exceed the 126 MB L2 every step; no flush needed",
+            "layout": "lane-segment chunks (<=1024 nnz / warp), hot columns packed into an L1-resident vector"}
 
 
 def run_reference(args, rank):
@@ -276,7 +277,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": "spmv_ws_kernel<plus-times>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "spmv_lane_kernel<plus-times>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fix / max(launches, 1)}
 
@@ -318,11 +319,13 @@ def main():
         if not ok:
             log("WARNING: GPU result differs from the CPU reference on the sample")
 
+    # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup
+    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0)
     if rank == 0:
         line = {"metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
                 "cpu_baseline": cpu, "y_checksum": checksum, "nnz": m.nnz}
         print(json.dumps(line), flush=True)
     if world > 1:

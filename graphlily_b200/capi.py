@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgraphlily_b200.so")
+LIB_PATH = os.environ.get("GLB_LIB_PATH") or os.path.join(_HERE, "lib", "libgraphlily_b200.so")   # env: tuning builds only
 
 OP_MUL_ADD, OP_LOGICAL_AND_OR, OP_ADD_MIN = 0, 1, 2
 MASK_NONE, MASK_WRITE_TO_ZERO, MASK_WRITE_TO_ONE = 0, 1, 2

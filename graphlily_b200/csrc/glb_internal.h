@@ -62,10 +62,10 @@ struct glb_ctx_s {
 // one) are finished by the fix-up kernel from per-chunk carries: see spmv.cu.
 #define GLB_GROUP 128u
 #define GLB_MAX_GROUPS 8
-#define GLB_ROW_CAP 256u
+#define GLB_ROW_CAP 128u
 #define GLB_FLAG 0x80000000u
 #define GLB_DEFAULT_TILE_K 40960u
-#define GLB_DEFAULT_CARVEOUT_PCT 20u
+#define GLB_DEFAULT_CARVEOUT_PCT 12u
 
 struct glb_fixup_t {
     uint32_t row;    // global row id

@@ -51,7 +51,13 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kPrefetch = 2;  // groups of the matrix stream in flight ahead of the one being reduced
+#ifndef GLB_SPMV_PREFETCH
+#define GLB_SPMV_PREFETCH 2
+#endif
+#ifndef GLB_SPMV_MIN_BLOCKS
+#define GLB_SPMV_MIN_BLOCKS 5
+#endif
+constexpr int kPrefetch = GLB_SPMV_PREFETCH;  // groups of the matrix stream in flight ahead of the one being reduced
 
 struct SpmvParams {
     const uint32_t *__restrict__ stream;       // 256 words per group: 128 encoded columns, 128 fp32 values
@@ -81,25 +87,8 @@ struct SpmvParams {
     uint32_t n_fix_short, n_fix_long, n_empty;
 };
 
-// Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
-// spmv_module.h:513-532), then the optional fused eWiseAdd and dense assign.
-template <int OP>
-__device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, float total) {
-    float v = Semi<OP>::with_zero(P.zero, total);
-    if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
-        if (P.mask[row] != 0.0f) v = 0.0f;
-    } else if (P.mask_type == GLB_MASK_WRITE_TO_ONE) {
-        if (P.mask[row] == 0.0f) v = 0.0f;
-    }
-    if (P.add_enable) v = __fadd_rn(v, P.add_val);
-    P.y[row] = v;
-    if (P.assign_inout) {
-        bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? (v != 0.0f) : (v == 0.0f);
-        if (hit) P.assign_inout[row] = P.assign_val;
-    }
-}
-
-// Matrix stream: read once, kept out of L1 so it cannot evict the hot x lines.
+// Everything that is read once (matrix stream, flags, row ids, mask) is kept out of L1 so it
+// cannot evict the hot x lines.
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
     uint4 v;
     asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -111,6 +100,30 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     uint32_t v;
     asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+}
+
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));  // mask may alias assign_inout: not .nc
+    return v;
+}
+
+// Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
+// spmv_module.h:513-532), then the optional fused eWiseAdd and dense assign.
+template <int OP>
+__device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, float total) {
+    float v = Semi<OP>::with_zero(P.zero, total);
+    if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
+        if (ld_stream_f32(P.mask + row) != 0.0f) v = 0.0f;
+    } else if (P.mask_type == GLB_MASK_WRITE_TO_ONE) {
+        if (ld_stream_f32(P.mask + row) == 0.0f) v = 0.0f;
+    }
+    if (P.add_enable) v = __fadd_rn(v, P.add_val);
+    P.y[row] = v;
+    if (P.assign_inout) {
+        bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? (v != 0.0f) : (v == 0.0f);
+        if (hit) P.assign_inout[row] = P.assign_val;
+    }
 }
 
 // x gather: hot column words (< tile_k) index the packed hot vector through L1 (allocating),
@@ -130,7 +143,7 @@ __device__ __forceinline__ float gather_x(const float *hot_x, const float *x_col
 
 // One chunk (up to 8 groups of 128 non-zeros) by one warp.
 template <int OP>
-__global__ void __launch_bounds__(kThreads) spmv_lane_kernel(const SpmvParams P) {
+__global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
@@ -138,8 +151,8 @@ __global__ void __launch_bounds__(kThreads) spmv_lane_kernel(const SpmvParams P)
     if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
     float *const stage = stage_all[wib];
 
-    const uint32_t g0 = __ldg(P.chunk_goff + chunk);
-    const int n = int(__ldg(P.chunk_goff + chunk + 1) - g0);  // 1 .. GLB_MAX_GROUPS, warp-uniform
+    const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
+    const int n = int(ld_stream_u32(P.chunk_goff + chunk + 1) - g0);  // 1 .. GLB_MAX_GROUPS, warp-uniform
     const uint4 *gp = reinterpret_cast<const uint4 *>(P.stream) + size_t(g0) * 64 + lane;
     uint4 cq[kPrefetch + 1], aq[kPrefetch + 1];
 #pragma unroll
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) spmv_lane_kernel(const SpmvParams P)
         }
     }
     const uint32_t fw = ld_stream_u32(P.flags + size_t(chunk) * 32 + lane);
-    const uint32_t cf = __ldg(P.chunk_first + chunk);
+    const uint32_t cf = ld_stream_u32(P.chunk_first + chunk);
 
     // ordinal of this lane's first row end = number of row ends in the lanes below
     const uint32_t cnt = __popc(fw);
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) spmv_lane_kernel(const SpmvParams P)
         if (k == 0 && !fresh) {
             P.head_carry[chunk] = val;  // row began in an earlier chunk
         } else {
-            finish_row<OP>(P, __ldg(P.nz_rows + ord0 + k), val);
+            finish_row<OP>(P, ld_stream_u32(P.nz_rows + ord0 + k), val);
         }
     }
 }

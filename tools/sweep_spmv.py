@@ -23,8 +23,7 @@ y = torch.zeros_like(x)
 alg_bytes = 8 * m.nnz + 4 * (rows + 1) + 4 * rows + 4 * rows
 
 configs = [dict(GLB_SPMV_TILE_K=k, GLB_SPMV_CARVEOUT=c)
-           for k, c in [(0, 20), (16384, 20), (32768, 20), (40960, 20), (49152, 20), (40960, 10), (40960, 30), (49152, 10),
-                        (57344, 10)]]
+           for k, c in [(40960, 8), (40960, 12), (40960, 16), (40960, 20), (45056, 12), (49152, 12), (49152, 16), (32768, 12)]]
 if len(sys.argv) > 2:
     configs = [eval(sys.argv[2])]
 ref = None
