@@ -1,0 +1,177 @@
+// graphlily-b200: level-synchronous BFS (pull, push, direction-optimising pull_push).
+//
+// Same class and method surface as /root/reference/graphlily/app/bfs.h:20-360 and the same
+// results: distance[source] = 1, a vertex reached in iteration k gets k + 1, unreached stays 0
+// (:108-110,123); matrix values forced to 1, dimensions padded to 128 (:84-97).  Differences in
+// HOW, not in what:
+//   * with fused() on (default) one pull level is ONE launch: the eWiseAdd copy and the dense
+//     assign of :117-124 ride in the SpMV write-back (glb_spmv_fused) and vector / results swap;
+//     set_fused(false) replays the reference's three launches per level literally;
+//   * the push loop swaps the two sparse lists instead of copying results -> vector (:147-151);
+//   * the push -> pull switch densifies the frontier on the device (glb_sparse_to_dense) instead of
+//     the host round trip of :195-201.
+// compute_reference_results (:350-360) is not in the product; the tests link oracle/ for it.
+#ifndef GRAPHLILY_BFS_H_
+#define GRAPHLILY_BFS_H_
+
+#include <utility>
+
+#include "graphlily/app/module_collection.h"
+#include "graphlily/io/data_formatter.h"
+#include "graphlily/io/data_loader.h"
+#include "graphlily/module/add_scalar_vector_dense_module.h"
+#include "graphlily/module/assign_vector_dense_module.h"
+#include "graphlily/module/assign_vector_sparse_module.h"
+#include "graphlily/module/spmspv_module.h"
+#include "graphlily/module/spmv_module.h"
+
+namespace graphlily {
+namespace app {
+
+using graphlily::io::CSCMatrix;
+using graphlily::io::CSRMatrix;
+
+class BFS : public app::ModuleCollection {
+private:
+    module::SpMVModule<graphlily::val_t, graphlily::val_t> *SpMV_;
+    module::AssignVectorDenseModule<graphlily::val_t> *DenseAssign_;
+    module::SpMSpVModule<graphlily::val_t, graphlily::val_t, graphlily::idx_val_t> *SpMSpV_;
+    module::AssignVectorSparseModule<graphlily::val_t, graphlily::idx_val_t> *SparseAssign_;
+    module::eWiseAddModule<graphlily::val_t> *eWiseAdd_;
+    uint32_t matrix_num_rows_ = 0, matrix_num_cols_ = 0;
+    uint32_t num_channels_, spmv_out_buf_len_, spmspv_out_buf_len_, vec_buf_len_;
+    graphlily::SemiringType semiring_ = graphlily::LogicalSemiring;
+    bool fused_ = true;
+    uint32_t push_iterations_ = 0;
+
+    using aligned_dense_vec_t = graphlily::aligned_dense_vec_t;
+    using aligned_sparse_vec_t = graphlily::aligned_sparse_vec_t;
+
+    void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
+        const uint32_t n = matrix_num_rows_;
+        if (fused_) {
+            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
+                glb_spmv_epilogue_t ep = {0, 0.0f, SpMV_->mask_buf.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
+                SpMV_->run_fused(&ep);
+                std::swap(SpMV_->vector_buf, SpMV_->results_buf);
+            }
+        } else {
+            DenseAssign_->bind_mask_buf(SpMV_->vector_buf);
+            DenseAssign_->bind_inout_buf(SpMV_->mask_buf);
+            eWiseAdd_->bind_in_buf(SpMV_->results_buf);
+            eWiseAdd_->bind_out_buf(SpMV_->vector_buf);
+            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
+                SpMV_->run();
+                eWiseAdd_->run(n, 0);
+                DenseAssign_->run(n, iter + 1);
+            }
+        }
+    }
+
+    void push_setup(uint32_t source) {
+        aligned_sparse_vec_t spmspv_input(2);
+        spmspv_input[0] = {1, 0};  // one source vertex
+        spmspv_input[1] = {source, 1};
+        aligned_dense_vec_t distance(matrix_num_rows_, 0);
+        distance[source] = 1;
+        SpMSpV_->send_vector_host_to_device(spmspv_input);
+        SpMSpV_->send_mask_host_to_device(distance);
+        SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
+    }
+
+    void push_step(uint32_t iter) {
+        SpMSpV_->run();
+        std::swap(SpMSpV_->vector_buf, SpMSpV_->results_buf);  // the new frontier is the next input
+        SparseAssign_->bind_mask_buf(SpMSpV_->vector_buf);
+        SparseAssign_->run(iter + 1);
+    }
+
+public:
+    BFS(uint32_t num_channels, uint32_t spmv_out_buf_len, uint32_t spmspv_out_buf_len, uint32_t vec_buf_len)
+        : num_channels_(num_channels), spmv_out_buf_len_(spmv_out_buf_len), spmspv_out_buf_len_(spmspv_out_buf_len),
+          vec_buf_len_(vec_buf_len) {
+        SpMV_ = new module::SpMVModule<graphlily::val_t, graphlily::val_t>(num_channels_, spmv_out_buf_len_, vec_buf_len_);
+        SpMV_->set_semiring(semiring_);
+        SpMV_->set_mask_type(graphlily::kMaskWriteToZero);
+        add_module(SpMV_);
+        DenseAssign_ = new module::AssignVectorDenseModule<graphlily::val_t>();
+        DenseAssign_->set_mask_type(graphlily::kMaskWriteToOne);
+        add_module(DenseAssign_);
+        SpMSpV_ = new module::SpMSpVModule<graphlily::val_t, graphlily::val_t, graphlily::idx_val_t>(spmspv_out_buf_len_);
+        SpMSpV_->set_semiring(semiring_);
+        SpMSpV_->set_mask_type(graphlily::kMaskWriteToZero);
+        add_module(SpMSpV_);
+        SparseAssign_ = new module::AssignVectorSparseModule<graphlily::val_t, graphlily::idx_val_t>(false);
+        add_module(SparseAssign_);
+        eWiseAdd_ = new module::eWiseAddModule<graphlily::val_t>();
+        add_module(eWiseAdd_);
+    }
+
+    void set_fused(bool fused) { fused_ = fused; }
+    uint32_t get_nnz() { return SpMV_->get_nnz(); }
+    uint32_t get_num_rows() { return matrix_num_rows_; }
+    uint32_t get_push_iterations() { return push_iterations_; }
+
+    void load_and_format_matrix(CSRMatrix<float> csr_matrix, bool skip_empty_rows) {
+        graphlily::io::util_round_csr_matrix_dim(csr_matrix, num_channels_ * graphlily::pack_size,
+                                                 num_channels_ * graphlily::pack_size);
+        for (auto &x : csr_matrix.adj_data) x = 1;
+        CSCMatrix<float> csc_matrix = graphlily::io::csr2csc(csr_matrix);
+        SpMV_->load_and_format_matrix(csr_matrix, skip_empty_rows);
+        SpMSpV_->load_and_format_matrix(csc_matrix);
+        matrix_num_rows_ = SpMV_->get_num_rows();
+        matrix_num_cols_ = SpMV_->get_num_cols();
+        assert(matrix_num_rows_ == matrix_num_cols_);
+    }
+    void load_and_format_matrix(std::string csr_float_npz_path, bool skip_empty_rows) {
+        load_and_format_matrix(graphlily::io::load_csr_matrix_from_float_npz(csr_float_npz_path), skip_empty_rows);
+    }
+
+    void send_matrix_host_to_device() {
+        SpMV_->send_matrix_host_to_device();
+        SpMSpV_->send_matrix_host_to_device();
+    }
+
+    aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
+        aligned_dense_vec_t input(matrix_num_rows_, semiring_.zero);
+        aligned_dense_vec_t distance(matrix_num_rows_, 0);
+        input[source] = 1;
+        distance[source] = 1;
+        SpMV_->send_vector_host_to_device(input);
+        SpMV_->send_mask_host_to_device(distance);
+        pull_loop(1, num_iterations);
+        return SpMV_->send_mask_device_to_host();
+    }
+
+    aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
+        push_setup(source);
+        for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);
+        return SpMSpV_->send_mask_device_to_host();
+    }
+
+    aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
+        const uint32_t n = matrix_num_rows_;
+        push_setup(source);
+        uint32_t iter = 1;
+        uint32_t vector_nnz;
+        do {
+            push_step(iter);
+            vector_nnz = SpMSpV_->get_vector_nnz();
+            iter++;
+        } while (iter < num_iterations && (float(vector_nnz) / n < threshold));
+        push_iterations_ = iter - 1;
+        // switch from push to pull: the last frontier becomes the dense SpMV input, on the device
+        SpMV_->bind_mask_buf(SpMSpV_->mask_buf);
+        if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
+            SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
+        GLB_CHECK(glb_sparse_to_dense(runtime_->ctx(), SpMSpV_->vector_buf.sparse(), SpMV_->vector_buf.f32(), n,
+                                      graphlily::LogicalSemiring.zero));
+        pull_loop(iter, num_iterations);
+        return SpMSpV_->send_mask_device_to_host();  // the mask of SpMV on the host is not valid
+    }
+};
+
+}  // namespace app
+}  // namespace graphlily
+
+#endif  // GRAPHLILY_BFS_H_

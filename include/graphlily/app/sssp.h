@@ -1,0 +1,200 @@
+// graphlily-b200: single-source shortest paths over the min-plus semiring (pull, push, pull_push).
+//
+// Same surface and results as /root/reference/graphlily/app/sssp.h:68-253: _preprocess (:16-62)
+// sets every weight to 1 and gives every row a zero-weight diagonal; dist0 = TropicalSemiring.zero
+// (255), dist[source] = 0; one iteration is dist <- A min.+ dist.  Unreached vertices stay exactly
+// 255 because min(255, 1 + 255) = 255.  The push -> pull switch copies the distance vector on the
+// device (:226-233 does the same with copy_buffer_device_to_device).
+#ifndef GRAPHLILY_SSSP_H_
+#define GRAPHLILY_SSSP_H_
+
+#include <utility>
+
+#include "graphlily/app/module_collection.h"
+#include "graphlily/io/data_formatter.h"
+#include "graphlily/io/data_loader.h"
+#include "graphlily/module/add_scalar_vector_dense_module.h"
+#include "graphlily/module/assign_vector_sparse_module.h"
+#include "graphlily/module/spmspv_module.h"
+#include "graphlily/module/spmv_module.h"
+
+namespace graphlily {
+namespace app {
+
+namespace detail {
+
+// sssp.h:16-62 in one O(nnz) pass with the same output as the reference's in-place insertions,
+// including its quirk: while walking row r it reads the row END from the not yet shifted indptr
+// (sssp.h:31-32), so after k insertions it scans only the first len - k entries of the row, treats
+// a row with len == k as empty, and inserts before the last scanned entry when no larger column
+// was seen (sssp.h:49-52).
+inline void sssp_preprocess(graphlily::io::CSRMatrix<float> &m) {
+    const uint32_t num_rows = uint32_t(m.adj_indptr.size() - 1);
+    std::vector<float> data;
+    std::vector<uint32_t> indices, indptr(size_t(num_rows) + 1, 0);
+    data.reserve(m.adj_data.size() + num_rows);
+    indices.reserve(m.adj_indices.size() + num_rows);
+    uint64_t k = 0;  // insertions so far
+    for (uint32_t r = 0; r < num_rows; r++) {
+        const uint64_t s = m.adj_indptr[r], e = m.adj_indptr[r + 1], len = e - s;
+        int64_t insert_at = -1, zero_at = -1;
+        if (len == k) {
+            insert_at = int64_t(s);
+        } else if (len > k) {
+            const uint64_t scan_end = e - k;
+            for (uint64_t i = s; i < scan_end; i++) {
+                const uint32_t c = m.adj_indices[i];
+                if (c == r) { zero_at = int64_t(i); break; }
+                if (c > r || i == scan_end - 1) { insert_at = int64_t(i); break; }
+            }
+        }
+        if (len == 0 && insert_at >= 0) {
+            indices.push_back(r);
+            data.push_back(0.0f);
+        }
+        for (uint64_t i = s; i < e; i++) {
+            if (insert_at == int64_t(i)) {
+                indices.push_back(r);
+                data.push_back(0.0f);
+            }
+            indices.push_back(m.adj_indices[i]);
+            data.push_back(zero_at == int64_t(i) ? 0.0f : 1.0f);
+        }
+        if (insert_at >= 0) k++;
+        indptr[r + 1] = uint32_t(indices.size());
+    }
+    m.adj_data.swap(data);
+    m.adj_indices.swap(indices);
+    m.adj_indptr.swap(indptr);
+}
+
+}  // namespace detail
+
+class SSSP : public app::ModuleCollection {
+private:
+    module::SpMVModule<graphlily::val_t, graphlily::val_t> *SpMV_;
+    module::SpMSpVModule<graphlily::val_t, graphlily::val_t, graphlily::idx_val_t> *SpMSpV_;
+    module::AssignVectorSparseModule<graphlily::val_t, graphlily::idx_val_t> *SparseAssign_;
+    module::eWiseAddModule<graphlily::val_t> *eWiseAdd_;
+    uint32_t matrix_num_rows_ = 0, matrix_num_cols_ = 0;
+    uint32_t num_channels_, spmv_out_buf_len_, spmspv_out_buf_len_, vec_buf_len_;
+    graphlily::SemiringType semiring_ = graphlily::TropicalSemiring;
+    bool fused_ = true;
+    uint32_t push_iterations_ = 0;
+    using aligned_dense_vec_t = graphlily::aligned_dense_vec_t;
+    using aligned_sparse_vec_t = graphlily::aligned_sparse_vec_t;
+
+    void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
+        if (fused_) {
+            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
+                SpMV_->run();
+                std::swap(SpMV_->vector_buf, SpMV_->results_buf);
+            }
+        } else {
+            eWiseAdd_->bind_in_buf(SpMV_->results_buf);
+            eWiseAdd_->bind_out_buf(SpMV_->vector_buf);
+            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
+                SpMV_->run();
+                eWiseAdd_->run(matrix_num_rows_, 0);
+            }
+        }
+    }
+
+    void push_setup(uint32_t source) {
+        aligned_sparse_vec_t spmspv_input(2);
+        spmspv_input[0] = {1, 0};
+        spmspv_input[1] = {source, 0};
+        aligned_dense_vec_t distance(matrix_num_rows_, semiring_.zero);
+        distance[source] = 0;
+        SpMSpV_->send_vector_host_to_device(spmspv_input);
+        SpMSpV_->send_mask_host_to_device(distance);
+        SparseAssign_->bind_mask_buf(SpMSpV_->results_buf);
+        SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
+        SparseAssign_->bind_new_frontier_buf(SpMSpV_->vector_buf);
+    }
+
+public:
+    SSSP(uint32_t num_channels, uint32_t spmv_out_buf_len, uint32_t spmspv_out_buf_len, uint32_t vec_buf_len)
+        : num_channels_(num_channels), spmv_out_buf_len_(spmv_out_buf_len), spmspv_out_buf_len_(spmspv_out_buf_len),
+          vec_buf_len_(vec_buf_len) {
+        SpMV_ = new module::SpMVModule<graphlily::val_t, graphlily::val_t>(num_channels_, spmv_out_buf_len_, vec_buf_len_);
+        SpMV_->set_semiring(semiring_);
+        SpMV_->set_mask_type(graphlily::kNoMask);
+        add_module(SpMV_);
+        SpMSpV_ = new module::SpMSpVModule<graphlily::val_t, graphlily::val_t, graphlily::idx_val_t>(spmspv_out_buf_len_);
+        SpMSpV_->set_semiring(semiring_);
+        SpMSpV_->set_mask_type(graphlily::kNoMask);
+        add_module(SpMSpV_);
+        SparseAssign_ = new module::AssignVectorSparseModule<graphlily::val_t, graphlily::idx_val_t>(true);
+        add_module(SparseAssign_);
+        eWiseAdd_ = new module::eWiseAddModule<graphlily::val_t>();
+        add_module(eWiseAdd_);
+    }
+
+    void set_fused(bool fused) { fused_ = fused; }
+    uint32_t get_nnz() { return SpMV_->get_nnz(); }
+    uint32_t get_num_rows() { return matrix_num_rows_; }
+    uint32_t get_push_iterations() { return push_iterations_; }
+
+    void load_and_format_matrix(graphlily::io::CSRMatrix<float> csr_matrix, bool skip_empty_rows) {
+        detail::sssp_preprocess(csr_matrix);
+        graphlily::io::util_round_csr_matrix_dim(csr_matrix, num_channels_ * graphlily::pack_size,
+                                                 num_channels_ * graphlily::pack_size);
+        graphlily::io::CSCMatrix<float> csc_matrix = graphlily::io::csr2csc(csr_matrix);
+        SpMV_->load_and_format_matrix(csr_matrix, skip_empty_rows);
+        SpMSpV_->load_and_format_matrix(csc_matrix);
+        matrix_num_rows_ = SpMV_->get_num_rows();
+        matrix_num_cols_ = SpMV_->get_num_cols();
+        assert(matrix_num_rows_ == matrix_num_cols_);
+    }
+    void load_and_format_matrix(std::string csr_float_npz_path, bool skip_empty_rows) {
+        load_and_format_matrix(graphlily::io::load_csr_matrix_from_float_npz(csr_float_npz_path), skip_empty_rows);
+    }
+
+    void send_matrix_host_to_device() {
+        SpMV_->send_matrix_host_to_device();
+        SpMSpV_->send_matrix_host_to_device();
+    }
+
+    aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
+        aligned_dense_vec_t input(matrix_num_rows_, semiring_.zero);
+        input[source] = 0;
+        SpMV_->send_vector_host_to_device(input);
+        pull_loop(1, num_iterations);
+        return SpMV_->send_vector_device_to_host();
+    }
+
+    aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
+        push_setup(source);
+        for (uint32_t iter = 1; iter <= num_iterations; iter++) {
+            SpMSpV_->run();
+            SparseAssign_->run();
+        }
+        return SpMSpV_->send_mask_device_to_host();
+    }
+
+    aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
+        const uint32_t n = matrix_num_rows_;
+        push_setup(source);
+        uint32_t iter = 1;
+        uint32_t vector_nnz;
+        do {
+            SpMSpV_->run();
+            SparseAssign_->run();
+            vector_nnz = SpMSpV_->get_results_nnz();
+            iter++;
+        } while (iter < num_iterations && (float(vector_nnz) / n < threshold));
+        push_iterations_ = iter - 1;
+        // switch from push to pull: the distance vector becomes the SpMV input (device copy)
+        if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
+            SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
+        SpMV_->copy_buffer_device_to_device(SpMSpV_->mask_buf, SpMV_->vector_buf, sizeof(graphlily::val_t) * n);
+        pull_loop(iter, num_iterations);
+        return SpMV_->send_vector_device_to_host();
+    }
+};
+
+}  // namespace app
+}  // namespace graphlily
+
+#endif  // GRAPHLILY_SSSP_H_

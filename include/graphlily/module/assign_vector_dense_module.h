@@ -1,0 +1,64 @@
+// graphlily-b200: masked scalar assign into a dense vector.
+//
+// Same public surface as /root/reference/graphlily/module/assign_vector_dense_module.h:17-164;
+// run() becomes glb_assign_dense.  kNoMask is an error: the reference prints and exits (:88-95).
+#ifndef GRAPHLILY_ASSIGN_VECTOR_DENSE_MODULE_H_
+#define GRAPHLILY_ASSIGN_VECTOR_DENSE_MODULE_H_
+
+#include "graphlily/global.h"
+#include "graphlily/module/base_module.h"
+
+namespace graphlily {
+namespace module {
+
+template <typename vector_data_t>
+class AssignVectorDenseModule : public BaseModule {
+private:
+    graphlily::MaskType mask_type_ = graphlily::kNoMask;
+    using aligned_dense_vec_t = std::vector<vector_data_t, aligned_allocator<vector_data_t>>;
+    aligned_dense_vec_t mask_, inout_;
+
+public:
+    // Device buffers
+    DeviceBuffer mask_buf;
+    DeviceBuffer inout_buf;
+
+    AssignVectorDenseModule() : BaseModule("overlay") {}
+
+    void set_mask_type(graphlily::MaskType mask_type) {
+        if (mask_type == graphlily::kNoMask) {
+            std::cerr << "Please set the mask type" << std::endl;
+            exit(EXIT_FAILURE);
+        }
+        mask_type_ = mask_type;
+    }
+
+    void send_mask_host_to_device(aligned_dense_vec_t &mask) {
+        mask_ = mask;
+        mask_buf = upload(mask_);
+    }
+    void send_inout_host_to_device(aligned_dense_vec_t &inout) {
+        inout_ = inout;
+        inout_buf = upload(inout_);
+    }
+    void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
+    void bind_inout_buf(DeviceBuffer src_buf) { inout_buf = src_buf; }
+
+    void run(uint32_t len, vector_data_t val) {
+        GLB_CHECK(glb_assign_dense(ctx(), mask_buf.f32(), inout_buf.f32(), len, val, mask_type_));
+    }
+
+    aligned_dense_vec_t send_mask_device_to_host() {
+        download(mask_, mask_buf, mask_buf.bytes() / sizeof(vector_data_t));
+        return mask_;
+    }
+    aligned_dense_vec_t send_inout_device_to_host() {
+        download(inout_, inout_buf, inout_buf.bytes() / sizeof(vector_data_t));
+        return inout_;
+    }
+};
+
+}  // namespace module
+}  // namespace graphlily
+
+#endif  // GRAPHLILY_ASSIGN_VECTOR_DENSE_MODULE_H_

@@ -1,0 +1,111 @@
+// graphlily-b200: SpMSpV operator module, sparse y = A[:, idx(x)] (+).(x) x with a dense mask.
+//
+// Same public surface as /root/reference/graphlily/module/spmspv_module.h:26-254.  formatCSC +
+// upload (:264-370) becomes glb_csc_create; run() (:437-441) becomes glb_spmspv; get_results_nnz
+// (:239-242) reads slot 0 of the result list.  Vectors follow the sparse convention of global.h:
+// element 0 = {nnz, -}.
+#ifndef GRAPHLILY_SPMSPV_MODULE_H_
+#define GRAPHLILY_SPMSPV_MODULE_H_
+
+#include <type_traits>
+
+#include "graphlily/global.h"
+#include "graphlily/io/data_loader.h"
+#include "graphlily/module/base_module.h"
+
+namespace graphlily {
+namespace module {
+
+using graphlily::io::CSCMatrix;
+
+template <typename matrix_data_t, typename vector_data_t, typename idx_val_t>
+class SpMSpVModule : public BaseModule {
+    static_assert(std::is_same<matrix_data_t, float>::value && std::is_same<vector_data_t, float>::value,
+                  "graphlily-b200 computes in fp32 (val_t = float)");
+    static_assert(sizeof(idx_val_t) == sizeof(glb_idx_val_t), "idx_val_t must match the C ABI");
+private:
+    graphlily::MaskType mask_type_ = graphlily::kNoMask;
+    graphlily::SemiringType semiring_ = graphlily::ArithmeticSemiring;
+    uint32_t out_buf_len_;  // FPGA tuning argument: accepted, unused
+    using aligned_dense_vec_t = std::vector<vector_data_t, aligned_allocator<vector_data_t>>;
+    using aligned_sparse_vec_t = std::vector<idx_val_t, aligned_allocator<idx_val_t>>;
+    aligned_sparse_vec_t vector_, results_;
+    aligned_dense_vec_t mask_;
+    CSCMatrix<float> csc_matrix_float_;
+    glb_csc_t matrix_ = nullptr;
+
+    uint32_t count_of(const DeviceBuffer &list) {
+        uint32_t n = 0;
+        GLB_CHECK(glb_sparse_count(ctx(), list.sparse(), &n));
+        return n;
+    }
+
+public:
+    // Device buffers
+    DeviceBuffer vector_buf;
+    DeviceBuffer mask_buf;
+    DeviceBuffer results_buf;
+
+    explicit SpMSpVModule(uint32_t out_buf_len) : BaseModule("overlay"), out_buf_len_(out_buf_len) {}
+    ~SpMSpVModule() override { glb_csc_destroy(matrix_); }
+
+    uint32_t get_num_rows() { return csc_matrix_float_.num_rows; }
+    uint32_t get_num_cols() { return csc_matrix_float_.num_cols; }
+    uint32_t get_nnz() { return csc_matrix_float_.adj_indptr[csc_matrix_float_.num_cols]; }
+    void set_semiring(graphlily::SemiringType semiring) { semiring_ = semiring; }
+    void set_mask_type(graphlily::MaskType mask_type) { mask_type_ = mask_type; }
+
+    void load_and_format_matrix(CSCMatrix<float> const &csc_matrix_float) { csc_matrix_float_ = csc_matrix_float; }
+
+    // Matrix upload + the result (rows + 1) and vector (cols + 1) lists, spmspv_module.h:290-370.
+    void send_matrix_host_to_device() {
+        const CSCMatrix<float> &m = csc_matrix_float_;
+        glb_csc_destroy(matrix_);
+        matrix_ = nullptr;
+        GLB_CHECK(glb_csc_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
+                                 m.adj_data.data(), &matrix_));
+        aligned_sparse_vec_t empty_rows(size_t(m.num_rows) + 1, idx_val_t{0, 0});
+        aligned_sparse_vec_t empty_cols(size_t(m.num_cols) + 1, idx_val_t{0, 0});
+        results_buf = upload(empty_rows);
+        vector_buf = upload(empty_cols);
+    }
+
+    void send_vector_host_to_device(aligned_sparse_vec_t &vector) {
+        vector_ = vector;
+        if (!vector_buf.valid() || vector_buf.bytes() < vector_.size() * sizeof(idx_val_t))
+            vector_buf = DeviceBuffer(runtime_, vector_.size() * sizeof(idx_val_t));
+        GLB_CHECK(glb_buffer_h2d(ctx(), vector_buf.ptr(), vector_.data(), vector_.size() * sizeof(idx_val_t)));
+    }
+    void send_mask_host_to_device(aligned_dense_vec_t &mask) {
+        mask_ = mask;
+        mask_buf = upload(mask_);
+    }
+    void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
+
+    void run() {
+        GLB_CHECK(glb_spmspv(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.sparse(),
+                             mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.sparse()));
+    }
+
+    aligned_sparse_vec_t send_vector_device_to_host() {
+        download(vector_, vector_buf, size_t(count_of(vector_buf)) + 1);
+        return vector_;
+    }
+    aligned_dense_vec_t send_mask_device_to_host() {
+        download(mask_, mask_buf, get_num_rows());
+        return mask_;
+    }
+    aligned_sparse_vec_t send_results_device_to_host() {
+        download(results_, results_buf, size_t(count_of(results_buf)) + 1);
+        return results_;
+    }
+    uint32_t get_results_nnz() { return count_of(results_buf); }
+    uint32_t get_vector_nnz() { return count_of(vector_buf); }
+
+    CSCMatrix<float> const &host_matrix() { return csc_matrix_float_; }
+};
+
+}  // namespace module
+}  // namespace graphlily
+
+#endif  // GRAPHLILY_SPMSPV_MODULE_H_

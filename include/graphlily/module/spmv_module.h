@@ -1,0 +1,110 @@
+// graphlily-b200: SpMV operator module, y = A (+).(x) x with an optional dense mask.
+//
+// Same public surface as /root/reference/graphlily/module/spmv_module.h:26-272 (constructor
+// arguments, set_semiring / set_mask_type, load_and_format_matrix, send_*_host_to_device,
+// bind_mask_buf, run, send_*_device_to_host, public vector_buf / mask_buf / results_buf).  The CPSR
+// formatting + 16-channel upload (:282-420) becomes glb_csr_create (lane-segment layout); run()
+// (:471-475: setArg + enqueueTask + finish) becomes glb_spmv on the runtime's stream -- it returns
+// without synchronising, every send_*_device_to_host synchronises.
+// compute_reference_results (:478-532) is not part of the product: the CPU restatement lives in
+// oracle/ and is linked by the tests only.
+#ifndef GRAPHLILY_SPMV_MODULE_H_
+#define GRAPHLILY_SPMV_MODULE_H_
+
+#include <type_traits>
+
+#include "graphlily/global.h"
+#include "graphlily/io/data_loader.h"
+#include "graphlily/module/base_module.h"
+
+namespace graphlily {
+namespace module {
+
+using graphlily::io::CSRMatrix;
+
+template <typename matrix_data_t, typename vector_data_t>
+class SpMVModule : public BaseModule {
+    static_assert(std::is_same<matrix_data_t, float>::value && std::is_same<vector_data_t, float>::value,
+                  "graphlily-b200 computes in fp32 (val_t = float)");
+private:
+    graphlily::MaskType mask_type_ = graphlily::kNoMask;
+    graphlily::SemiringType semiring_ = graphlily::ArithmeticSemiring;
+    uint32_t num_channels_, out_buf_len_, vec_buf_len_;  // FPGA tuning arguments: accepted, unused
+    using aligned_dense_vec_t = std::vector<vector_data_t, aligned_allocator<vector_data_t>>;
+    aligned_dense_vec_t vector_, mask_, results_;
+    CSRMatrix<float> csr_matrix_float_;
+    glb_csr_t matrix_ = nullptr;
+
+public:
+    // Device buffers
+    DeviceBuffer vector_buf;
+    DeviceBuffer mask_buf;
+    DeviceBuffer results_buf;
+
+    SpMVModule(uint32_t num_channels, uint32_t out_buf_len, uint32_t vec_buf_len)
+        : BaseModule("overlay"), num_channels_(num_channels), out_buf_len_(out_buf_len), vec_buf_len_(vec_buf_len) {}
+    ~SpMVModule() override { glb_csr_destroy(matrix_); }
+
+    void set_semiring(graphlily::SemiringType semiring) { semiring_ = semiring; }
+    void set_mask_type(graphlily::MaskType mask_type) { mask_type_ = mask_type; }
+    uint32_t get_num_rows() { return csr_matrix_float_.num_rows; }
+    uint32_t get_num_cols() { return csr_matrix_float_.num_cols; }
+    uint32_t get_nnz() { return csr_matrix_float_.adj_indptr[csr_matrix_float_.num_rows]; }
+
+    // skip_empty_rows is a CPSR option (spmv_module.h:306-312); the lane-segment layout always
+    // keeps empty rows out of the nnz stream.
+    void load_and_format_matrix(CSRMatrix<float> const &csr_matrix_float, bool /*skip_empty_rows*/) {
+        csr_matrix_float_ = csr_matrix_float;
+    }
+
+    // Builds the device layout for rows [row_begin, row_end) (default: all) and uploads it.
+    void send_matrix_host_to_device(uint32_t row_begin = 0, uint32_t row_end = 0xffffffffu) {
+        const CSRMatrix<float> &m = csr_matrix_float_;
+        if (row_end == 0xffffffffu) row_end = m.num_rows;
+        glb_csr_destroy(matrix_);
+        matrix_ = nullptr;
+        GLB_CHECK(glb_csr_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
+                                 m.adj_data.data(), row_begin, row_end, &matrix_));
+        results_buf = DeviceBuffer(runtime_, sizeof(vector_data_t) * m.num_rows);
+        GLB_CHECK(glb_buffer_fill_f32(ctx(), results_buf.f32(), 0.0f, m.num_rows));
+    }
+
+    void send_vector_host_to_device(aligned_dense_vec_t &vector) {
+        vector_ = vector;
+        vector_buf = upload(vector_);
+    }
+    void send_mask_host_to_device(aligned_dense_vec_t &mask) {
+        mask_ = mask;
+        mask_buf = upload(mask_);
+    }
+    void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
+
+    void run() { run_fused(nullptr); }
+
+    // One launch for SpMV + the eWiseAdd / dense assign the apps run right after it (glb_spmv_fused).
+    void run_fused(const glb_spmv_epilogue_t *epilogue) {
+        GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.f32(),
+                                 mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.f32(), epilogue));
+    }
+
+    aligned_dense_vec_t send_vector_device_to_host() {
+        download(vector_, vector_buf, get_num_cols());
+        return vector_;
+    }
+    aligned_dense_vec_t send_mask_device_to_host() {
+        download(mask_, mask_buf, get_num_rows());
+        return mask_;
+    }
+    aligned_dense_vec_t send_results_device_to_host() {
+        download(results_, results_buf, get_num_rows());
+        return results_;
+    }
+
+    glb_csr_t device_matrix() { return matrix_; }
+    CSRMatrix<float> const &host_matrix() { return csr_matrix_float_; }
+};
+
+}  // namespace module
+}  // namespace graphlily
+
+#endif  // GRAPHLILY_SPMV_MODULE_H_

@@ -1,0 +1,99 @@
+// CPU-only tests of the host IO layer (include/graphlily/io), restating the golden vectors of the
+// reference's tests/test_io.cpp (create_csr_matrix :68-80, npz load :83-93, convert :96-107, csr2csc
+// :110-118, round dim :121-130, normalise :133-140) and pinning sssp_preprocess to the oracle.
+#include "graphlily/app/sssp.h"
+#include "test_util.h"
+
+static CSRMatrix<float> csr_matrix_1() {  // [[1,2,3,4],[5,0,6,0],[0,7,0,0],[0,0,0,8]]
+    return graphlily::io::create_csr_matrix<float>(4, 4, {1, 2, 3, 4, 5, 6, 7, 8}, {0, 1, 2, 3, 0, 2, 1, 3}, {0, 4, 6, 7, 8});
+}
+
+TEST(DataLoader, CreateCSRMatrix) {
+    auto m = csr_matrix_1();
+    EXPECT_EQ(m.num_rows, 4u);
+    EXPECT_EQ(m.adj_indptr.size(), 5u);
+    EXPECT_EQ(m.adj_data[7], 8.0f);
+}
+
+TEST(DataLoader, LoadCSRMatrixFromFloatNpz) {
+    const char *dir = getenv("GLB_TEST_DATA");
+    std::string base = dir ? dir : "tests/golden";
+    auto eye = graphlily::io::load_csr_matrix_from_float_npz(base + "/eye_10_csr_float32.npz");
+    ASSERT_EQ(eye.num_rows, 10u);
+    ASSERT_EQ(eye.num_cols, 10u);
+    ASSERT_EQ(eye.adj_data.size(), 10u);
+    for (uint32_t i = 0; i < 10; i++) {
+        EXPECT_EQ(eye.adj_data[i], 1.0f);
+        EXPECT_EQ(eye.adj_indices[i], i);
+        EXPECT_EQ(eye.adj_indptr[i], i);
+    }
+    auto line = graphlily::io::load_csr_matrix_from_float_npz(base + "/line_8_csr_float32.npz");
+    ASSERT_EQ(line.num_rows, 8u);
+    ASSERT_EQ(line.adj_indices.size(), 7u);
+    for (uint32_t i = 0; i < 7; i++) EXPECT_EQ(line.adj_indices[i], i);
+    EXPECT_EQ(line.adj_indptr[1], 0u);
+    EXPECT_EQ(line.adj_indptr[8], 7u);
+}
+
+TEST(DataLoader, Csr2Csc) {
+    auto csc = graphlily::io::csr2csc(csr_matrix_1());
+    std::vector<float> data = {1, 5, 2, 7, 3, 6, 4, 8};
+    std::vector<uint32_t> indices = {0, 1, 0, 2, 0, 1, 0, 3}, indptr = {0, 2, 4, 6, 8};
+    EXPECT_TRUE(csc.adj_data == data);
+    EXPECT_TRUE(csc.adj_indices == indices);
+    EXPECT_TRUE(csc.adj_indptr == indptr);
+}
+
+TEST(DataFormatter, RoundCSRMatrixDim) {
+    auto m = csr_matrix_1();
+    graphlily::io::util_round_csr_matrix_dim(m, 3, 5);
+    EXPECT_EQ(m.num_rows, 6u);
+    EXPECT_EQ(m.num_cols, 5u);
+    std::vector<uint32_t> indptr = {0, 4, 6, 7, 8, 8, 8};
+    EXPECT_TRUE(m.adj_indptr == indptr);
+}
+
+TEST(DataFormatter, NormalizeCSRMatrixByOutdegree) {
+    auto m = csr_matrix_1();
+    graphlily::io::util_normalize_csr_matrix_by_outdegree(m);
+    std::vector<float> expect = {0.5f, 0.5f, 0.5f, 0.5f, 0.5f, 0.5f, 0.5f, 0.5f};
+    EXPECT_TRUE(m.adj_data == expect);
+}
+
+TEST(DataFormatter, MatchesOracleOnRandomMatrices) {
+    for (uint32_t seed = 1; seed <= 4; seed++) {
+        auto m = skewed_csr(700 + 13 * seed, seed);
+        // csr2csc
+        auto csc = graphlily::io::csr2csc(m);
+        std::vector<uint32_t> ip(m.num_cols + 1), ix(m.adj_indices.size());
+        std::vector<float> d(m.adj_data.size());
+        oracle_csr2csc(m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(), m.adj_data.data(), ip.data(),
+                       ix.data(), d.data());
+        EXPECT_TRUE(csc.adj_indptr == ip && csc.adj_indices == ix && csc.adj_data == d);
+        // normalise
+        auto n1 = m;
+        graphlily::io::util_normalize_csr_matrix_by_outdegree(n1);
+        auto d2 = m.adj_data;
+        oracle_normalize_outdegree(m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(), d2.data());
+        EXPECT_TRUE(n1.adj_data == d2);
+        // SSSP preprocess (with and without existing diagonals)
+        auto p = m;
+        graphlily::app::detail::sssp_preprocess(p);
+        std::vector<uint32_t> oip(m.num_rows + 1), oix(m.adj_indices.size() + m.num_rows);
+        std::vector<float> od(oix.size());
+        int64_t w = oracle_sssp_preprocess(m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
+                                           m.adj_data.data(), oip.data(), oix.data(), od.data());
+        oix.resize(size_t(w));
+        od.resize(size_t(w));
+        EXPECT_TRUE(p.adj_indptr == oip && p.adj_indices == oix && p.adj_data == od);
+    }
+}
+
+TEST(Global, ConvertSparseVecToDenseVec) {
+    sparse_t s = {{2, 0}, {3, 7.0f}, {0, 5.0f}};
+    auto d = graphlily::convert_sparse_vec_to_dense_vec<sparse_t, dense_t, float>(s, 5, 255.0f);
+    dense_t expect = {5.0f, 255.0f, 255.0f, 7.0f, 255.0f};
+    EXPECT_TRUE(d == expect);
+}
+
+MINI_TEST_MAIN
