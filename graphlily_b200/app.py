@@ -49,6 +49,25 @@ class ModuleCollection:
         for m in self.modules_:
             m.set_context(self.ctx)
 
+    # -- multi-GPU: row-range sharding of the pull (SpMV) direction, SURVEY.md 8e -------------
+    rank_, world_ = 0, 1
+
+    def set_sharding(self, rank, world):
+        """This process owns rows [rank, rank + 1) * N / world of the CSR; the context must already
+        hold an NCCL communicator of ``world`` ranks (``ctx.comm_init``).  After every SpMV the
+        full-length result is completed by one in-place allgather (``_exchange``)."""
+        assert 0 <= rank < world
+        self.rank_, self.world_ = rank, world
+
+    def _row_range(self, n):
+        assert n % self.world_ == 0, "padded dimension must divide by the number of ranks"
+        slot = n // self.world_
+        return self.rank_ * slot, (self.rank_ + 1) * slot
+
+    def _exchange(self, buf, n):
+        if self.world_ > 1:
+            self.ctx.allgather_f32(buf, n // self.world_)
+
 
 def _load(path_or_csr):
     if isinstance(path_or_csr, str):
@@ -94,8 +113,9 @@ class BFS(ModuleCollection):
         assert m.num_rows == m.num_cols
 
     def send_matrix_host_to_device(self):
-        self.SpMV_.send_matrix_host_to_device()
-        self.SpMSpV_.send_matrix_host_to_device()
+        self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
+        if self.world_ == 1:   # the push direction is single-GPU in this round
+            self.SpMSpV_.send_matrix_host_to_device()
 
     # -- pull ------------------------------------------------------------------------
     def _pull_loop(self, first_iter, num_iterations, fused):
@@ -104,8 +124,10 @@ class BFS(ModuleCollection):
             for it in range(first_iter, num_iterations + 1):
                 ep = Epilogue(0, 0.0, self.SpMV_.mask_buf.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE)
                 self.SpMV_.run(ep)
+                self._exchange(self.SpMV_.results_buf, n)   # distance stays row-local until the end
                 self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
         else:
+            assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.DenseAssign_.bind_mask_buf(self.SpMV_.vector_buf)
             self.DenseAssign_.bind_inout_buf(self.SpMV_.mask_buf)
             self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
@@ -125,6 +147,7 @@ class BFS(ModuleCollection):
         self.SpMV_.send_vector_host_to_device(inp)
         self.SpMV_.send_mask_host_to_device(distance)
         self._pull_loop(1, num_iterations, fused)
+        self._exchange(self.SpMV_.mask_buf, n)
         return self.SpMV_.send_mask_device_to_host()
 
     # -- push ------------------------------------------------------------------------
@@ -200,8 +223,8 @@ class PageRank(ModuleCollection):
         self.matrix_num_rows_, self.matrix_num_cols_ = m.num_rows, m.num_cols
         assert m.num_rows == m.num_cols
 
-    def send_matrix_host_to_device(self, row_begin=0, row_end=None):
-        self.SpMV_.send_matrix_host_to_device(row_begin, row_end)
+    def send_matrix_host_to_device(self):
+        self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
 
     def pull(self, damping, num_iterations, fused=True):
         """pagerank.h:80-90"""
@@ -212,8 +235,10 @@ class PageRank(ModuleCollection):
         if fused:
             for _ in range(num_iterations):
                 self.SpMV_.run(Epilogue(1, teleport, None, 0.0, 0))
+                self._exchange(self.SpMV_.results_buf, n)
                 self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
         else:
+            assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
             self.eWiseAdd_.bind_out_buf(self.SpMV_.vector_buf)
             for _ in range(num_iterations):
@@ -257,16 +282,19 @@ class SSSP(ModuleCollection):
         assert m.num_rows == m.num_cols
 
     def send_matrix_host_to_device(self):
-        self.SpMV_.send_matrix_host_to_device()
-        self.SpMSpV_.send_matrix_host_to_device()
+        self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
+        if self.world_ == 1:   # the push direction is single-GPU in this round
+            self.SpMSpV_.send_matrix_host_to_device()
 
     def _pull_loop(self, first_iter, num_iterations, fused):
         n = self.matrix_num_rows_
         if fused:
             for _ in range(first_iter, num_iterations + 1):
                 self.SpMV_.run()
+                self._exchange(self.SpMV_.results_buf, n)
                 self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
         else:
+            assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
             self.eWiseAdd_.bind_out_buf(self.SpMV_.vector_buf)
             for _ in range(first_iter, num_iterations + 1):

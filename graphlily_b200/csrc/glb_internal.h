@@ -41,6 +41,10 @@ struct glb_ctx_s {
     // optional per-kernel timing (glb_ctx_kernel_timing): event triples of timed launches
     bool timing = false;
     std::vector<cudaEvent_t> timing_events;  // 3 per launch: before main, after main, after fix-up
+    // page-locked bounce buffer for blocking copies from / to pageable host memory (two slots)
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 // ---------------------------------------------------------------- lane-segment CSR (SpMV)

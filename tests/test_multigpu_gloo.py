@@ -1,0 +1,85 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): row-range sharding + one allgather per iteration.
+
+No GPU here, so the per-rank SpMV is the sequential model of the kernel schedule
+(tests/layout_model.py) run over the rank's own shard layout (``glb_csr_format_host`` with a row
+range); what is under test is the partition (``ModuleCollection._row_range``), that shard layouts
+keep GLOBAL row ids and write only their slice, and that an in-place allgather of equal slots
+rebuilds the full next-iteration vector -- the protocol ``bench.py --gpus N`` and
+``app.PageRank.set_sharding`` run with NCCL on the GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from graphlily_b200 import capi, datasets
+    from graphlily_b200.app import ModuleCollection
+    from layout_model import run_model
+
+    m = datasets.powerlaw_csr(2048, 2048, 40000, seed=9, max_degree=3000)   # same seed on every rank
+    mc = ModuleCollection()
+    mc.set_sharding(rank, world)
+    rb, re = mc._row_range(m.num_rows)
+    assert (re - rb) * world == m.num_rows
+    L = capi.format_host(m, rb, re, tile_k=64)
+    assert L["nnz"] == int(m.indptr[re]) - int(m.indptr[rb])
+    x = np.full(m.num_cols, np.float32(1.0 / m.num_cols), np.float32)
+    for _ in range(3):   # three PageRank-shaped iterations: x <- A x + c
+        y, written = run_model(L, x, 0, 0.0, m.num_rows)
+        assert written[rb:re].all() and not written[:rb].any() and not written[re:].any()
+        full = torch.zeros(m.num_rows, dtype=torch.float32)
+        full[rb:re] = torch.from_numpy(y[rb:re] + np.float32(1e-4))
+        slots = list(full.view(world, -1).unbind(0))           # in-place allgather of equal slots
+        dist.all_gather(slots, full[rb:re].clone())
+        x = full.numpy().copy()
+    np.save(os.path.join(out_dir, f"x{rank}.npy"), x)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_iterations_match_oracle(tmp_path, oracle):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, ROOT)
+    from graphlily_b200 import datasets
+    m = datasets.powerlaw_csr(2048, 2048, 40000, seed=9, max_degree=3000)
+    x = np.full(m.num_cols, np.float32(1.0 / m.num_cols), np.float32)
+    for _ in range(3):
+        x = oracle.port.spmv(m, 0, 0.0, 0, x) + np.float32(1e-4)
+    got = [np.load(tmp_path / f"x{r}.npy") for r in range(world)]
+    assert np.array_equal(got[0], got[1])                      # every rank holds the same full vector
+    assert np.allclose(got[0], x, rtol=1e-5, atol=1e-9)
+
+
+def test_row_range_partition():
+    sys.path.insert(0, ROOT)
+    from graphlily_b200.app import ModuleCollection
+    for world in (1, 2, 4, 8):
+        seen = []
+        for rank in range(world):
+            mc = ModuleCollection()
+            mc.set_sharding(rank, world)
+            seen.append(mc._row_range(2_449_024))
+        assert seen[0][0] == 0 and seen[-1][1] == 2_449_024
+        assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    mc = ModuleCollection()
+    mc.set_sharding(1, 8)
+    with pytest.raises(AssertionError):
+        mc._row_range(1001)
