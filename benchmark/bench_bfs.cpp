@@ -1,0 +1,39 @@
+// BFS: the flow of /root/reference/benchmark/bench_bfs.cpp:35-90 (pull, then pull-push with
+// threshold 0.001; GTEPS = nnz * iterations / seconds, computed in 64 bits -- the reference's
+// uint32 product overflows on large graphs, :69).
+#include "bench_common.h"
+#include "graphlily/app/bfs.h"
+
+int main(int argc, char *argv[]) {
+    BenchArgs args = parse_args(argc, argv, "bench_bfs [tuning ints... bitstream] <dataset.npz> <num_iterations>");
+    const uint32_t num_iterations = args.ints_after.empty() ? 10 : uint32_t(args.ints_after[0]);
+    graphlily::app::BFS bfs(16, 0, 0, 0);
+    bfs.set_target("hw");
+    bfs.set_up_runtime("");
+    bfs.load_and_format_matrix(args.dataset, true);
+    std::cout << "finished load_and_format_matrix" << std::endl;
+    bfs.send_matrix_host_to_device();
+    const uint32_t source = 0;
+    const double op_count = double(bfs.get_nnz()) * num_iterations;
+
+    auto kernel_results = bfs.pull(source, num_iterations);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    kernel_results = bfs.pull(source, num_iterations);
+    double sec = seconds_since(t1);
+    std::cout << "Pull average_time: " << sec * 1000 << " ms" << std::endl;
+    std::cout << "Pull Compute THROUGHPUT = " << op_count / 1e9 / sec << " GTEPS" << std::endl;
+
+    const float threshold = 0.001;
+    kernel_results = bfs.pull_push(source, num_iterations, threshold);
+    t1 = std::chrono::high_resolution_clock::now();
+    kernel_results = bfs.pull_push(source, num_iterations, threshold);
+    sec = seconds_since(t1);
+    std::cout << "SpMSpV runs for " << bfs.get_push_iterations() << " iterations" << std::endl;
+    std::cout << "Pull-Push average_time: " << sec * 1000 << " ms" << std::endl;
+    std::cout << "Pull-Push Compute THROUGHPUT = " << op_count / 1e9 / sec << " GTEPS" << std::endl;
+    size_t reached = 0;
+    for (auto d : kernel_results) reached += d != 0;
+    std::cout << "reached " << reached << " of " << kernel_results.size() << " vertices; "
+              << num_iterations / sec << " iterations / s" << std::endl;
+    return 0;
+}

@@ -718,17 +718,32 @@ int glb_spmv_host(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type,
     GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask_host, "mask is NULL but mask_type != kNoMask");
     GLB_CUDA(cudaSetDevice(ctx->device));
     if (!m->dx) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->dx), sizeof(float) * m->num_cols));
-    if (!m->dy) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->dy), sizeof(float) * m->num_rows));
     if (mask_type != GLB_MASK_NONE && !m->dmask)
         GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->dmask), sizeof(float) * m->num_rows));
+    // When y_host is page-locked (glb_host_alloc, cudaHostAlloc, torch pin_memory) the kernels store
+    // the rows straight into it over PCIe (coalesced 128-byte writes), so the device-to-host leg
+    // overlaps the SpMV instead of following it.
+    float *y_dev = nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        y_dev = static_cast<float *>(attr.devicePointer);
+    else
+        cudaGetLastError();
+    const bool zero_copy = y_dev != nullptr;
+    if (!zero_copy) {
+        if (!m->dy) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->dy), sizeof(float) * m->num_rows));
+        y_dev = m->dy;
+    }
     GLB_CUDA(cudaMemcpyAsync(m->dx, x_host, sizeof(float) * m->num_cols, cudaMemcpyHostToDevice, ctx->stream));
     if (mask_type != GLB_MASK_NONE)
         GLB_CUDA(cudaMemcpyAsync(m->dmask, mask_host, sizeof(float) * m->num_rows, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = glb_spmv(ctx, m, op, zero, mask_type, m->dx, m->dmask, m->dy);
+    int rc = glb_spmv(ctx, m, op, zero, mask_type, m->dx, m->dmask, y_dev);
     if (rc) return rc;
-    const size_t nr = size_t(m->row_end - m->row_begin);
-    GLB_CUDA(cudaMemcpyAsync(y_host + m->row_begin, m->dy + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+    if (!zero_copy) {
+        const size_t nr = size_t(m->row_end - m->row_begin);
+        GLB_CUDA(cudaMemcpyAsync(y_host + m->row_begin, m->dy + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    }
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
     return GLB_OK;
 }
