@@ -66,10 +66,13 @@ struct glb_ctx_s {
 // one) are finished by the fix-up kernel from per-chunk carries: see spmv.cu.
 #define GLB_GROUP 128u
 #define GLB_MAX_GROUPS 8
+#ifndef GLB_ROW_CAP
 #define GLB_ROW_CAP 128u
+#endif
 #define GLB_FLAG 0x80000000u
 #define GLB_DEFAULT_TILE_K 40960u
 #define GLB_DEFAULT_CARVEOUT_PCT 12u
+#define GLB_DEFAULT_TILE_THREADS 0u
 
 struct glb_fixup_t {
     uint32_t row;    // global row id
@@ -101,6 +104,7 @@ struct glb_csr_s {
     uint32_t *hot_cols = nullptr;  // rank -> column
     float *hot_x = nullptr;        // x[hot_cols[.]], rebuilt by every SpMV launch
     int smem_carveout_pct = 20;
+    uint32_t tile_threads = 0;     // > 0: persistent shared-memory-tile kernel with that many threads per CTA
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
     size_t device_bytes = 0;

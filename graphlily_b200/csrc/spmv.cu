@@ -141,16 +141,25 @@ __device__ __forceinline__ float gather_x(const float *hot_x, const float *x_col
     return v;
 }
 
-// One chunk (up to 8 groups of 128 non-zeros) by one warp.
-template <int OP>
-__global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
-    __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned wib = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
-    float *const stage = stage_all[wib];
+// Shared-memory flavour of the gather: hot words index the CTA's copy of hot_x in shared memory.
+__device__ __forceinline__ float gather_x_tile(uint32_t tile_base, const float *x_cold, uint32_t tile_k, uint32_t c) {
+    float v;
+    asm("{\n"
+        " .reg .pred p;\n"
+        " setp.lt.u32 p, %3, %4;\n"
+        " @p ld.shared.f32 %0, [%1];\n"
+        " @!p ld.global.nc.L1::no_allocate.f32 %0, [%2];\n"
+        "}"
+        : "=f"(v)
+        : "r"(tile_base + c * 4u), "l"(x_cold + c), "r"(c), "r"(tile_k));
+    return v;
+}
 
+// One chunk (up to 8 groups of 128 non-zeros) by one warp.  TILE: the hot vector is in shared
+// memory at tile_base (persistent kernel), else it is read through L1.
+template <int OP, bool TILE>
+__device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
+                                              float *const stage, const uint32_t tile_base) {
     const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
     const int n = int(ld_stream_u32(P.chunk_goff + chunk + 1) - g0);  // 1 .. GLB_MAX_GROUPS, warp-uniform
     const uint4 *gp = reinterpret_cast<const uint4 *>(P.stream) + size_t(g0) * 64 + lane;
@@ -191,7 +200,8 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kerne
             const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
             float xv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xv[e] = gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+            for (int e = 0; e < 4; ++e)
+                xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float prod = Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
@@ -233,6 +243,84 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kerne
         } else {
             finish_row<OP>(P, ld_stream_u32(P.nz_rows + ord0 + k), val);
         }
+    }
+}
+
+// Variant L1: one chunk per warp, hot x lines kept in L1 by the cache hints.
+template <int OP>
+__global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
+    __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
+    if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
+    process_chunk<OP, false>(P, chunk, lane, stage_all[wib], 0u);
+}
+
+// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!done);
+}
+
+// Variant TILE: persistent CTAs, one per SM.  The CTA pulls the packed hot vector into shared
+// memory with TMA bulk copies once (192 KB from L2), then its warps walk the chunk list round
+// robin; hot gathers are bank-parallel LDS with no eviction, cold ones go around L1 as before.
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) spmv_lane_tile_kernel(const SpmvParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    const unsigned n_warps = blockDim.x >> 5;
+    float *stage = tile + ((P.tile_k + 3u) & ~3u);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + n_warps * GLB_ROW_CAP);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+
+    const uint32_t bytes = P.tile_k * 4u;
+    const bool bulk_ok = (bytes % 16u == 0) && ((reinterpret_cast<uintptr_t>(P.hot_x) & 15u) == 0);
+    if (bulk_ok) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            constexpr uint32_t kPiece = 32768;
+            for (uint32_t off = 0; off < bytes; off += kPiece) {
+                const uint32_t nb = (bytes - off < kPiece) ? (bytes - off) : kPiece;
+                bulk_g2s(reinterpret_cast<unsigned char *>(tile) + off,
+                         reinterpret_cast<const unsigned char *>(P.hot_x) + off, nb, bar);
+            }
+        }
+        mbar_wait(bar, 0);
+    } else {  // unaligned caller vector under the identity numbering: plain loads
+        for (uint32_t i = threadIdx.x; i < P.tile_k; i += blockDim.x) tile[i] = P.hot_x[i];
+        __syncthreads();
+    }
+
+    const uint32_t tile_base = smem_u32(tile);
+    const uint32_t total_warps = gridDim.x * n_warps;
+    for (uint32_t chunk = blockIdx.x * n_warps + wib; chunk < P.n_chunks; chunk += total_warps) {
+        process_chunk<OP, true>(P, chunk, lane, stage + wib * GLB_ROW_CAP, tile_base);
+        __syncwarp();  // the staging array is reused by the next chunk
     }
 }
 
@@ -288,7 +376,18 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
         GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
     }
-    if (P.n_chunks) {
+    if (P.n_chunks && m->tile_threads) {
+        const uint32_t n_warps = m->tile_threads / 32;
+        const size_t smem = size_t((P.tile_k + 3u) & ~3u) * 4 + size_t(n_warps) * GLB_ROW_CAP * 4 + 16;
+        static thread_local size_t attr_set[3] = {0, 0, 0};
+        if (attr_set[OP] < smem) {
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            attr_set[OP] = smem;
+        }
+        uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
+        if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
+        spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
+    } else if (P.n_chunks) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
         static thread_local int carveout_set[3] = {-1, -1, -1};
         if (carveout_set[OP] != m->smem_carveout_pct) {
@@ -610,6 +709,10 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     };
     const uint32_t tile_k = env_u32("GLB_SPMV_TILE_K", GLB_DEFAULT_TILE_K);
     const uint32_t carveout = env_u32("GLB_SPMV_CARVEOUT", GLB_DEFAULT_CARVEOUT_PCT);
+    //   GLB_SPMV_TILE_THREADS=<n>    0: hot vector through L1 (one chunk per warp); 32..1024: persistent
+    //                                CTAs of n threads that keep it in shared memory (TMA bulk load)
+    uint32_t tile_threads = env_u32("GLB_SPMV_TILE_THREADS", GLB_DEFAULT_TILE_THREADS);
+    if (tile_threads > 1024 || tile_threads % 32) tile_threads = 1024;
 
     HostLayout L;
     int rc = format_host(num_rows, num_cols, indptr, indices, data, row_begin, row_end, tile_k, L);
@@ -633,6 +736,10 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     m->tile_k = L.tile_k;
     m->n_hot = uint32_t(L.hot_cols.size());
     m->smem_carveout_pct = int(carveout > 100 ? 100 : carveout);
+    // the shared-memory flavour needs the tile, the staging arrays and the barrier in 227 KB
+    if (L.tile_k == 0 || size_t((L.tile_k + 3u) & ~3u) * 4 + size_t(tile_threads / 32) * GLB_ROW_CAP * 4 + 16 > 227 * 1024)
+        tile_threads = 0;
+    m->tile_threads = tile_threads;
 
     size_t bytes = 0;
     const size_t words = size_t(L.n_groups) * 256;

@@ -22,8 +22,9 @@ x = torch.from_numpy(x_host).to(dev)
 y = torch.zeros_like(x)
 alg_bytes = 8 * m.nnz + 4 * (rows + 1) + 4 * rows + 4 * rows
 
-configs = [dict(GLB_SPMV_TILE_K=k, GLB_SPMV_CARVEOUT=c)
-           for k, c in [(40960, 8), (40960, 12), (40960, 16), (40960, 20), (45056, 12), (49152, 12), (49152, 16), (32768, 12)]]
+configs = [dict(GLB_SPMV_TILE_K=40960, GLB_SPMV_CARVEOUT=12, GLB_SPMV_TILE_THREADS=0)] + \
+          [dict(GLB_SPMV_TILE_K=k, GLB_SPMV_CARVEOUT=12, GLB_SPMV_TILE_THREADS=t)
+           for k, t in [(40960, 1024), (49152, 1024), (49152, 768), (40960, 768), (32768, 1024), (49152, 512)]]
 if len(sys.argv) > 2:
     configs = [eval(sys.argv[2])]
 ref = None
