@@ -140,23 +140,18 @@ class BFS(ModuleCollection):
     def pull(self, source, num_iterations, fused=True):
         """bfs.h:106-126"""
         n = self.matrix_num_rows_
-        inp = np.full(n, self.semiring_[2], np.float32)
-        distance = np.zeros(n, np.float32)
-        inp[source] = 1
-        distance[source] = 1
-        self.SpMV_.send_vector_host_to_device(inp)
-        self.SpMV_.send_mask_host_to_device(distance)
+        # input = zero but input[source] = 1; distance = 0 but distance[source] = 1 (bfs.h:108-112),
+        # built on the device instead of uploaded
+        self.SpMV_.set_vector_constant(self.semiring_[2], source, 1.0)
+        self.SpMV_.set_mask_constant(0.0, source, 1.0)
         self._pull_loop(1, num_iterations, fused)
         self._exchange(self.SpMV_.mask_buf, n)
         return self.SpMV_.send_mask_device_to_host()
 
     # -- push ------------------------------------------------------------------------
     def _push_setup(self, source):
-        n = self.matrix_num_rows_
-        distance = np.zeros(n, np.float32)
-        distance[source] = 1
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [1.0]))
-        self.SpMSpV_.send_mask_host_to_device(distance)
+        self.SpMSpV_.set_mask_constant(0.0, source, 1.0)      # distance, bfs.h:138-141
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
 
     def _push_step(self, it):
@@ -229,9 +224,8 @@ class PageRank(ModuleCollection):
     def pull(self, damping, num_iterations, fused=True):
         """pagerank.h:80-90"""
         n = self.matrix_num_rows_
-        rank = np.full(n, np.float32(1.0 / n), np.float32)
         teleport = float((np.float32(1) - np.float32(damping)) / np.float32(n))
-        self.SpMV_.send_vector_host_to_device(rank)
+        self.SpMV_.set_vector_constant(float(np.float32(1.0 / n)))   # rank0 = 1 / N, pagerank.h:81-82
         if fused:
             for _ in range(num_iterations):
                 self.SpMV_.run(Epilogue(1, teleport, None, 0.0, 0))
@@ -303,17 +297,13 @@ class SSSP(ModuleCollection):
 
     def pull(self, source, num_iterations, fused=True):
         """sssp.h:152-166"""
-        inp = np.full(self.matrix_num_rows_, self.semiring_[2], np.float32)
-        inp[source] = 0
-        self.SpMV_.send_vector_host_to_device(inp)
+        self.SpMV_.set_vector_constant(self.semiring_[2], source, 0.0)   # sssp.h:153-156
         self._pull_loop(1, num_iterations, fused)
         return self.SpMV_.send_vector_device_to_host()
 
     def _push_setup(self, source):
-        distance = np.full(self.matrix_num_rows_, self.semiring_[2], np.float32)
-        distance[source] = 0
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [0.0]))
-        self.SpMSpV_.send_mask_host_to_device(distance)
+        self.SpMSpV_.set_mask_constant(self.semiring_[2], source, 0.0)   # distance, sssp.h:172-176
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.results_buf)
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
         self.SparseAssign_.bind_new_frontier_buf(self.SpMSpV_.vector_buf)

@@ -194,6 +194,12 @@ class DeviceBuffer:
         assert array.nbytes <= self.nbytes
         check(lib.glb_buffer_h2d(self.ctx.handle, self.ptr, array.ctypes.data, array.nbytes))
 
+    def write_at(self, byte_offset, array):
+        """Overwrite a slice of the buffer (e.g. the one non-constant element of a start vector)."""
+        array = np.ascontiguousarray(array)
+        assert byte_offset + array.nbytes <= self.nbytes
+        check(lib.glb_buffer_h2d(self.ctx.handle, self.ptr + byte_offset, array.ctypes.data, array.nbytes))
+
     def read(self, dtype, count):
         out = np.empty(count, dtype=dtype)
         assert out.nbytes <= self.nbytes

@@ -46,6 +46,14 @@ class BaseModule:
     def _dense_to_device(self, vec):
         return self.ctx.to_device(np.ascontiguousarray(vec, np.float32))
 
+    def _constant_on_device(self, n, value, index=None, index_value=None):
+        """A start vector that is constant but for one element, built on the device (a fill kernel
+        and a 4-byte copy) instead of uploading n floats."""
+        buf = self.ctx.zeros_f32(n, value)
+        if index is not None:
+            buf.write_at(4 * int(index), np.array([index_value], np.float32))
+        return buf
+
 
 class SpMVModule(BaseModule):
     """spmv_module.h:26-272"""
@@ -87,6 +95,12 @@ class SpMVModule(BaseModule):
 
     def send_mask_host_to_device(self, mask):
         self.mask_buf = self._dense_to_device(mask)          # spmv_module.h:444-459
+
+    def set_vector_constant(self, value, index=None, index_value=None):
+        self.vector_buf = self._constant_on_device(self.get_num_cols(), value, index, index_value)
+
+    def set_mask_constant(self, value, index=None, index_value=None):
+        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value)
 
     def bind_mask_buf(self, src_buf):
         self.mask_buf = src_buf                              # spmv_module.h:463-467
@@ -148,6 +162,9 @@ class SpMSpVModule(BaseModule):
 
     def send_mask_host_to_device(self, mask):
         self.mask_buf = self._dense_to_device(mask)          # spmspv_module.h:403-433
+
+    def set_mask_constant(self, value, index=None, index_value=None):
+        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value)
 
     def bind_mask_buf(self, src_buf):
         self.mask_buf = src_buf

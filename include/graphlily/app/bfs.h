@@ -72,10 +72,8 @@ private:
         aligned_sparse_vec_t spmspv_input(2);
         spmspv_input[0] = {1, 0};  // one source vertex
         spmspv_input[1] = {source, 1};
-        aligned_dense_vec_t distance(matrix_num_rows_, 0);
-        distance[source] = 1;
         SpMSpV_->send_vector_host_to_device(spmspv_input);
-        SpMSpV_->send_mask_host_to_device(distance);
+        SpMSpV_->set_mask_constant(0, source, 1);  // distance: 0 but distance[source] = 1, built on the device
         SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
     }
 
@@ -133,12 +131,10 @@ public:
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
-        aligned_dense_vec_t input(matrix_num_rows_, semiring_.zero);
-        aligned_dense_vec_t distance(matrix_num_rows_, 0);
-        input[source] = 1;
-        distance[source] = 1;
-        SpMV_->send_vector_host_to_device(input);
-        SpMV_->send_mask_host_to_device(distance);
+        // input = zero, input[source] = 1; distance = 0, distance[source] = 1 (bfs.h:108-112): built on
+        // the device instead of uploaded
+        SpMV_->set_vector_constant(semiring_.zero, source, 1);
+        SpMV_->set_mask_constant(0, source, 1);
         pull_loop(1, num_iterations);
         return SpMV_->send_mask_device_to_host();
     }

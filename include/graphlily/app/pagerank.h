@@ -62,9 +62,8 @@ public:
 
     aligned_dense_vec_t pull(float damping, uint32_t num_iterations) {
         const uint32_t n = matrix_num_rows_;
-        aligned_dense_vec_t rank(n, 1.0 / n);
         const float teleport = (1 - damping) / n;
-        SpMV_->send_vector_host_to_device(rank);
+        SpMV_->set_vector_constant(float(1.0 / n));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
         if (fused_) {
             glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
             for (uint32_t iter = 1; iter <= num_iterations; iter++) {

@@ -104,10 +104,8 @@ private:
         aligned_sparse_vec_t spmspv_input(2);
         spmspv_input[0] = {1, 0};
         spmspv_input[1] = {source, 0};
-        aligned_dense_vec_t distance(matrix_num_rows_, semiring_.zero);
-        distance[source] = 0;
         SpMSpV_->send_vector_host_to_device(spmspv_input);
-        SpMSpV_->send_mask_host_to_device(distance);
+        SpMSpV_->set_mask_constant(semiring_.zero, source, 0);  // distance (sssp.h:172-176), built on the device
         SparseAssign_->bind_mask_buf(SpMSpV_->results_buf);
         SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
         SparseAssign_->bind_new_frontier_buf(SpMSpV_->vector_buf);
@@ -157,9 +155,7 @@ public:
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
-        aligned_dense_vec_t input(matrix_num_rows_, semiring_.zero);
-        input[source] = 0;
-        SpMV_->send_vector_host_to_device(input);
+        SpMV_->set_vector_constant(semiring_.zero, source, 0);  // sssp.h:153-156
         pull_loop(1, num_iterations);
         return SpMV_->send_vector_device_to_host();
     }

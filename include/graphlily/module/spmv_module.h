@@ -79,6 +79,15 @@ public:
     }
     void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
 
+    // Start vectors of the apps (constant but for the source entry) without a host upload.
+    void set_vector_constant(vector_data_t value) { vector_buf = constant_on_device(get_num_cols(), value); }
+    void set_vector_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
+        vector_buf = constant_on_device(get_num_cols(), value, true, index, index_value);
+    }
+    void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
+        mask_buf = constant_on_device(get_num_rows(), value, true, index, index_value);
+    }
+
     void run() { run_fused(nullptr); }
 
     // One launch for SpMV + the eWiseAdd / dense assign the apps run right after it (glb_spmv_fused).
