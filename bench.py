@@ -121,7 +121,7 @@ def workload_config(n_gpus):
             "generator": f"graphlily_b200.datasets.powerlaw_csr(seed={SEED}): Pareto(2.1) row degrees 1..2^20, "
                          "Zipf(0.9) column popularity, random column labels",
             "rows": ROWS, "nnz": NNZ, "semiring": "plus-times",
-            "sharding": f"row-range x{n_gpus}, one NCCL allgather of y per step" if n_gpus > 1 else "none",
+            "sharding": f"row-range x{n_gpus}" if n_gpus > 1 else "none",
             "l2": "matrix streams (1.07 GB) exceed the 126 MB L2 every step; no flush needed",
             "layout": "lane-segment chunks (<=1024 nnz / warp), hot columns packed into an L1-resident vector"}
 
@@ -209,19 +209,55 @@ def main():
     log(f"rank {rank}: rows [{rb},{re}) nnz {info['nnz']} chunks {info['chunks']} fixups {info['fixups']} "
         f"layout {info['device_bytes'] / 1e9:.3f} GB, format+upload {time.time() - t0:.1f}s")
 
-    if world > 1:
-        uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
-
     x_host = np.random.default_rng(SEED).integers(0, 2, n).astype(np.float32)
-    xa = torch.from_numpy(x_host).to(dev)
-    xb = torch.zeros_like(xa)
+    # N > 1: how each rank's slice of y reaches the other ranks before the next step.
+    #   "peer"  (default) the SpMV write-back stores every row into all ranks' copies of the vector
+    #           over NVLink (peer-mapped memory, glb_spmv_exchange); a signal / wait kernel follows
+    #   "nccl"  one in-place ncclAllGather after the kernels (GLB_EXCHANGE=nccl, or when CUDA IPC
+    #           between the per-GPU processes is not available)
+    exchange, xc = "none", None
+    if world > 1:
+        exchange = os.environ.get("GLB_EXCHANGE", "peer")
+        if exchange == "peer":
+            def all_gather_bytes(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            try:
+                xc = capi.Exchange(ctx, n, rank, world, all_gather_bytes)
+            except capi.GlbError as e:
+                log(f"rank {rank}: peer exchange unavailable ({e}); using the NCCL allgather")
+                exchange = "nccl"
+            ok = torch.tensor([1 if xc is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                xc, exchange = None, "nccl"
+        if exchange == "nccl":
+            uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(uid[0], rank, world)
+
+    class Vec:   # a full-length device vector: a torch tensor, or a peer-mapped exchange vector
+        def __init__(self, which):
+            self.which = which
+            self.t = None if xc is not None else torch.zeros(n, dtype=torch.float32, device=dev)
+
+        def ptr(self):
+            return xc.vector(self.which) if xc is not None else self.t.data_ptr()
+
+        def load(self, host):
+            capi.check(capi.lib.glb_buffer_h2d(ctx.handle, self.ptr(), host.ctypes.data, host.nbytes))
+
+    xa, xb = Vec(0), Vec(1)
+    xa.load(x_host)
 
     def step(src, dst):
-        A.spmv(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.data_ptr(), None, dst.data_ptr())
-        if world > 1:
-            ctx.allgather_f32(dst.data_ptr(), slot)
+        if xc is not None:
+            xc.spmv(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.which, dst.which)
+        else:
+            A.spmv(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.ptr(), None, dst.ptr())
+            if world > 1:
+                ctx.allgather_f32(dst.ptr(), slot)
 
     def run_steps(k, src, dst):
         for _ in range(k):
@@ -257,7 +293,9 @@ def main():
     gteps = m.nnz / (ms_step * 1e-3) / 1e9
 
     # ---- dominant kernel alone (events inside the C ABI, same stream) --------------------------
-    xa.copy_(torch.from_numpy(x_host))
+    barrier()
+    xa.load(x_host)
+    barrier()
     ctx.kernel_timing(True)
     run_steps(args.steps, xa, xb)
     ms_main, ms_fix, launches = ctx.kernel_timing_read()
@@ -320,11 +358,15 @@ def main():
             log("WARNING: GPU result differs from the CPU reference on the sample")
 
     # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup
-    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0)
+    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (1 if xc is not None else 0)
     if rank == 0:
+        cfg = workload_config(world)
+        if world > 1:
+            cfg["exchange"] = ("y rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped "
+                               "memory) + signal/wait kernel" if exchange == "peer" else "one in-place ncclAllGather of y per step")
         line = {"metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
                 "cpu_baseline": cpu, "y_checksum": checksum, "nnz": m.nnz}
         print(json.dumps(line), flush=True)

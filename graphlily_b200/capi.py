@@ -85,6 +85,13 @@ SIGNATURES = {
     "glb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "glb_comm_destroy": (C.c_int, [_vp]),
     "glb_allgather_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "glb_xchg_create": (C.c_int, [_vp, C.c_uint32, C.c_int, C.POINTER(_vp)]),
+    "glb_xchg_export": (C.c_int, [_vp, _vp]),
+    "glb_xchg_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "glb_xchg_vector": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "glb_xchg_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "glb_xchg_destroy": (C.c_int, [_vp]),
+    "glb_spmv_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp, C.POINTER(Epilogue)]),
 }
 
 
@@ -278,6 +285,41 @@ class CsrMatrix:
             self.close()
         except Exception:
             pass
+
+
+class Exchange:
+    """Peer-mapped vectors of a row-sharded run (glb_xchg_t): every rank's SpMV stores its rows
+    into all ranks' copies, so no allgather follows the kernel.  ``all_gather_bytes(b)`` must
+    return the list of every rank's ``b`` in rank order (e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, ctx, n_floats, rank, nranks, all_gather_bytes, n_vectors=2):
+        h = _vp()
+        check(lib.glb_xchg_create(ctx.handle, int(n_floats), n_vectors, C.byref(h)))
+        self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, h, int(n_floats), rank, nranks
+        mine = (C.c_char * 64)()
+        check(lib.glb_xchg_export(h, mine))
+        handles = b"".join(all_gather_bytes(bytes(mine)))
+        assert len(handles) == 64 * nranks
+        check(lib.glb_xchg_connect(h, rank, nranks, C.c_char_p(handles)))
+
+    def vector(self, which):
+        p = _vp()
+        check(lib.glb_xchg_vector(self.handle, which, C.byref(p)))
+        return p.value
+
+    def spmv(self, matrix, op, zero, mask_type, src_vec, dst_vec, mask=None, epilogue=None):
+        check(lib.glb_spmv_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
+                                    _ptr(mask), C.byref(epilogue) if epilogue is not None else None))
+
+    def timed_out(self):
+        t = C.c_int(0)
+        check(lib.glb_xchg_status(self.handle, C.byref(t)))
+        return bool(t.value)
+
+    def close(self):
+        if self.handle:
+            lib.glb_xchg_destroy(self.handle)
+            self.handle = None
 
 
 class CscMatrix:

@@ -341,4 +341,124 @@ int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank) {
     return GLB_OK;
 }
 
+// ------------------------------------------------------------------------ peer exchange
+// A row-sharded iteration needs every rank's slice of y on every rank before the next SpMV.
+// Instead of an allgather after the kernel, the SpMV write-back stores each row into all peers'
+// copies (glb_spmv_exchange); what is left of the collective is this signal / wait step.
+__global__ void xchg_signal_wait_kernel(uint32_t *const *peer_flags, uint32_t *local_flags, int rank, int nranks,
+                                        uint32_t epoch, uint32_t *err) {
+    const int p = int(threadIdx.x);
+    if (p >= nranks || p == rank) return;
+    // all SpMV stores of this rank were issued by kernels that completed before this one started
+    // (stream order); publish, then wait for the peer's slice
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    uint32_t seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + p) : "memory");
+        if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; fail loudly at the next sync
+            *err = 1;
+            break;
+        }
+    } while (seen < epoch);
+}
+
+int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc) {
+    xc->epoch++;
+    xchg_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(xc->d_peer_flags, xc->local_flags, xc->rank, xc->nranks, xc->epoch,
+                                                      xc->d_err);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t *out) {
+    GLB_REQUIRE(ctx && out && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
+    *out = nullptr;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    glb_xchg_t xc = new glb_xchg_s();
+    xc->ctx = ctx;
+    xc->n = n_floats;
+    xc->n_vectors = n_vectors;
+    const size_t vec_bytes = (size_t(n_floats) * n_vectors * sizeof(float) + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&xc->local), vec_bytes + 256);  // plain cudaMalloc: IPC-exportable
+    if (e == cudaSuccess) e = cudaMemset(xc->local, 0, vec_bytes + 256);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_peer_flags), sizeof(uint32_t *) * (GLB_MAX_PEERS + 1));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_err), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(xc->d_err, 0, sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        glb_set_error("glb_xchg_create: %s", cudaGetErrorString(e));
+        glb_xchg_destroy(xc);
+        return e == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA;
+    }
+    xc->local_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->local) + vec_bytes);
+    *out = xc;
+    return GLB_OK;
+}
+
+int glb_xchg_export(glb_xchg_t xc, void *handle64) {
+    GLB_REQUIRE(xc && handle64, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GLB_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GLB_CUDA(cudaIpcGetMemHandle(&h, xc->local));
+    memcpy(handle64, &h, sizeof(h));
+    return GLB_OK;
+}
+
+int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles) {
+    GLB_REQUIRE(xc && handles && nranks >= 1 && nranks <= GLB_MAX_PEERS + 1 && rank >= 0 && rank < nranks, "bad argument");
+    GLB_CUDA(cudaSetDevice(xc->ctx->device));
+    const size_t vec_bytes = (size_t(xc->n) * xc->n_vectors * sizeof(float) + 255) & ~size_t(255);
+    xc->rank = rank;
+    xc->nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            xc->peer[r] = xc->local;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const char *>(handles) + size_t(r) * GLB_IPC_HANDLE_BYTES, sizeof(h));
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                glb_set_error("glb_xchg_connect: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+                cudaGetLastError();
+                return GLB_ECUDA;
+            }
+            xc->peer[r] = static_cast<float *>(p);
+        }
+        xc->peer_flags[r] = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->peer[r]) + vec_bytes);
+    }
+    GLB_CUDA(cudaMemcpy(xc->d_peer_flags, xc->peer_flags, sizeof(uint32_t *) * (GLB_MAX_PEERS + 1), cudaMemcpyHostToDevice));
+    xc->connected = true;
+    return GLB_OK;
+}
+
+int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr) {
+    GLB_REQUIRE(xc && local_ptr && which >= 0 && which < xc->n_vectors, "bad argument");
+    *local_ptr = xc->local + size_t(which) * xc->n;
+    return GLB_OK;
+}
+
+int glb_xchg_status(glb_xchg_t xc, int *timed_out) {
+    GLB_REQUIRE(xc && timed_out, "NULL argument");
+    uint32_t e = 0;
+    GLB_CUDA(cudaStreamSynchronize(xc->ctx->stream));
+    GLB_CUDA(cudaMemcpy(&e, xc->d_err, sizeof(e), cudaMemcpyDeviceToHost));
+    *timed_out = int(e);
+    return GLB_OK;
+}
+
+int glb_xchg_destroy(glb_xchg_t xc) {
+    if (!xc) return GLB_OK;
+    cudaSetDevice(xc->ctx->device);
+    cudaStreamSynchronize(xc->ctx->stream);
+    for (int r = 0; r < xc->nranks; ++r)
+        if (xc->connected && r != xc->rank && xc->peer[r]) cudaIpcCloseMemHandle(xc->peer[r]);
+    cudaFree(xc->local);
+    cudaFree(xc->d_peer_flags);
+    cudaFree(xc->d_err);
+    delete xc;
+    return GLB_OK;
+}
+
 }  // extern "C"

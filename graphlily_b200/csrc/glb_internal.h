@@ -124,8 +124,29 @@ struct glb_csc_s {
     uint32_t *counter = nullptr;  // output cursor
 };
 
+// ---------------------------------------------------------------- peer exchange (multi-GPU)
+// Every rank owns one cudaMalloc'd block [n_vectors x n floats][flags]; the blocks of all ranks
+// are mapped into every process with CUDA IPC, so a kernel can store rows straight into the
+// peers' copies.  flags[s] of rank r = last epoch rank s has finished writing into r's block.
+#define GLB_MAX_PEERS 7
+struct glb_xchg_s {
+    glb_ctx_t ctx = nullptr;
+    uint32_t n = 0;      // floats per vector
+    int n_vectors = 0;
+    float *local = nullptr;               // this rank's block
+    uint32_t *local_flags = nullptr;      // GLB_MAX_PEERS + 1 slots, inside the block
+    bool connected = false;
+    int rank = 0, nranks = 1;
+    float *peer[GLB_MAX_PEERS + 1] = {};        // blocks of all ranks (peer[rank] == local)
+    uint32_t *peer_flags[GLB_MAX_PEERS + 1] = {};
+    uint32_t **d_peer_flags = nullptr;    // device copy of peer_flags
+    uint32_t *d_err = nullptr;            // set when a wait timed out
+    uint32_t epoch = 0;
+};
+extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
+
 // launchers (defined in the .cu files)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep);
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers);
 
 #endif  // GLB_INTERNAL_H_

@@ -69,6 +69,8 @@ struct SpmvParams {
     const float *x_cold;  // x - tile_k: cold column words index it directly
     const float *mask;    // may alias assign_inout
     float *y;
+    float *y_peer[GLB_MAX_PEERS];  // the same vector on the other GPUs of a row-sharded run (peer-mapped memory)
+    int n_peers;
     float *head_carry;
     float *tail_carry;
     uint32_t n_chunks;
@@ -120,6 +122,11 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
     }
     if (P.add_enable) v = __fadd_rn(v, P.add_val);
     P.y[row] = v;
+    // fused exchange: the row also goes straight into every peer's copy over NVLink, so the
+    // allgather of the next iteration's x rides inside the SpMV write-back
+#pragma unroll
+    for (int p = 0; p < GLB_MAX_PEERS; ++p)
+        if (p < P.n_peers) P.y_peer[p][row] = v;
     if (P.assign_inout) {
         bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? (v != 0.0f) : (v == 0.0f);
         if (hit) P.assign_inout[row] = P.assign_val;
@@ -430,9 +437,11 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 }  // namespace
 
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep) {
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
+    P.n_peers = n_peers;
+    for (int p = 0; p < n_peers && p < GLB_MAX_PEERS; ++p) P.y_peer[p] = y_peers[p];
     P.stream = m->stream;
     P.flags = m->flags;
     P.chunk_goff = m->chunk_goff;
@@ -810,7 +819,26 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0);
+}
+
+int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
+                      const float *mask, const glb_spmv_epilogue_t *ep) {
+    GLB_REQUIRE(xc && xc->connected, "exchange is not connected");
+    GLB_REQUIRE(src_vec >= 0 && src_vec < xc->n_vectors && dst_vec >= 0 && dst_vec < xc->n_vectors && src_vec != dst_vec,
+                "bad vector index");
+    GLB_REQUIRE(m && m->num_rows <= xc->n && m->num_cols <= xc->n, "matrix larger than the exchange vectors");
+    const float *x = xc->local + size_t(src_vec) * xc->n;
+    float *y = xc->local + size_t(dst_vec) * xc->n;
+    int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
+    if (rc) return rc;
+    float *peers[GLB_MAX_PEERS];
+    int n_peers = 0;
+    for (int r = 0; r < xc->nranks; ++r)
+        if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dst_vec) * xc->n;
+    rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers);
+    if (rc) return rc;
+    return glb_xchg_signal_wait(ctx, xc);
 }
 
 int glb_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,

@@ -244,6 +244,29 @@ int glb_comm_destroy(glb_ctx_t ctx);
 /* In-place allgather: every rank contributed buf[rank*count_per_rank .. +count_per_rank). */
 int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank);
 
+/* Fused exchange.  The allgather moves each rank's slice of y to every rank AFTER the SpMV; here
+ * the SpMV write-back itself stores every row into all ranks' copies of the vector over NVLink
+ * (peer-mapped memory, CUDA IPC across the per-GPU processes), so the transfer overlaps the
+ * kernel and what remains of the collective is one signal / wait kernel.
+ *   glb_xchg_create   allocates this rank's block: n_vectors (2..4) vectors of n_floats + flags
+ *   glb_xchg_export   64-byte IPC handle of the block; the host exchanges the handles of all ranks
+ *   glb_xchg_connect  maps the peers' blocks (handles = nranks x 64 bytes, in rank order)
+ *   glb_xchg_vector   local device pointer of vector `which` (fill vector 0 before the first step)
+ *   glb_spmv_exchange y = A (+).(x) x with x = local vector src_vec, y rows written into vector
+ *                     dst_vec of EVERY rank; returns after enqueueing the signal / wait, so the
+ *                     next call on this stream sees the complete dst_vec.  Alternate src / dst.
+ *   glb_xchg_status   synchronises; *timed_out != 0 if a peer never signalled (it died) */
+#define GLB_IPC_HANDLE_BYTES 64
+typedef struct glb_xchg_s *glb_xchg_t;
+int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t *out);
+int glb_xchg_export(glb_xchg_t xc, void *handle64);
+int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles);
+int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr);
+int glb_xchg_status(glb_xchg_t xc, int *timed_out);
+int glb_xchg_destroy(glb_xchg_t xc);
+int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
+                      int dst_vec, const float *mask, const glb_spmv_epilogue_t *ep);
+
 #ifdef __cplusplus
 }
 #endif
