@@ -68,6 +68,26 @@ class ModuleCollection:
         if self.world_ > 1:
             self.ctx.allgather_f32(buf, n // self.world_)
 
+    # -- launch replay: the iteration loop of an app is a fixed launch sequence ------------------
+    use_graphs_ = True
+    _GRAPH_CACHE = 8
+
+    def _replay(self, key, launches):
+        """Run ``launches()`` -- a loop of glb_* launches over fixed buffers and scalars -- as one
+        recorded CUDA graph (recorded at the first call with this ``key``, replayed afterwards): a
+        7-iteration BFS is 21 launches of 5-50 us kernels, which the host cannot enqueue fast enough
+        one by one.  Single-GPU only (the exchange step of a sharded run is not recorded)."""
+        if not self.use_graphs_ or self.world_ > 1:
+            launches()
+            return
+        cache = self.__dict__.setdefault("graphs_", {})
+        g = cache.get(key)
+        if g is None:
+            if len(cache) >= self._GRAPH_CACHE:
+                cache.pop(next(iter(cache)))
+            g = cache[key] = self.ctx.record(launches)
+        g.launch()
+
 
 def _load(path_or_csr):
     if isinstance(path_or_csr, str):
@@ -121,11 +141,20 @@ class BFS(ModuleCollection):
     def _pull_loop(self, first_iter, num_iterations, fused):
         n = self.matrix_num_rows_
         if fused:
-            for it in range(first_iter, num_iterations + 1):
-                ep = Epilogue(0, 0.0, self.SpMV_.mask_buf.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE)
-                self.SpMV_.run(ep)
-                self._exchange(self.SpMV_.results_buf, n)   # distance stays row-local until the end
-                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+            vec, res, mask = self.SpMV_.vector_buf, self.SpMV_.results_buf, self.SpMV_.mask_buf
+            iters = range(first_iter, num_iterations + 1)
+
+            def launches():
+                v, r = vec, res
+                for it in iters:
+                    ep = Epilogue(0, 0.0, mask.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE)
+                    self.SpMV_.run_with(v, mask, r, ep)
+                    self._exchange(r, n)   # distance stays row-local until the end
+                    v, r = r, v
+
+            self._replay(("bfs", first_iter, num_iterations, vec.ptr, res.ptr, mask.ptr), launches)
+            if len(iters) % 2:
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = res, vec
         else:
             assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.DenseAssign_.bind_mask_buf(self.SpMV_.vector_buf)
@@ -227,10 +256,18 @@ class PageRank(ModuleCollection):
         teleport = float((np.float32(1) - np.float32(damping)) / np.float32(n))
         self.SpMV_.set_vector_constant(float(np.float32(1.0 / n)))   # rank0 = 1 / N, pagerank.h:81-82
         if fused:
-            for _ in range(num_iterations):
-                self.SpMV_.run(Epilogue(1, teleport, None, 0.0, 0))
-                self._exchange(self.SpMV_.results_buf, n)
-                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+            vec, res = self.SpMV_.vector_buf, self.SpMV_.results_buf
+
+            def launches():
+                v, r = vec, res
+                for _ in range(num_iterations):
+                    self.SpMV_.run_with(v, None, r, Epilogue(1, teleport, None, 0.0, 0))
+                    self._exchange(r, n)
+                    v, r = r, v
+
+            self._replay(("pagerank", teleport, num_iterations, vec.ptr, res.ptr), launches)
+            if num_iterations % 2:
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = res, vec
         else:
             assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)
@@ -283,10 +320,19 @@ class SSSP(ModuleCollection):
     def _pull_loop(self, first_iter, num_iterations, fused):
         n = self.matrix_num_rows_
         if fused:
-            for _ in range(first_iter, num_iterations + 1):
-                self.SpMV_.run()
-                self._exchange(self.SpMV_.results_buf, n)
-                self.SpMV_.vector_buf, self.SpMV_.results_buf = self.SpMV_.results_buf, self.SpMV_.vector_buf
+            vec, res = self.SpMV_.vector_buf, self.SpMV_.results_buf
+            iters = range(first_iter, num_iterations + 1)
+
+            def launches():
+                v, r = vec, res
+                for _ in iters:
+                    self.SpMV_.run_with(v, None, r)
+                    self._exchange(r, n)
+                    v, r = r, v
+
+            self._replay(("sssp", len(iters), vec.ptr, res.ptr), launches)
+            if len(iters) % 2:
+                self.SpMV_.vector_buf, self.SpMV_.results_buf = res, vec
         else:
             assert self.world_ == 1, "the unfused launch sequence is single-GPU"
             self.eWiseAdd_.bind_in_buf(self.SpMV_.results_buf)

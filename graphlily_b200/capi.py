@@ -73,6 +73,7 @@ SIGNATURES = {
     "glb_spmv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_fused": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.POINTER(Epilogue)]),
     "glb_spmv_host": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "glb_spmv_host_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glb_spmspv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "glb_sparse_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
     "glb_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float]),
@@ -85,6 +86,10 @@ SIGNATURES = {
     "glb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "glb_comm_destroy": (C.c_int, [_vp]),
     "glb_allgather_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "glb_graph_begin": (C.c_int, [_vp]),
+    "glb_graph_end": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "glb_graph_launch": (C.c_int, [_vp, _vp]),
+    "glb_graph_destroy": (C.c_int, [_vp]),
     "glb_xchg_create": (C.c_int, [_vp, C.c_uint32, C.c_int, C.POINTER(_vp)]),
     "glb_xchg_export": (C.c_int, [_vp, _vp]),
     "glb_xchg_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -172,6 +177,22 @@ class Context:
     def allgather_f32(self, buf, count_per_rank):
         check(lib.glb_allgather_f32(self.handle, _ptr(buf), count_per_rank))
 
+    # ---- launch replay (CUDA graph of a fixed launch sequence) -----------------------------
+    def record(self, fn):
+        """Record the glb_* launches ``fn()`` makes on this context (nothing executes) -> Graph."""
+        check(lib.glb_graph_begin(self.handle))
+        try:
+            fn()
+        except BaseException:
+            h = _vp()
+            lib.glb_graph_end(self.handle, C.byref(h))
+            if h:
+                lib.glb_graph_destroy(h)
+            raise
+        h = _vp()
+        check(lib.glb_graph_end(self.handle, C.byref(h)))
+        return Graph(self, h)
+
     # ---- buffers ------------------------------------------------------------------
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)
@@ -186,6 +207,24 @@ class Context:
         buf = DeviceBuffer(self, 4 * n)
         check(lib.glb_buffer_fill_f32(self.handle, buf.ptr, float(value), n))
         return buf
+
+
+class Graph:
+    """A recorded launch sequence (glb_graph_t)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def launch(self):
+        check(lib.glb_graph_launch(self.ctx.handle, self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.glb_graph_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 class DeviceBuffer:
@@ -275,6 +314,16 @@ class CsrMatrix:
         check(lib.glb_spmv_host(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x_host), _ptr(mask_host),
                                 _ptr(y_host)))
 
+    def spmv_host_batch(self, op, zero, mask_type, x_hosts, mask_hosts, y_hosts):
+        """Pipelined glb_spmv_host over a sequence of host vectors (addresses or objects _ptr accepts)."""
+        n = len(x_hosts)
+        assert len(y_hosts) == n and (mask_hosts is None or len(mask_hosts) == n)
+        arr = C.c_void_p * n
+        xs = arr(*[_ptr(v) for v in x_hosts])
+        ys = arr(*[_ptr(v) for v in y_hosts])
+        ms = arr(*[_ptr(v) for v in mask_hosts]) if mask_hosts is not None else None
+        check(lib.glb_spmv_host_batch(self.ctx.handle, self.handle, op, zero, mask_type, n, xs, ms, ys))
+
     def close(self):
         if self.handle:
             lib.glb_csr_destroy(self.handle)
@@ -293,14 +342,23 @@ class Exchange:
     return the list of every rank's ``b`` in rank order (e.g. torch.distributed.all_gather_object)."""
 
     def __init__(self, ctx, n_floats, rank, nranks, all_gather_bytes, n_vectors=2):
-        h = _vp()
-        check(lib.glb_xchg_create(ctx.handle, int(n_floats), n_vectors, C.byref(h)))
-        self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, h, int(n_floats), rank, nranks
-        mine = (C.c_char * 64)()
-        check(lib.glb_xchg_export(h, mine))
-        handles = b"".join(all_gather_bytes(bytes(mine)))
-        assert len(handles) == 64 * nranks
-        check(lib.glb_xchg_connect(h, rank, nranks, C.c_char_p(handles)))
+        self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, None, int(n_floats), rank, nranks
+        # every rank reaches the handle exchange (a collective) whatever happened locally
+        mine, err = b"", None
+        try:
+            h = _vp()
+            check(lib.glb_xchg_create(ctx.handle, int(n_floats), n_vectors, C.byref(h)))
+            self.handle = h
+            buf = (C.c_char * 64)()
+            check(lib.glb_xchg_export(h, buf))
+            mine = bytes(buf)
+        except GlbError as e:
+            err = e
+        handles = all_gather_bytes(mine)
+        if err is not None or any(len(b) != 64 for b in handles):
+            self.close()
+            raise err or GlbError("peer exchange: another rank could not export its block")
+        check(lib.glb_xchg_connect(self.handle, rank, nranks, C.c_char_p(b"".join(handles))))
 
     def vector(self, which):
         p = _vp()

@@ -81,6 +81,10 @@ int glb_ctx_destroy(glb_ctx_t ctx) {
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+    for (auto &row : ctx->pipe_ev)
+        for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -338,6 +342,52 @@ int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank) {
     if (!ctx->nccl_comm) { glb_set_error("glb_allgather_f32: glb_comm_init was not called"); return GLB_ENCCL; }
     const float *send = buf + size_t(ctx->nccl_rank) * count_per_rank;
     GLB_NCCL(g_nccl.allgather(send, buf, count_per_rank, /*ncclFloat32*/ 7, ctx->nccl_comm, ctx->stream));
+    return GLB_OK;
+}
+
+// ------------------------------------------------------------------------ launch replay
+int glb_graph_begin(glb_ctx_t ctx) {
+    GLB_REQUIRE(ctx, "ctx is NULL");
+    GLB_REQUIRE(!ctx->timing, "kernel timing is on: switch it off before recording");
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    GLB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return GLB_OK;
+}
+
+int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out) {
+    GLB_REQUIRE(ctx && out, "NULL argument");
+    *out = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        glb_set_error("glb_graph_end: recording failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return GLB_ECUDA;
+    }
+    glb_graph_t g = new glb_graph_s();
+    g->device = ctx->device;
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        glb_set_error("glb_graph_end: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        delete g;
+        return GLB_ECUDA;
+    }
+    *out = g;
+    return GLB_OK;
+}
+
+int glb_graph_launch(glb_ctx_t ctx, glb_graph_t g) {
+    GLB_REQUIRE(ctx && g && g->exec, "NULL argument");
+    GLB_REQUIRE(g->device == ctx->device, "sequence was recorded on another device");
+    GLB_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    return GLB_OK;
+}
+
+int glb_graph_destroy(glb_graph_t g) {
+    if (!g) return GLB_OK;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
     return GLB_OK;
 }
 

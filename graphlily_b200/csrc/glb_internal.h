@@ -45,6 +45,9 @@ struct glb_ctx_s {
     void *staging = nullptr;
     size_t staging_bytes = 0;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]
 };
 
 // ---------------------------------------------------------------- lane-segment CSR (SpMV)
@@ -103,10 +106,13 @@ struct glb_csr_s {
     uint32_t n_hot = 0;            // entries of hot_cols (0 when tile_k == 0 or tile_k == num_cols: identity)
     uint32_t *hot_cols = nullptr;  // rank -> column
     float *hot_x = nullptr;        // x[hot_cols[.]], rebuilt by every SpMV launch
+    uint32_t *xbits = nullptr;     // or-and: one bit per stored column word, rebuilt by every or-and launch
+    bool all_nonzero = false;      // no stored value is 0.0f (or-and skips the value stream)
     int smem_carveout_pct = 20;
     uint32_t tile_threads = 0;     // > 0: persistent shared-memory-tile kernel with that many threads per CTA
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
+    float *dx2 = nullptr, *dmask2 = nullptr, *dy2 = nullptr;  // second slot of glb_spmv_host_batch
     size_t device_bytes = 0;
 };
 
@@ -144,6 +150,11 @@ struct glb_xchg_s {
     uint32_t epoch = 0;
 };
 extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
+
+struct glb_graph_s {
+    cudaGraphExec_t exec = nullptr;
+    int device = 0;
+};
 
 // launchers (defined in the .cu files)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,

@@ -67,6 +67,7 @@ struct SpmvParams {
     const uint32_t *__restrict__ nz_rows;
     const float *hot_x;   // x values of the hot columns, packed (or x itself when every column is hot)
     const float *x_cold;  // x - tile_k: cold column words index it directly
+    const uint32_t *xbits;  // or-and only: bit w = (x value of stored column word w) != 0, see pack_bits_kernel
     const float *mask;    // may alias assign_inout
     float *y;
     float *y_peer[GLB_MAX_PEERS];  // the same vector on the other GPUs of a row-sharded run (peer-mapped memory)
@@ -162,9 +163,19 @@ __device__ __forceinline__ float gather_x_tile(uint32_t tile_base, const float *
     return v;
 }
 
+// or-and flavour of the gather: only the truth value of x matters (spmv_module.h:497-500), so x is
+// packed to one bit per stored column word (pack_bits_kernel) and the gather reads the 32-bit word
+// holding it.  The bitmap is 1/32 of x: it stays L1-resident (all of it for graphs up to ~1.5 M
+// columns), so these gathers are L1 hits instead of L2 sector requests.
+__device__ __forceinline__ uint32_t gather_bit(const uint32_t *xbits, uint32_t c) {
+    return (__ldg(xbits + (c >> 5)) >> (c & 31u)) & 1u;
+}
+
 // One chunk (up to 8 groups of 128 non-zeros) by one warp.  TILE: the hot vector is in shared
 // memory at tile_base (persistent kernel), else it is read through L1.
-template <int OP, bool TILE>
+// BITS (or-and only): 0 = fp32 x gathers, 1 = bitmap gathers + value stream (a != 0 is tested),
+// 2 = bitmap gathers, pattern only (the formatter saw no stored zero: the value stream is not read).
+template <int OP, bool TILE, int BITS = 0>
 __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
                                               float *const stage, const uint32_t tile_base) {
     const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
@@ -175,7 +186,7 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
     for (int g = 0; g < kPrefetch; ++g) {
         if (g < n) {
             cq[g] = ld_stream_v4(gp + g * 64);
-            aq[g] = ld_stream_v4(gp + g * 64 + 32);
+            if (BITS != 2) aq[g] = ld_stream_v4(gp + g * 64 + 32);
         }
     }
     const uint32_t fw = ld_stream_u32(P.flags + size_t(chunk) * 32 + lane);
@@ -200,18 +211,21 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
         if (g < n) {
             if (g + kPrefetch < GLB_MAX_GROUPS && g + kPrefetch < n) {
                 cq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64);
-                aq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64 + 32);
+                if (BITS != 2) aq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64 + 32);
             }
-            const uint4 c4 = cq[g % (kPrefetch + 1)], a4 = aq[g % (kPrefetch + 1)];
+            const uint4 c4 = cq[g % (kPrefetch + 1)];
+            const uint4 a4 = (BITS != 2) ? aq[g % (kPrefetch + 1)] : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
             const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
             float xv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+            for (int e = 0; e < 4; ++e) {
+                if (BITS) xv[e] = __uint_as_float(gather_bit(P.xbits, c[e]) * 0x3f800000u);  // 0.0f / 1.0f
+                else xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float prod = Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
+                const float prod = (BITS == 2) ? xv[e] : Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
                 if (fw & (1u << (4 * g + e))) {
                     *sp++ = acc;
                     acc = Semi<OP>::ident();
@@ -262,6 +276,35 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kerne
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
     if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
     process_chunk<OP, false>(P, chunk, lane, stage_all[wib], 0u);
+}
+
+// Variant BITS (or-and): as above with x packed to a bitmap by pack_bits_kernel.
+template <int BITS>
+__global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_kernel(const SpmvParams P) {
+    __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wib = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
+    if (chunk >= P.n_chunks) return;
+    process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS>(P, chunk, lane, stage_all[wib], 0u);
+}
+
+// xbits: bit w = truth value of the x entry that stored column word w refers to.  Words below
+// tile_k are hot ranks (x[hot_cols[w]], or x[w] under the identity numbering), the others are
+// tile_k + column.  One warp packs 32 consecutive words with a ballot.
+__global__ void __launch_bounds__(kThreads) pack_bits_kernel(const float *__restrict__ x, const uint32_t *__restrict__ hot_cols,
+                                                           uint32_t *__restrict__ xbits, uint32_t tile_k, uint32_t n_hot,
+                                                           uint32_t num_cols, uint32_t n_words32) {
+    const uint32_t w = blockIdx.x * kThreads + threadIdx.x;  // grid covers n_words32 * 32 exactly
+    bool t = false;
+    if (w < tile_k) {
+        const uint32_t c = n_hot ? __ldg(hot_cols + w) : w;
+        t = (c < num_cols) && __ldg(x + c) != 0.0f;
+    } else if (w - tile_k < num_cols) {
+        t = __ldg(x + (w - tile_k)) != 0.0f;
+    }
+    const unsigned b = __ballot_sync(kFull, t);
+    if ((threadIdx.x & 31u) == 0 && (w >> 5) < n_words32) xbits[w >> 5] = b;
 }
 
 // ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
@@ -394,6 +437,16 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
         if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
         spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
+    } else if (P.n_chunks && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
+        const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        static thread_local int bits_carveout_set = -1;
+        if (bits_carveout_set != m->smem_carveout_pct) {
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, m->smem_carveout_pct));
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, m->smem_carveout_pct));
+            bits_carveout_set = m->smem_carveout_pct;
+        }
+        if (m->all_nonzero) spmv_lane_bits_kernel<2><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else spmv_lane_bits_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(P);
     } else if (P.n_chunks) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
         static thread_local int carveout_set[3] = {-1, -1, -1};
@@ -448,7 +501,15 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.chunk_first = m->chunk_first;
     P.nz_rows = m->nz_rows;
     P.tile_k = m->tile_k;
-    if (m->n_hot && m->n_chunks) {  // pack the x values of the hot columns
+    if (op == GLB_OP_LOGICAL_AND_OR && m->xbits && m->n_chunks && !m->tile_threads) {
+        // or-and: one bit per stored column word replaces the fp32 gathers
+        const uint32_t n_words32 = (m->tile_k + m->num_cols + 31u) / 32u;
+        const uint32_t threads = n_words32 * 32u;
+        pack_bits_kernel<<<(threads + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->xbits, m->tile_k,
+                                                                                          m->n_hot, m->num_cols, n_words32);
+        P.xbits = m->xbits;
+        P.hot_x = x;
+    } else if (m->n_hot && m->n_chunks) {  // pack the x values of the hot columns
         gather_hot_kernel<<<(m->n_hot + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->hot_x,
                                                                                             m->n_hot);
         P.hot_x = m->hot_x;
@@ -495,6 +556,7 @@ struct HostLayout {
     std::vector<glb_fixup_t> fix_short, fix_long;
     uint64_t nnz = 0, sb = 0;
     uint32_t n_chunks = 0, n_groups = 0, tile_k = 0;
+    bool all_nonzero = false;  // no stored value is 0.0f: or-and may skip the value stream
     ~HostLayout() { free(stream); }
 };
 
@@ -631,6 +693,12 @@ static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *ind
     L.stream = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * 256 * size_t(L.n_groups ? L.n_groups : 1)));
     if (!L.stream) { glb_set_error("glb_csr_create: host allocation failed"); return GLB_ENOMEM; }
     const uint32_t *dbits = reinterpret_cast<const uint32_t *>(data ? data + sb : nullptr);
+    L.all_nonzero = false;
+    if (data) {
+        bool any_zero = false;
+        for (uint64_t i = 0; i < nnz && !any_zero; ++i) any_zero = (data[sb + i] == 0.0f);
+        L.all_nonzero = !any_zero;
+    }
     const uint32_t *encp = enc.empty() ? nullptr : enc.data();
     parallel_for(n_chunks, 256, [&](size_t cb, size_t ce) {
         for (size_t c = cb; c < ce; ++c) {
@@ -745,6 +813,7 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     m->tile_k = L.tile_k;
     m->n_hot = uint32_t(L.hot_cols.size());
     m->smem_carveout_pct = int(carveout > 100 ? 100 : carveout);
+    m->all_nonzero = L.all_nonzero;
     // the shared-memory flavour needs the tile, the staging arrays and the barrier in 227 KB
     if (L.tile_k == 0 || size_t((L.tile_k + 3u) & ~3u) * 4 + size_t(tile_threads / 32) * GLB_ROW_CAP * 4 + 16 > 227 * 1024)
         tile_threads = 0;
@@ -764,6 +833,9 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
         rc = upload(ctx, &m->hot_cols, L.hot_cols.data(), L.hot_cols.size(), L.hot_cols.size(), &bytes);
         if (!rc) rc = upload<float>(ctx, &m->hot_x, nullptr, 0, m->n_hot, &bytes);
     }
+    //   GLB_SPMV_BITS=0              or-and SpMV gathers fp32 x like the other semirings (default 1: bitmap)
+    if (!rc && env_u32("GLB_SPMV_BITS", 1) && L.n_chunks)
+        rc = upload<uint32_t>(ctx, &m->xbits, nullptr, 0, (size_t(L.tile_k) + num_cols + 31) / 32 + 1, &bytes);
     if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -782,8 +854,9 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->stream); cudaFree(m->flags); cudaFree(m->chunk_goff); cudaFree(m->chunk_first); cudaFree(m->nz_rows);
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
-    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x);
+    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
+    cudaFree(m->dx2); cudaFree(m->dmask2); cudaFree(m->dy2);
     delete m;
     return GLB_OK;
 }
@@ -879,6 +952,67 @@ int glb_spmv_host(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type,
         GLB_CUDA(cudaMemcpyAsync(y_host + m->row_begin, m->dy + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
                                  ctx->stream));
     }
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GLB_OK;
+}
+
+// Pipelined flavour of glb_spmv_host for a sequence of independent vectors: three streams (upload,
+// kernels, download) over two device slots, so vector k+1 rides up the PCIe link and result k-1
+// rides down while the kernels work on vector k.  Every vector is still copied host -> device and
+// every result device -> host; what changes is that the three legs of consecutive vectors overlap
+// (PCIe is full duplex and the copy engines run beside the SMs).  Host buffers should be page-locked
+// (glb_host_alloc); pageable ones work but their copies do not overlap.
+int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, int n_vectors,
+                        const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts) {
+    GLB_REQUIRE(ctx && m && x_hosts && y_hosts && n_vectors >= 0, "bad argument");
+    GLB_REQUIRE(m->ctx == ctx, "matrix belongs to another context");
+    GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask_hosts, "mask_hosts is NULL but mask_type != kNoMask");
+    for (int k = 0; k < n_vectors; ++k) {
+        GLB_REQUIRE(x_hosts[k] && y_hosts[k], "NULL vector in the batch");
+        GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask_hosts[k], "NULL mask in the batch");
+    }
+    if (n_vectors == 0) return GLB_OK;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_in) GLB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) GLB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (auto &row : ctx->pipe_ev)
+        for (cudaEvent_t &e : row)
+            if (!e) GLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const bool masked = mask_type != GLB_MASK_NONE;
+    float **dxs[2] = {&m->dx, &m->dx2}, **dms[2] = {&m->dmask, &m->dmask2}, **dys[2] = {&m->dy, &m->dy2};
+    for (int s = 0; s < 2; ++s) {
+        if (!*dxs[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dxs[s]), sizeof(float) * m->num_cols));
+        if (!*dys[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dys[s]), sizeof(float) * m->num_rows));
+        if (masked && !*dms[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dms[s]), sizeof(float) * m->num_rows));
+    }
+    cudaEvent_t *uploaded = ctx->pipe_ev[0], *computed = ctx->pipe_ev[1], *downloaded = ctx->pipe_ev[2];
+    const size_t nr = size_t(m->row_end - m->row_begin);
+    // work already queued on the caller's stream (an earlier glb_spmv_host may still read slot 0) goes first
+    GLB_CUDA(cudaEventRecord(computed[0], ctx->stream));
+    GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, computed[0], 0));
+    for (int k = 0; k < n_vectors; ++k) {
+        const int s = k & 1;
+        // upload k: slot s is free once the kernels of vector k-2 have read it
+        if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, computed[s], 0));
+        GLB_CUDA(cudaMemcpyAsync(*dxs[s], x_hosts[k], sizeof(float) * m->num_cols, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (masked)
+            GLB_CUDA(cudaMemcpyAsync(*dms[s], mask_hosts[k], sizeof(float) * m->num_rows, cudaMemcpyHostToDevice, ctx->copy_in));
+        GLB_CUDA(cudaEventRecord(uploaded[s], ctx->copy_in));
+        // kernels k: need the upload, and the download of result k-2 must have drained dy[s]
+        GLB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[s], 0));
+        if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[s], 0));
+        int rc = glb_spmv(ctx, m, op, zero, mask_type, *dxs[s], masked ? *dms[s] : nullptr, *dys[s]);
+        if (rc) return rc;
+        GLB_CUDA(cudaEventRecord(computed[s], ctx->stream));
+        // download k
+        GLB_CUDA(cudaStreamWaitEvent(ctx->copy_out, computed[s], 0));
+        GLB_CUDA(cudaMemcpyAsync(y_hosts[k] + m->row_begin, *dys[s] + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
+                                 ctx->copy_out));
+        GLB_CUDA(cudaEventRecord(downloaded[s], ctx->copy_out));
+    }
+    // the caller's stream ends after the last download, so stream-ordered work and events that follow see it
+    GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[(n_vectors - 1) & 1], 0));
+    if (n_vectors >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[n_vectors & 1], 0));
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
     return GLB_OK;
 }

@@ -46,10 +46,16 @@ class BaseModule:
     def _dense_to_device(self, vec):
         return self.ctx.to_device(np.ascontiguousarray(vec, np.float32))
 
-    def _constant_on_device(self, n, value, index=None, index_value=None):
+    def _constant_on_device(self, n, value, index=None, index_value=None, reuse=None):
         """A start vector that is constant but for one element, built on the device (a fill kernel
-        and a 4-byte copy) instead of uploading n floats."""
-        buf = self.ctx.zeros_f32(n, value)
+        and a 4-byte copy) instead of uploading n floats.  ``reuse``: an existing buffer of the
+        right size is refilled in place, so the app loops see the same addresses call after call
+        (their recorded launch sequences stay valid)."""
+        if reuse is not None and reuse.ptr and reuse.nbytes == 4 * n:
+            buf = reuse
+            capi.check(capi.lib.glb_buffer_fill_f32(self.ctx.handle, buf.ptr, float(value), n))
+        else:
+            buf = self.ctx.zeros_f32(n, value)
         if index is not None:
             buf.write_at(4 * int(index), np.array([index_value], np.float32))
         return buf
@@ -97,19 +103,23 @@ class SpMVModule(BaseModule):
         self.mask_buf = self._dense_to_device(mask)          # spmv_module.h:444-459
 
     def set_vector_constant(self, value, index=None, index_value=None):
-        self.vector_buf = self._constant_on_device(self.get_num_cols(), value, index, index_value)
+        self.vector_buf = self._constant_on_device(self.get_num_cols(), value, index, index_value, self.vector_buf)
 
     def set_mask_constant(self, value, index=None, index_value=None):
-        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value)
+        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value, self.mask_buf)
 
     def bind_mask_buf(self, src_buf):
         self.mask_buf = src_buf                              # spmv_module.h:463-467
 
     def run(self, epilogue=None):
         """spmv_module.h:471-475"""
+        self.run_with(self.vector_buf, self.mask_buf, self.results_buf, epilogue)
+
+    def run_with(self, vector_buf, mask_buf, results_buf, epilogue=None):
+        """run() on explicit buffers (the app loops ping-pong vector / results instead of copying)."""
         op, _one, zero = self.semiring_
-        self.matrix.spmv(op, zero, self.mask_type_, self.vector_buf,
-                         self.mask_buf if self.mask_type_ != capi.MASK_NONE else None, self.results_buf, epilogue)
+        self.matrix.spmv(op, zero, self.mask_type_, vector_buf,
+                         mask_buf if self.mask_type_ != capi.MASK_NONE else None, results_buf, epilogue)
 
     def send_vector_device_to_host(self):
         return self.vector_buf.read(np.float32, self.get_num_cols())
@@ -164,7 +174,7 @@ class SpMSpVModule(BaseModule):
         self.mask_buf = self._dense_to_device(mask)          # spmspv_module.h:403-433
 
     def set_mask_constant(self, value, index=None, index_value=None):
-        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value)
+        self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value, self.mask_buf)
 
     def bind_mask_buf(self, src_buf):
         self.mask_buf = src_buf

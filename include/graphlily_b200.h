@@ -193,6 +193,14 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
 int glb_spmv_host(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x_host,
                   const float *mask_host, float *y_host);
 
+/* The same sequence for n_vectors independent vectors (the loop of bench_spmv.cpp:96-104 with a
+ * fresh host vector per run), pipelined: upload of vector k+1, kernels of vector k and download of
+ * result k-1 run concurrently on three streams over two device slots.  y_hosts[k] receives rows
+ * [row_begin, row_end) of A (+).(x) x_hosts[k]; mask_hosts may be NULL when mask_type is kNoMask.
+ * Returns after the last result has landed. */
+int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, int n_vectors,
+                        const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts);
+
 /* ------------------------------------------------------------------ overlay mode 2
  * kernel_spmspv (kernel_spmspv_impl.h:448-562) == SpMSpVModule::compute_reference_results
  * (spmspv_module.h:446-520) followed by the device's sparse write-back: for each active
@@ -266,6 +274,22 @@ int glb_xchg_status(glb_xchg_t xc, int *timed_out);
 int glb_xchg_destroy(glb_xchg_t xc);
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
                       int dst_vec, const float *mask, const glb_spmv_epilogue_t *ep);
+
+/* ------------------------------------------------------------------ launch replay ------
+ * The reference drains its queue after every module run (spmv_module.h:471-475); an app
+ * iteration is 2-3 such launches (bfs.h:117-124).  Here launches are stream-ordered, and a fixed
+ * sequence (the iteration loop of an app: same buffers, same per-iteration scalars) can be
+ * recorded once as a CUDA graph and replayed with one call:
+ *   glb_graph_begin   every glb_* launch on this context that follows is recorded, not executed
+ *                     (no blocking call -- copies to / from the host, glb_ctx_sync, glb_sparse_count,
+ *                     buffer allocation, glb_spmv_exchange -- may be made while recording)
+ *   glb_graph_end     stops recording and returns the executable sequence
+ *   glb_graph_launch  enqueues the whole sequence on the context's stream */
+typedef struct glb_graph_s *glb_graph_t;
+int glb_graph_begin(glb_ctx_t ctx);
+int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out);
+int glb_graph_launch(glb_ctx_t ctx, glb_graph_t g);
+int glb_graph_destroy(glb_graph_t g);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,32 @@ def test_spmv_powerlaw_1m_nnz(ctx, oracle, op, zero):
     check_vec(gpu_spmv(ctx, m, op, zero, 0, x, None), oracle.port.spmv(m, op, zero, 0, x), op)
 
 
+@pytest.mark.parametrize("stored_zeros", [False, True])
+def test_spmv_or_and_bitmap_hot_and_cold_columns(ctx, oracle, stored_zeros):
+    # or-and packs x to one bit per stored column word (pack_bits_kernel): more columns than tile_k so
+    # both the hot-rank and the cold-column bit ranges are read; with and without stored 0.0 values
+    # (pattern-only kernel vs value-testing kernel); x holds negative, tiny, -0.0 and NaN entries.
+    rng = np.random.default_rng(77)
+    n = 100_003
+    m = datasets.powerlaw_csr(6000, n, 400_000, seed=13, max_degree=50_000, value=3.0)
+    if stored_zeros:
+        m.data = rng.integers(0, 2, m.nnz).astype(np.float32) * np.float32(-2.5)
+    x = np.zeros(n, np.float32)
+    pick = rng.random(n)
+    x[pick < 0.02] = 1.0
+    x[(pick >= 0.02) & (pick < 0.03)] = -1e-42   # denormal: still true
+    x[(pick >= 0.03) & (pick < 0.04)] = -0.0
+    x[(pick >= 0.04) & (pick < 0.045)] = np.nan
+    mask = rng.integers(0, 2, m.num_rows).astype(np.float32)
+    for mt in MASKS:
+        for zero in (0.0, 1.0):
+            check_vec(gpu_spmv(ctx, m, 1, zero, mt, x, mask), oracle.port.spmv(m, 1, zero, mt, x, mask), 1)
+    ref = oracle.port.spmv(m, 1, 0.0, 0, x)
+    y = gpu_spmv(ctx, m, 1, 0.0, 0, x, None, 1000, 4097, y_init=-7.0)
+    assert y[1000:4097].tobytes() == ref[1000:4097].tobytes()
+    assert (y[:1000] == -7.0).all() and (y[4097:] == -7.0).all()
+
+
 def test_spmv_empty_matrix_and_zero_value(ctx, oracle):
     m = CSRMatrix(6, 4, np.zeros(0, np.float32), np.zeros(0, np.uint32), np.zeros(7, np.uint32))
     x = np.ones(4, np.float32)
