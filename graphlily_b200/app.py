@@ -49,23 +49,60 @@ class ModuleCollection:
         for m in self.modules_:
             m.set_context(self.ctx)
 
+    def set_pinned_results(self, on=True):
+        """Result vectors are returned as the modules' page-locked host mirrors (valid until the next
+        run) instead of fresh copies: see BaseModule.pinned_results."""
+        for m in self.modules_:
+            m.pinned_results = bool(on)
+
     # -- multi-GPU: row-range sharding of the pull (SpMV) direction, SURVEY.md 8e -------------
     rank_, world_ = 0, 1
 
-    def set_sharding(self, rank, world):
-        """This process owns rows [rank, rank + 1) * N / world of the CSR; the context must already
-        hold an NCCL communicator of ``world`` ranks (``ctx.comm_init``).  After every SpMV the
-        full-length result is completed by one in-place allgather (``_exchange``)."""
+    exchange_ = None
+
+    def set_sharding(self, rank, world, exchange=None):
+        """This process owns rows [rank, rank + 1) * N / world of the CSR.  How the slices of y meet
+        before the next iteration:
+        * ``exchange`` = a connected ``capi.Exchange`` (>= 3 vectors of N floats): the SpMV
+          write-back stores every row into all ranks' copies over NVLink (``glb_spmv_exchange``);
+        * else the context must hold an NCCL communicator of ``world`` ranks (``ctx.comm_init``) and
+          one in-place allgather follows every SpMV."""
         assert 0 <= rank < world
-        self.rank_, self.world_ = rank, world
+        self.rank_, self.world_, self.exchange_ = rank, world, exchange
 
     def _row_range(self, n):
         assert n % self.world_ == 0, "padded dimension must divide by the number of ranks"
         slot = n // self.world_
         return self.rank_ * slot, (self.rank_ + 1) * slot
 
+    def _bind_exchange(self):
+        """After the matrix upload: vector / results / mask of the SpMV module become exchange vectors."""
+        xc = self.exchange_
+        if xc is None:
+            return
+        assert xc.n == self.matrix_num_rows_ and xc.n_vectors >= 3, "exchange must hold 3 vectors of the padded dimension"
+        self.SpMV_.exchange = xc
+        self.SpMV_.vector_buf, self.SpMV_.results_buf, self.SpMV_.mask_buf = xc.buffer(0), xc.buffer(1), xc.buffer(2)
+
+    def _begin_run(self):
+        """No rank starts writing into the peers' vectors before every rank has finished reading the
+        previous run's results out of them."""
+        if self.exchange_ is not None:
+            self.exchange_.barrier()
+
     def _exchange(self, buf, n):
-        if self.world_ > 1:
+        """After every SpMV.  With peer-mapped vectors the exchange already happened in the write-back."""
+        if self.world_ > 1 and self.exchange_ is None:
+            self.ctx.allgather_f32(buf, n // self.world_)
+
+    def _gather(self, buf, n):
+        """Completes a vector whose rows were updated shard-locally (BFS distance, at the end)."""
+        if self.world_ == 1:
+            return
+        if self.exchange_ is not None:
+            slot = n // self.world_
+            self.exchange_.allgather(buf.tag[1], self.rank_ * slot, slot)
+        else:
             self.ctx.allgather_f32(buf, n // self.world_)
 
     # -- launch replay: the iteration loop of an app is a fixed launch sequence ------------------
@@ -134,6 +171,7 @@ class BFS(ModuleCollection):
 
     def send_matrix_host_to_device(self):
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
+        self._bind_exchange()
         if self.world_ == 1:   # the push direction is single-GPU in this round
             self.SpMSpV_.send_matrix_host_to_device()
 
@@ -169,12 +207,13 @@ class BFS(ModuleCollection):
     def pull(self, source, num_iterations, fused=True):
         """bfs.h:106-126"""
         n = self.matrix_num_rows_
+        self._begin_run()
         # input = zero but input[source] = 1; distance = 0 but distance[source] = 1 (bfs.h:108-112),
         # built on the device instead of uploaded
         self.SpMV_.set_vector_constant(self.semiring_[2], source, 1.0)
         self.SpMV_.set_mask_constant(0.0, source, 1.0)
         self._pull_loop(1, num_iterations, fused)
-        self._exchange(self.SpMV_.mask_buf, n)
+        self._gather(self.SpMV_.mask_buf, n)
         return self.SpMV_.send_mask_device_to_host()
 
     # -- push ------------------------------------------------------------------------
@@ -249,10 +288,12 @@ class PageRank(ModuleCollection):
 
     def send_matrix_host_to_device(self):
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
+        self._bind_exchange()
 
     def pull(self, damping, num_iterations, fused=True):
         """pagerank.h:80-90"""
         n = self.matrix_num_rows_
+        self._begin_run()
         teleport = float((np.float32(1) - np.float32(damping)) / np.float32(n))
         self.SpMV_.set_vector_constant(float(np.float32(1.0 / n)))   # rank0 = 1 / N, pagerank.h:81-82
         if fused:
@@ -314,6 +355,7 @@ class SSSP(ModuleCollection):
 
     def send_matrix_host_to_device(self):
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
+        self._bind_exchange()
         if self.world_ == 1:   # the push direction is single-GPU in this round
             self.SpMSpV_.send_matrix_host_to_device()
 
@@ -343,6 +385,7 @@ class SSSP(ModuleCollection):
 
     def pull(self, source, num_iterations, fused=True):
         """sssp.h:152-166"""
+        self._begin_run()
         self.SpMV_.set_vector_constant(self.semiring_[2], source, 0.0)   # sssp.h:153-156
         self._pull_loop(1, num_iterations, fused)
         return self.SpMV_.send_vector_device_to_host()

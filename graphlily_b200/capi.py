@@ -94,6 +94,8 @@ SIGNATURES = {
     "glb_xchg_export": (C.c_int, [_vp, _vp]),
     "glb_xchg_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "glb_xchg_vector": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "glb_xchg_allgather": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_size_t]),
+    "glb_xchg_barrier": (C.c_int, [_vp, _vp]),
     "glb_xchg_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "glb_xchg_destroy": (C.c_int, [_vp]),
     "glb_spmv_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp, C.POINTER(Epilogue)]),
@@ -235,6 +237,15 @@ class DeviceBuffer:
         check(lib.glb_buffer_alloc(ctx.handle, int(nbytes), C.byref(p)))
         self.ctx, self.ptr, self.nbytes = ctx, p.value, int(nbytes)
 
+    owned, tag = True, None
+
+    @classmethod
+    def view(cls, ctx, ptr, nbytes, tag=None):
+        """Non-owning handle over device memory that belongs to something else (an exchange vector)."""
+        b = cls.__new__(cls)
+        b.ctx, b.ptr, b.nbytes, b.owned, b.tag = ctx, int(ptr), int(nbytes), False, tag
+        return b
+
     def write(self, array):
         array = np.ascontiguousarray(array)
         assert array.nbytes <= self.nbytes
@@ -246,8 +257,12 @@ class DeviceBuffer:
         assert byte_offset + array.nbytes <= self.nbytes
         check(lib.glb_buffer_h2d(self.ctx.handle, self.ptr + byte_offset, array.ctypes.data, array.nbytes))
 
-    def read(self, dtype, count):
-        out = np.empty(count, dtype=dtype)
+    def read(self, dtype, count, out=None):
+        """Blocking copy to the host: a fresh array, or ``out`` (e.g. a PinnedArray's view)."""
+        if out is None:
+            out = np.empty(count, dtype=dtype)
+        assert out.dtype == np.dtype(dtype) and out.size >= count and out.nbytes <= max(self.nbytes, out.nbytes)
+        out = out[:count]
         assert out.nbytes <= self.nbytes
         check(lib.glb_buffer_d2h(self.ctx.handle, out.ctypes.data, self.ptr, out.nbytes))
         return out
@@ -260,13 +275,34 @@ class DeviceBuffer:
         return body["index"].copy(), body["val"].copy()
 
     def free(self):
-        if self.ptr and self.ctx.handle:
+        if self.owned and self.ptr and self.ctx.handle:
             lib.glb_buffer_free(self.ctx.handle, self.ptr)
         self.ptr = None
 
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """Page-locked host array (glb_host_alloc): copies to / from it run at full PCIe speed and are
+    not staged.  ``.array`` is a numpy view; the memory is released with the object."""
+
+    def __init__(self, count, dtype=np.float32):
+        dtype = np.dtype(dtype)
+        p = _vp()
+        check(lib.glb_host_alloc(max(1, count * dtype.itemsize), C.byref(p)))
+        self.ptr = p.value
+        self.array = np.frombuffer((C.c_char * (count * dtype.itemsize)).from_address(self.ptr), dtype=dtype, count=count)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                lib.glb_host_free(self.ptr)
+                self.ptr = None
         except Exception:
             pass
 
@@ -343,6 +379,7 @@ class Exchange:
 
     def __init__(self, ctx, n_floats, rank, nranks, all_gather_bytes, n_vectors=2):
         self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, None, int(n_floats), rank, nranks
+        self.n_vectors = n_vectors
         # every rank reaches the handle exchange (a collective) whatever happened locally
         mine, err = b"", None
         try:
@@ -368,6 +405,16 @@ class Exchange:
     def spmv(self, matrix, op, zero, mask_type, src_vec, dst_vec, mask=None, epilogue=None):
         check(lib.glb_spmv_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
                                     _ptr(mask), C.byref(epilogue) if epilogue is not None else None))
+
+    def buffer(self, which):
+        """Vector ``which`` as a (non-owning) DeviceBuffer."""
+        return DeviceBuffer.view(self.ctx, self.vector(which), 4 * self.n, tag=("xchg", which))
+
+    def allgather(self, which, offset, count):
+        check(lib.glb_xchg_allgather(self.ctx.handle, self.handle, which, offset, count))
+
+    def barrier(self):
+        check(lib.glb_xchg_barrier(self.ctx.handle, self.handle))
 
     def timed_out(self):
         t = C.c_int(0)

@@ -74,8 +74,28 @@ int glb_ctx_create(int device, void *cuda_stream, glb_ctx_t *out) {
     return GLB_OK;
 }
 
+}  // extern "C"
+
+static void ctx_free(glb_ctx_t ctx);
+void glb_ctx_retain(glb_ctx_t ctx) { ctx->children++; }
+void glb_ctx_release(glb_ctx_t ctx) {
+    if (--ctx->children == 0 && ctx->destroyed) ctx_free(ctx);
+}
+
+extern "C" {
+
 int glb_ctx_destroy(glb_ctx_t ctx) {
-    if (!ctx) return GLB_OK;
+    if (!ctx || ctx->destroyed) return GLB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->destroyed = true;
+    if (ctx->children == 0) ctx_free(ctx);
+    return GLB_OK;
+}
+
+}  // extern "C"
+
+static void ctx_free(glb_ctx_t ctx) {
     cudaSetDevice(ctx->device);
     glb_comm_destroy(ctx);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
@@ -88,8 +108,9 @@ int glb_ctx_destroy(glb_ctx_t ctx) {
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
-    return GLB_OK;
 }
+
+extern "C" {
 
 int glb_ctx_sync(glb_ctx_t ctx) {
     GLB_REQUIRE(ctx, "ctx is NULL");
@@ -366,10 +387,13 @@ int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out) {
     }
     glb_graph_t g = new glb_graph_s();
     g->device = ctx->device;
+    g->ctx = ctx;
+    glb_ctx_retain(ctx);
     e = cudaGraphInstantiate(&g->exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) {
         glb_set_error("glb_graph_end: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        glb_ctx_release(ctx);
         delete g;
         return GLB_ECUDA;
     }
@@ -387,6 +411,7 @@ int glb_graph_launch(glb_ctx_t ctx, glb_graph_t g) {
 int glb_graph_destroy(glb_graph_t g) {
     if (!g) return GLB_OK;
     if (g->exec) cudaGraphExecDestroy(g->exec);
+    glb_ctx_release(g->ctx);
     delete g;
     return GLB_OK;
 }
@@ -428,6 +453,7 @@ int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t 
     GLB_CUDA(cudaSetDevice(ctx->device));
     glb_xchg_t xc = new glb_xchg_s();
     xc->ctx = ctx;
+    glb_ctx_retain(ctx);
     xc->n = n_floats;
     xc->n_vectors = n_vectors;
     const size_t vec_bytes = (size_t(n_floats) * n_vectors * sizeof(float) + 255) & ~size_t(255);
@@ -489,6 +515,21 @@ int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr) {
     return GLB_OK;
 }
 
+int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc) {
+    GLB_REQUIRE(ctx && xc && xc->connected && xc->ctx == ctx, "exchange is not connected to this context");
+    return glb_xchg_signal_wait(ctx, xc);
+}
+
+int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count) {
+    GLB_REQUIRE(ctx && xc && xc->connected && xc->ctx == ctx, "exchange is not connected to this context");
+    GLB_REQUIRE(which >= 0 && which < xc->n_vectors && offset + count <= xc->n, "slice outside the vector");
+    const size_t at = size_t(which) * xc->n + offset;
+    for (int r = 0; r < xc->nranks && count; ++r)
+        if (r != xc->rank)
+            GLB_CUDA(cudaMemcpyAsync(xc->peer[r] + at, xc->local + at, count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return glb_xchg_signal_wait(ctx, xc);
+}
+
 int glb_xchg_status(glb_xchg_t xc, int *timed_out) {
     GLB_REQUIRE(xc && timed_out, "NULL argument");
     uint32_t e = 0;
@@ -507,6 +548,7 @@ int glb_xchg_destroy(glb_xchg_t xc) {
     cudaFree(xc->local);
     cudaFree(xc->d_peer_flags);
     cudaFree(xc->d_err);
+    glb_ctx_release(xc->ctx);
     delete xc;
     return GLB_OK;
 }

@@ -32,6 +32,11 @@ void glb_set_error(const char *fmt, ...);
 
 // ---------------------------------------------------------------- context
 struct glb_ctx_s {
+    // Matrices, exchanges and recorded sequences keep their context alive: glb_ctx_destroy with
+    // children outstanding only marks it, the last child's destroy releases it (hosts with garbage
+    // collection destroy objects in any order).
+    int children = 0;
+    bool destroyed = false;
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -153,8 +158,12 @@ extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal 
 
 struct glb_graph_s {
     cudaGraphExec_t exec = nullptr;
+    glb_ctx_t ctx = nullptr;
     int device = 0;
 };
+
+void glb_ctx_retain(glb_ctx_t ctx);
+void glb_ctx_release(glb_ctx_t ctx);  // child destroyed; frees the context if it was destroyed meanwhile
 
 // launchers (defined in the .cu files)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,

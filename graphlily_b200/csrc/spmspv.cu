@@ -193,6 +193,7 @@ int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     GLB_CUDA(cudaSetDevice(ctx->device));
     glb_csc_t m = new glb_csc_s();
     m->ctx = ctx;
+    glb_ctx_retain(ctx);
     m->num_rows = num_rows;
     m->num_cols = num_cols;
     m->nnz = nnz;
@@ -227,6 +228,7 @@ int glb_csc_destroy(glb_csc_t m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->counter);
+    glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
 }

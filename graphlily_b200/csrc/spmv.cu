@@ -799,6 +799,7 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
 
     glb_csr_t m = new glb_csr_s();
     m->ctx = ctx;
+    glb_ctx_retain(ctx);
     m->num_rows = num_rows;
     m->num_cols = num_cols;
     m->row_begin = row_begin;
@@ -857,6 +858,7 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
     cudaFree(m->dx2); cudaFree(m->dmask2); cudaFree(m->dy2);
+    glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
 }

@@ -263,6 +263,11 @@ int glb_allgather_f32(glb_ctx_t ctx, float *buf, size_t count_per_rank);
  *   glb_spmv_exchange y = A (+).(x) x with x = local vector src_vec, y rows written into vector
  *                     dst_vec of EVERY rank; returns after enqueueing the signal / wait, so the
  *                     next call on this stream sees the complete dst_vec.  Alternate src / dst.
+ *   glb_xchg_allgather every rank's slice [offset, offset + count) of vector `which` is copied into
+ *                     all peers' copies (peer-to-peer copies on the stream) + signal / wait: what
+ *                     ncclAllGather does for vectors the SpMV did not write (BFS distance at the end)
+ *   glb_xchg_barrier  signal / wait alone: no rank's later work on its stream starts before every
+ *                     rank's earlier work has finished (call between two runs that reuse the vectors)
  *   glb_xchg_status   synchronises; *timed_out != 0 if a peer never signalled (it died) */
 #define GLB_IPC_HANDLE_BYTES 64
 typedef struct glb_xchg_s *glb_xchg_t;
@@ -270,6 +275,8 @@ int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t 
 int glb_xchg_export(glb_xchg_t xc, void *handle64);
 int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles);
 int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr);
+int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count);
+int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc);
 int glb_xchg_status(glb_xchg_t xc, int *timed_out);
 int glb_xchg_destroy(glb_xchg_t xc);
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,

@@ -128,3 +128,33 @@ def test_pagerank_large_rows_against_fp64(ctx, oracle):
         r64 = a64 @ r64 + tele
     assert (np.abs(got - r64) <= 1e-5 * np.abs(r64)).all()
     assert (np.abs(got - ref) <= np.abs(ref - r64) + 1e-5 * np.abs(ref)).all()
+
+
+def test_replayed_loops_and_pinned_results_over_many_sources(ctx, oracle):
+    """The pull loops run as recorded launch sequences over buffers that are refilled in place: many
+    sources / iteration counts on one app object (odd counts swap the ping-pong roles between
+    calls), with graphs on and off, and with the page-locked result mirrors."""
+    g = datasets.powerlaw_graph(20000, 400000, seed=6, diagonal=True)
+    mb, ms = prep_bfs(oracle, g), prep_sssp(oracle, g)
+    bfs, s = app.BFS(), app.SSSP()
+    for a in (bfs, s):
+        a.set_up_runtime(None, ctx=ctx)
+        a.load_and_format_matrix(g)
+        a.send_matrix_host_to_device()
+    for pinned in (False, True):
+        bfs.set_pinned_results(pinned)
+        s.set_pinned_results(pinned)
+        for src, iters in ((0, 3), (7, 4), (123, 3), (19999, 5), (7, 4), (0, 3)):
+            for graphs in (True, False):
+                bfs.use_graphs_ = s.use_graphs_ = graphs
+                assert bfs.pull(src, iters).tobytes() == oracle.port.bfs(mb, src, iters).tobytes(), (src, iters, graphs)
+                assert s.pull(src, iters).tobytes() == oracle.port.sssp(ms, src, iters).tobytes(), (src, iters, graphs)
+                assert bfs.pull_push(src, iters, 0.01).tobytes() == oracle.port.bfs(mb, src, iters).tobytes()
+    mp = prep_pagerank(oracle, g, 0.85)
+    pr = app.PageRank()
+    pr.set_up_runtime(None, ctx=ctx)
+    pr.load_and_format_matrix(g, 0.85)
+    pr.send_matrix_host_to_device()
+    pr.set_pinned_results(True)
+    for iters in (3, 4, 3, 1):
+        assert_close_rel(pr.pull(0.85, iters), oracle.port.pagerank(mp, 0.85, iters), 1e-5)

@@ -1,0 +1,108 @@
+"""Row-sharded runs on 2 GPUs (skipped on a 1-GPU box): the peer-mapped exchange
+(``glb_spmv_exchange`` -- SpMV write-back stores rows into every rank's vectors over NVLink, CUDA IPC
+between the per-GPU processes) and the apps on top of it, each against the oracle on the full
+matrix.  One process per GPU; gloo carries the IPC handles."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from graphlily_b200 import app, capi, datasets
+    from graphlily_b200.io import CSRMatrix
+    from util import assert_close_rel
+
+    def all_gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    ctx = capi.Context(rank)
+    # ---- raw exchange: five ping-pong iterations x <- A x of each semiring ---------------------
+    n = 8192
+    m = datasets.powerlaw_csr(n, n, 1 << 18, seed=21, max_degree=5000, value=1.0 / 32)   # same seed on every rank
+    slot = n // world
+    A = capi.CsrMatrix(ctx, m, rank * slot, (rank + 1) * slot)
+    xc = capi.Exchange(ctx, n, rank, world, all_gather_bytes, n_vectors=3)
+    rng = np.random.default_rng(5)
+    for op, zero, x0 in ((0, 0.0, rng.random(n).astype(np.float32)),
+                         (1, 0.0, (rng.random(n) < 0.001).astype(np.float32)),
+                         (2, 255.0, np.where(rng.random(n) < 0.001, 0.0, 255.0).astype(np.float32))):
+        mm = m if op != 2 else CSRMatrix(n, n, np.ones(m.nnz, np.float32), m.indices, m.indptr)
+        Aop = A if op != 2 else capi.CsrMatrix(ctx, mm, rank * slot, (rank + 1) * slot)
+        xc.barrier()
+        xc.buffer(0).write(x0)
+        ref = x0
+        for it in range(5):
+            xc.spmv(Aop, op, zero, capi.MASK_NONE, it % 2, (it + 1) % 2)
+            ref = oracle.port.spmv(mm, op, zero, 0, ref)
+        got = xc.buffer(1).read(np.float32, n)
+        if op == 0:
+            assert_close_rel(got, ref, 1e-4)      # five iterations of 1e-5-per-step differences
+        else:
+            assert got.tobytes() == ref.tobytes(), f"rank {rank} op {op}"
+    # the slice gather
+    v = np.full(n, -1.0, np.float32)
+    v[rank * slot:(rank + 1) * slot] = rank + 1
+    xc.barrier()
+    xc.buffer(2).write(v)
+    xc.allgather(2, rank * slot, slot)
+    got = xc.buffer(2).read(np.float32, n)
+    assert (got.reshape(world, slot) == np.arange(1, world + 1, dtype=np.float32)[:, None]).all()
+    assert not xc.timed_out()
+    dist.barrier()
+    xc.close()
+
+    # ---- the apps over the exchange -------------------------------------------------------------
+    g = datasets.powerlaw_graph(4096, 60000, seed=2)
+    for name in ("bfs", "pagerank", "sssp"):
+        a = {"bfs": app.BFS, "pagerank": app.PageRank, "sssp": app.SSSP}[name]()
+        a.set_up_runtime(None, ctx=ctx)
+        a.load_and_format_matrix(*((g, 0.9) if name == "pagerank" else (g,)))
+        x2 = capi.Exchange(ctx, a.matrix_num_rows_, rank, world, all_gather_bytes, n_vectors=3)
+        a.set_sharding(rank, world, x2)
+        a.send_matrix_host_to_device()
+        mat = a.csr_matrix_
+        for rep in range(3):     # repeated runs reuse the vectors: the start-of-run barrier is under test
+            if name == "bfs":
+                got, ref = a.pull(rep, 5), oracle.port.bfs(mat, rep, 5)
+            elif name == "pagerank":
+                got, ref = a.pull(0.9, 3 + rep), oracle.port.pagerank(mat, 0.9, 3 + rep)
+            else:
+                got, ref = a.pull(rep, 4), oracle.port.sssp(mat, rep, 4, 255.0)
+            if name == "pagerank":
+                assert_close_rel(got, ref, 1e-5)
+            else:
+                assert got.tobytes() == ref.tobytes(), f"rank {rank} {name} run {rep}"
+        assert not x2.timed_out()
+        dist.barrier()
+        x2.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_and_apps_on_two_gpus():
+    from graphlily_b200 import capi
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    mp.start_processes(_worker, args=(2, _free_port()), nprocs=2, join=True, start_method="spawn")

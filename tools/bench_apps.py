@@ -39,6 +39,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graphs (debugging)")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--copy-results", action="store_true",
+                    help="return fresh host copies of the result vectors (the reference's semantics) instead of the "
+                         "modules' page-locked mirrors")
     args = ap.parse_args()
 
     import torch
@@ -55,10 +58,18 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = capi.Context(local_rank, stream.cuda_stream)
-    if world > 1:
+    # N > 1: "peer" (default) = SpMV write-back stores rows into every rank's vectors over NVLink
+    # (glb_spmv_exchange); GLB_EXCHANGE=nccl = one in-place ncclAllGather after every SpMV
+    exchange_kind = os.environ.get("GLB_EXCHANGE", "peer") if world > 1 else "none"
+    if exchange_kind == "nccl":
         uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
+
+    def all_gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
 
     def timed(fn, reps):
         fn()   # warm-up (also the result that is checked)
@@ -72,11 +83,26 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        # the iteration loop alone (device events around the app's launch sequence of the last call)
+        loop_ms = loop_ev[0].elapsed_time(loop_ev[1]) if loop_ev[2] else float("nan")
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms, loop_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out
+            ms, loop_ms = float(t[0].item()), float(t[1].item())
+        return ms, out, loop_ms
+
+    loop_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), False]
+
+    def instrument(a):
+        """Bracket the app's iteration loop (ModuleCollection._replay) with events on the stream."""
+        inner = a._replay
+
+        def bracketed(key, launches):
+            loop_ev[0].record(stream)
+            inner(key, launches)
+            loop_ev[1].record(stream)
+            loop_ev[2] = True
+        a._replay = bracketed
 
     def emit(name, cfg, nnz, iters, modes, check):
         if rank == 0:
@@ -102,36 +128,59 @@ def main():
             g = datasets.powerlaw_graph(n, nnz_target, seed=5, diagonal=True, device=dev)
             a = app.SSSP()
         a.set_up_runtime(None, ctx=ctx)
-        a.set_sharding(rank, world)
+        a.set_pinned_results(not args.copy_results)
+        instrument(a)
         if name == "pagerank":
             a.load_and_format_matrix(g, 0.9)
         else:
             a.load_and_format_matrix(g)
+        xc = capi.Exchange(ctx, a.matrix_num_rows_, rank, world, all_gather_bytes, n_vectors=3) if exchange_kind == "peer" else None
+        a.set_sharding(rank, world, xc)
         a.send_matrix_host_to_device()
         nnz = a.get_nnz()
         log(f"{name}: {n} vertices, nnz {nnz}, generated + formatted + uploaded in {time.time() - t0:.1f}s")
         cfg = {"vertices": n, "nnz": nnz, "generator": "graphlily_b200.datasets.powerlaw_graph (symmetric, Zipf 0.9)",
-               "sharding": f"row-range x{world} + NCCL allgather per iteration" if world > 1 else "none"}
+               "sharding": "none" if world == 1 else f"row-range x{world}, " + (
+                   "rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped memory)"
+                   if exchange_kind == "peer" else "NCCL allgather per iteration")}
         source = 0
         modes = {}
         results = {}
         if name == "pagerank":
-            ms, out = timed(lambda: a.pull(0.9, iters), args.reps)
+            ms, out, loop_ms = timed(lambda: a.pull(0.9, iters), args.reps)
             modes["pull"] = {"ms_total": ms, "ms_per_iteration": ms / iters, "iterations_per_sec": iters / ms * 1e3,
-                             "gteps": nnz / (ms / iters * 1e-3) / 1e9}
-            results["pull"] = out
+                             "gteps": nnz / (ms / iters * 1e-3) / 1e9, "loop_only_ms_per_iteration": loop_ms / iters,
+                             "loop_only_gteps": nnz / (loop_ms / iters * 1e-3) / 1e9}
+            results["pull"] = out.copy()
         else:
             run_modes = [("pull", lambda: a.pull(source, iters))]
             if world == 1:
                 run_modes += [("pull_push", lambda: a.pull_push(source, iters, 0.001 if name == "bfs" else 0.05)),
                               ("push", lambda: a.push(source, iters))]
             for mode, fn in run_modes:
-                ms, out = timed(fn, args.reps)
+                loop_ev[2] = False
+                ms, out, loop_ms = timed(fn, args.reps)
                 modes[mode] = {"ms_total": ms, "ms_per_iteration": ms / iters, "iterations_per_sec": iters / ms * 1e3,
                                "gteps": nnz * iters / (ms * 1e-3) / 1e9}
+                if mode == "pull":
+                    modes[mode].update(loop_only_ms_per_iteration=loop_ms / iters,
+                                       loop_only_iterations_per_sec=iters / loop_ms * 1e3,
+                                       loop_only_gteps=nnz * iters / (loop_ms * 1e-3) / 1e9)
                 if mode == "pull_push":
                     modes[mode]["push_iterations"] = a.push_iterations_
-                results[mode] = out
+                results[mode] = out.copy()   # the mirror is overwritten by the next mode
+        # where the time goes: kernels only (events inside the C ABI around every SpMV main / fix-up
+        # launch, this rank), next to the whole-call figure above (start vectors, exchange, read-back)
+        a.use_graphs_ = False
+        ctx.kernel_timing(True)
+        (a.pull(0.9, iters) if name == "pagerank" else a.pull(source, iters))
+        ms_main, ms_fix, launches = ctx.kernel_timing_read()
+        ctx.kernel_timing(False)
+        a.use_graphs_ = True
+        kt = torch.tensor([ms_main + ms_fix], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        modes["pull"]["spmv_kernels_ms_per_iteration_max_over_ranks"] = float(kt.item()) / max(launches, 1)
         check = None
         if not args.no_check and rank == 0:
             import oracle   # test infrastructure: the checker, never the thing measured
@@ -176,6 +225,10 @@ def main():
                 check["reached_vertices"] = int((ref != (0 if name == "bfs" else 255)).sum())
         emit(name, cfg, nnz, iters, modes, check)
         del a
+        if xc is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            xc.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
