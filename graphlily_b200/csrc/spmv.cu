@@ -88,6 +88,7 @@ struct SpmvParams {
     const glb_fixup_t *fix_long;
     const uint32_t *empty_rows;
     uint32_t n_fix_short, n_fix_long, n_empty;
+    uint32_t n_nz_rows;
 };
 
 // Everything that is read once (matrix stream, flags, row ids, mask) is kept out of L1 so it
@@ -175,7 +176,8 @@ __device__ __forceinline__ uint32_t gather_bit(const uint32_t *xbits, uint32_t c
 // memory at tile_base (persistent kernel), else it is read through L1.
 // BITS (or-and only): 0 = fp32 x gathers, 1 = bitmap gathers + value stream (a != 0 is tested),
 // 2 = bitmap gathers, pattern only (the formatter saw no stored zero: the value stream is not read).
-template <int OP, bool TILE, int BITS = 0>
+// MASKED: the launch has a mask (compile-time so that unmasked launches carry none of the skip logic).
+template <int OP, bool TILE, int BITS = 0, bool MASKED = true>
 __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
                                               float *const stage, const uint32_t tile_base) {
     const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
@@ -203,13 +205,31 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
     const uint32_t excl = incl - cnt;
     const uint32_t total = __shfl_sync(kFull, incl, 31);
 
+    // Rows the mask discards need no gathers (the pull BFS case: from the third level on almost
+    // every vertex is already visited).  The lane's run covers rows excl .. excl + cnt of the chunk;
+    // it is "live" unless every one of them is masked out (lanes with many short rows do not check).
+    // The mask vector may be the fused assign's inout, but a row is only ever assigned by the warp
+    // (or the fix-up launch) that finishes it, after these reads.
+    bool lane_live = true;
+    if (MASKED && P.mask_type != GLB_MASK_NONE && cnt <= 3u) {
+        lane_live = false;
+        const uint32_t ord_base = (cf & ~GLB_FLAG) + excl;
+        for (uint32_t j = 0; j <= cnt; ++j) {
+            const uint32_t ord = ord_base + j;
+            if (ord >= P.n_nz_rows) continue;  // the padding pseudo-row of the last chunk
+            const float mv = ld_stream_f32(P.mask + ld_stream_u32(P.nz_rows + ord));
+            lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? (mv == 0.0f) : (mv != 0.0f);
+        }
+    }
+    const bool chunk_live = !MASKED || __any_sync(kFull, lane_live);
+
     // the lane's run: serial reduction in registers; every flagged element closes the open row
     float *sp = stage + excl;
     float acc = Semi<OP>::ident();
 #pragma unroll
     for (int g = 0; g < GLB_MAX_GROUPS; ++g) {
         if (g < n) {
-            if (g + kPrefetch < GLB_MAX_GROUPS && g + kPrefetch < n) {
+            if (chunk_live && g + kPrefetch < GLB_MAX_GROUPS && g + kPrefetch < n) {
                 cq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64);
                 if (BITS != 2) aq[(g + kPrefetch) % (kPrefetch + 1)] = ld_stream_v4(gp + (g + kPrefetch) * 64 + 32);
             }
@@ -217,15 +237,18 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
             const uint4 a4 = (BITS != 2) ? aq[g % (kPrefetch + 1)] : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
             const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
-            float xv[4];
+            float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (!MASKED || lane_live) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (BITS) xv[e] = __uint_as_float(gather_bit(P.xbits, c[e]) * 0x3f800000u);  // 0.0f / 1.0f
-                else xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+                for (int e = 0; e < 4; ++e) {
+                    if (BITS) xv[e] = __uint_as_float(gather_bit(P.xbits, c[e]) * 0x3f800000u);  // 0.0f / 1.0f
+                    else xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
+                }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float prod = (BITS == 2) ? xv[e] : Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
+                float prod = (BITS == 2) ? xv[e] : Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
+                if (MASKED && !lane_live) prod = Semi<OP>::ident();  // every row of this lane is masked out
                 if (fw & (1u << (4 * g + e))) {
                     *sp++ = acc;
                     acc = Semi<OP>::ident();
@@ -268,25 +291,25 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
 }
 
 // Variant L1: one chunk per warp, hot x lines kept in L1 by the cache hints.
-template <int OP>
+template <int OP, bool MASKED>
 __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
     if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
-    process_chunk<OP, false>(P, chunk, lane, stage_all[wib], 0u);
+    process_chunk<OP, false, 0, MASKED>(P, chunk, lane, stage_all[wib], 0u);
 }
 
 // Variant BITS (or-and): as above with x packed to a bitmap by pack_bits_kernel.
-template <int BITS>
+template <int BITS, bool MASKED>
 __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_kernel(const SpmvParams P) {
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
     if (chunk >= P.n_chunks) return;
-    process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS>(P, chunk, lane, stage_all[wib], 0u);
+    process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS, MASKED>(P, chunk, lane, stage_all[wib], 0u);
 }
 
 // xbits: bit w = truth value of the x entry that stored column word w refers to.  Words below
@@ -441,22 +464,31 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
         static thread_local int bits_carveout_set = -1;
         if (bits_carveout_set != m->smem_carveout_pct) {
-            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, m->smem_carveout_pct));
-            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, m->smem_carveout_pct));
-            bits_carveout_set = m->smem_carveout_pct;
+            const int pct = m->smem_carveout_pct;
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            bits_carveout_set = pct;
         }
-        if (m->all_nonzero) spmv_lane_bits_kernel<2><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else spmv_lane_bits_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(P);
+        const bool masked = P.mask_type != GLB_MASK_NONE;
+        if (m->all_nonzero && masked) spmv_lane_bits_kernel<2, true><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else if (m->all_nonzero) spmv_lane_bits_kernel<2, false><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else if (masked) spmv_lane_bits_kernel<1, true><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else spmv_lane_bits_kernel<1, false><<<grid, kThreads, 0, ctx->stream>>>(P);
     } else if (P.n_chunks) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
         static thread_local int carveout_set[3] = {-1, -1, -1};
         if (carveout_set[OP] != m->smem_carveout_pct) {
-            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          m->smem_carveout_pct));
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           m->smem_carveout_pct));
             carveout_set[OP] = m->smem_carveout_pct;
         }
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        spmv_lane_kernel<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+        if (P.mask_type != GLB_MASK_NONE) spmv_lane_kernel<OP, true><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else spmv_lane_kernel<OP, false><<<grid, kThreads, 0, ctx->stream>>>(P);
     }
     if (ctx->timing) GLB_CUDA(cudaEventRecord(ev[1], ctx->stream));
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
@@ -537,6 +569,7 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_short = m->n_fix_short;
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
+    P.n_nz_rows = m->n_nz_rows;
     switch (op) {
         case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, m, P);
         case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);

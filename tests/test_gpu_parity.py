@@ -119,6 +119,24 @@ def test_spmv_or_and_bitmap_hot_and_cold_columns(ctx, oracle, stored_zeros):
     assert (y[:1000] == -7.0).all() and (y[4097:] == -7.0).all()
 
 
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+@pytest.mark.parametrize("density", [0.0, 0.003, 0.5, 1.0])
+def test_spmv_mask_driven_skipping(ctx, oracle, op, zero, density):
+    # lanes / chunks whose rows are all masked out skip their gathers: masks from "everything
+    # discarded" to "nothing discarded", over rows inside a lane, across lanes and across chunks
+    rng = np.random.default_rng(40 + op)
+    ip = [0]
+    for d in rng.choice([0, 1, 2, 3, 8, 31, 32, 33, 100, 1024, 1500, 5000, 40000], 400):
+        ip.append(ip[-1] + int(d))
+    nnz, ncols = ip[-1], 70_000
+    m = CSRMatrix(len(ip) - 1, ncols, (rng.random(nnz) + 0.5 if op == 0 else rng.integers(1, 3, nnz)).astype(np.float32),
+                  rng.integers(0, ncols, nnz).astype(np.uint32), np.array(ip, np.uint32))
+    x = (rng.integers(0, 2, ncols) * (1 + rng.random(ncols))).astype(np.float32)
+    keep = (rng.random(m.num_rows) < density).astype(np.float32)
+    for mt, mask in ((1, 1.0 - keep), (2, keep)):     # WriteToZero discards mask != 0, WriteToOne mask == 0
+        check_vec(gpu_spmv(ctx, m, op, zero, mt, x, mask), oracle.port.spmv(m, op, zero, mt, x, mask), op)
+
+
 def test_spmv_empty_matrix_and_zero_value(ctx, oracle):
     m = CSRMatrix(6, 4, np.zeros(0, np.float32), np.zeros(0, np.uint32), np.zeros(7, np.uint32))
     x = np.ones(4, np.float32)
