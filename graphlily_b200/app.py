@@ -251,6 +251,7 @@ class BFS(ModuleCollection):
         self.push_iterations_ = it - 1
         # switch: the last frontier becomes the dense SpMV input, on the device
         self.SpMV_.bind_mask_buf(self.SpMSpV_.mask_buf)
+        self.SpMV_.home_buffers()
         if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
             self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
         capi.sparse_to_dense(self.ctx, self.SpMSpV_.vector_buf, self.SpMV_.vector_buf, n, LogicalSemiring[2])
@@ -419,6 +420,7 @@ class SSSP(ModuleCollection):
                 break
         self.push_iterations_ = it - 1
         # switch: the distance vector becomes the SpMV input (device copy, no host round trip)
+        self.SpMV_.home_buffers()
         if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
             self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
         capi.d2d(self.ctx, self.SpMV_.vector_buf, self.SpMSpV_.mask_buf, 4 * n)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "glb_buffer_d2h_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "glb_buffer_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "glb_buffer_fill_f32": (C.c_int, [_vp, _vp, C.c_float, C.c_size_t]),
+    "glb_buffer_fill_one_f32": (C.c_int, [_vp, _vp, C.c_float, C.c_size_t, C.c_size_t, C.c_float]),
     "glb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "glb_host_free": (C.c_int, [_vp]),
     "glb_csr_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),

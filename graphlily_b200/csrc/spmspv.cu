@@ -142,6 +142,12 @@ __global__ void fill_f32_kernel(float *dst, float val, size_t n) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = val;
 }
 
+// start vector of an app: constant but for one element (bfs.h:108-112, sssp.h:153-156)
+__global__ void fill_one_f32_kernel(float *dst, float val, size_t n, size_t index, float index_val) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i == index) ? index_val : val;
+}
+
 __global__ void sparse_scatter_kernel(const glb_idx_val_t *__restrict__ list, float *dense, uint32_t len) {
     const uint32_t n = list[0].index;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -178,6 +184,17 @@ int glb_buffer_fill_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n) {
     const size_t cap = size_t(ctx->num_sms) * 16;
     if (blocks > cap) blocks = cap;
     fill_f32_kernel<<<unsigned(blocks), kThreads, 0, ctx->stream>>>(dst_dev, val, n);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_buffer_fill_one_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n, size_t index, float index_val) {
+    GLB_REQUIRE(ctx && (n == 0 || dst_dev), "NULL argument");
+    GLB_REQUIRE(index < n, "index outside the vector");
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    const size_t cap = size_t(ctx->num_sms) * 16;
+    if (blocks > cap) blocks = cap;
+    fill_one_f32_kernel<<<unsigned(blocks), kThreads, 0, ctx->stream>>>(dst_dev, val, n, index, index_val);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }

@@ -50,11 +50,16 @@ private:
     void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
         const uint32_t n = matrix_num_rows_;
         if (fused_) {
-            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
-                glb_spmv_epilogue_t ep = {0, 0.0f, SpMV_->mask_buf.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
-                SpMV_->run_fused(&ep);
-                std::swap(SpMV_->vector_buf, SpMV_->results_buf);
-            }
+            DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf, mask = SpMV_->mask_buf;
+            replay({1, first_iter, num_iterations, key_of(vec.ptr()), key_of(res.ptr()), key_of(mask.ptr())}, [&] {
+                DeviceBuffer v = vec, r = res;
+                for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
+                    glb_spmv_epilogue_t ep = {0, 0.0f, mask.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
+                    SpMV_->run_fused(v, mask, r, &ep);
+                    std::swap(v, r);
+                }
+            });
+            if (num_iterations >= first_iter && (num_iterations - first_iter + 1) % 2) std::swap(SpMV_->vector_buf, SpMV_->results_buf);
         } else {
             DenseAssign_->bind_mask_buf(SpMV_->vector_buf);
             DenseAssign_->bind_inout_buf(SpMV_->mask_buf);
@@ -158,6 +163,7 @@ public:
         push_iterations_ = iter - 1;
         // switch from push to pull: the last frontier becomes the dense SpMV input, on the device
         SpMV_->bind_mask_buf(SpMSpV_->mask_buf);
+        SpMV_->home_buffers();
         if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
             SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
         GLB_CHECK(glb_sparse_to_dense(runtime_->ctx(), SpMSpV_->vector_buf.sparse(), SpMV_->vector_buf.f32(), n,

@@ -8,8 +8,11 @@
 #define GRAPHLILY_MODULE_COLLECTION_H_
 
 #include <cassert>
+#include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "graphlily/global.h"
@@ -28,13 +31,38 @@ protected:
     std::string target_ = "hw";
     std::shared_ptr<Runtime> runtime_;
 
+    // Launch replay.  The iteration loop of an app is a fixed launch sequence (same buffers, same
+    // per-iteration scalars): it is recorded once per key as a CUDA graph (glb_graph_begin / _end)
+    // and replayed with one glb_graph_launch afterwards -- a 7-level BFS is 21 launches of 5-50 us
+    // kernels that one host thread cannot enqueue fast enough one by one.
+    bool use_graphs_ = true;
+    std::vector<std::pair<std::vector<uint64_t>, glb_graph_t>> graphs_;
+    static constexpr size_t kGraphCache = 8;
+
+    void replay(const std::vector<uint64_t> &key, const std::function<void()> &launches) {
+        if (!use_graphs_) { launches(); return; }
+        for (auto &kv : graphs_)
+            if (kv.first == key) { GLB_CHECK(glb_graph_launch(runtime_->ctx(), kv.second)); return; }
+        if (graphs_.size() >= kGraphCache) { glb_graph_destroy(graphs_.front().second); graphs_.erase(graphs_.begin()); }
+        glb_graph_t g = nullptr;
+        GLB_CHECK(glb_graph_begin(runtime_->ctx()));
+        launches();
+        GLB_CHECK(glb_graph_end(runtime_->ctx(), &g));
+        graphs_.emplace_back(key, g);
+        GLB_CHECK(glb_graph_launch(runtime_->ctx(), g));
+    }
+    static uint64_t key_of(const void *p) { return uint64_t(reinterpret_cast<uintptr_t>(p)); }
+    static uint64_t key_of(float v) { uint32_t b; memcpy(&b, &v, sizeof(b)); return b; }
+
 public:
     ModuleCollection() {}
     ModuleCollection(const ModuleCollection &) = delete;
     ModuleCollection &operator=(const ModuleCollection &) = delete;
     virtual ~ModuleCollection() {
+        for (auto &kv : graphs_) glb_graph_destroy(kv.second);
         for (size_t i = 0; i < num_modules_; i++) delete modules_[i];
     }
+    void set_use_graphs(bool on) { use_graphs_ = on; }
 
     void add_module(BaseModule *module) {
         modules_.push_back(module);

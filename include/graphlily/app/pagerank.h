@@ -65,11 +65,16 @@ public:
         const float teleport = (1 - damping) / n;
         SpMV_->set_vector_constant(float(1.0 / n));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
         if (fused_) {
-            glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
-            for (uint32_t iter = 1; iter <= num_iterations; iter++) {
-                SpMV_->run_fused(&ep);
-                std::swap(SpMV_->vector_buf, SpMV_->results_buf);
-            }
+            DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
+            replay({2, key_of(teleport), num_iterations, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
+                glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
+                DeviceBuffer v = vec, r = res;
+                for (uint32_t iter = 1; iter <= num_iterations; iter++) {
+                    SpMV_->run_fused(v, DeviceBuffer(), r, &ep);
+                    std::swap(v, r);
+                }
+            });
+            if (num_iterations % 2) std::swap(SpMV_->vector_buf, SpMV_->results_buf);
         } else {
             eWiseAdd_->bind_in_buf(SpMV_->results_buf);
             eWiseAdd_->bind_out_buf(SpMV_->vector_buf);

@@ -86,10 +86,16 @@ private:
 
     void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
         if (fused_) {
-            for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
-                SpMV_->run();
-                std::swap(SpMV_->vector_buf, SpMV_->results_buf);
-            }
+            DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
+            const uint32_t count = num_iterations >= first_iter ? num_iterations - first_iter + 1 : 0;
+            replay({3, count, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
+                DeviceBuffer v = vec, r = res;
+                for (uint32_t k = 0; k < count; k++) {
+                    SpMV_->run_fused(v, DeviceBuffer(), r, nullptr);
+                    std::swap(v, r);
+                }
+            });
+            if (count % 2) std::swap(SpMV_->vector_buf, SpMV_->results_buf);
         } else {
             eWiseAdd_->bind_in_buf(SpMV_->results_buf);
             eWiseAdd_->bind_out_buf(SpMV_->vector_buf);
@@ -182,6 +188,7 @@ public:
         } while (iter < num_iterations && (float(vector_nnz) / n < threshold));
         push_iterations_ = iter - 1;
         // switch from push to pull: the distance vector becomes the SpMV input (device copy)
+        SpMV_->home_buffers();
         if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
             SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
         SpMV_->copy_buffer_device_to_device(SpMSpV_->mask_buf, SpMV_->vector_buf, sizeof(graphlily::val_t) * n);

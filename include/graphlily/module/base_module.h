@@ -37,12 +37,15 @@ protected:
         GLB_CHECK(glb_buffer_h2d(ctx(), buf.ptr(), host.data(), host.size() * sizeof(host[0])));
         return buf;
     }
-    // A vector that is constant but for one element, built on the device (fill kernel + 4-byte
-    // copy) instead of uploading n values.
-    DeviceBuffer constant_on_device(uint32_t n, float value, bool has_index = false, uint32_t index = 0, float index_value = 0) {
-        DeviceBuffer buf(runtime_, sizeof(float) * size_t(n));
-        GLB_CHECK(glb_buffer_fill_f32(ctx(), buf.f32(), value, n));
-        if (has_index) GLB_CHECK(glb_buffer_h2d(ctx(), buf.f32() + index, &index_value, sizeof(float)));
+    // A vector that is constant but for one element, built on the device in one launch instead of
+    // uploading n values.  A buffer of the right size is refilled in place, so the app loops see the
+    // same addresses call after call and their recorded launch sequences stay valid.
+    DeviceBuffer constant_on_device(const DeviceBuffer &reuse, uint32_t n, float value, bool has_index = false,
+                                    uint32_t index = 0, float index_value = 0) {
+        DeviceBuffer buf = (reuse.valid() && reuse.bytes() == sizeof(float) * size_t(n))
+                               ? reuse : DeviceBuffer(runtime_, sizeof(float) * size_t(n));
+        if (has_index) GLB_CHECK(glb_buffer_fill_one_f32(ctx(), buf.f32(), value, n, index, index_value));
+        else GLB_CHECK(glb_buffer_fill_f32(ctx(), buf.f32(), value, n));
         return buf;
     }
     template <typename vec_t>

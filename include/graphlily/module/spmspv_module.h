@@ -82,7 +82,7 @@ public:
     }
     void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
     void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        mask_buf = constant_on_device(get_num_rows(), value, true, index, index_value);
+        mask_buf = constant_on_device(mask_buf, get_num_rows(), value, true, index, index_value);
     }
 
     void run() {

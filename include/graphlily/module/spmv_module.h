@@ -80,12 +80,21 @@ public:
     void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
 
     // Start vectors of the apps (constant but for the source entry) without a host upload.
-    void set_vector_constant(vector_data_t value) { vector_buf = constant_on_device(get_num_cols(), value); }
+    // The app loops ping-pong vector / results and end with the roles swapped after an odd number of
+    // iterations; a new run starts from the same assignment every time (lower address = vector), so
+    // the recorded launch sequence of the previous run with these arguments is found again.
+    void home_buffers() {
+        if (vector_buf.valid() && results_buf.valid() && vector_buf.bytes() == results_buf.bytes() &&
+            vector_buf.ptr() > results_buf.ptr())
+            std::swap(vector_buf, results_buf);
+    }
+    void set_vector_constant(vector_data_t value) { home_buffers(); vector_buf = constant_on_device(vector_buf, get_num_cols(), value); }
     void set_vector_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        vector_buf = constant_on_device(get_num_cols(), value, true, index, index_value);
+        home_buffers();
+        vector_buf = constant_on_device(vector_buf, get_num_cols(), value, true, index, index_value);
     }
     void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        mask_buf = constant_on_device(get_num_rows(), value, true, index, index_value);
+        mask_buf = constant_on_device(mask_buf, get_num_rows(), value, true, index, index_value);
     }
 
     void run() { run_fused(nullptr); }
@@ -94,6 +103,13 @@ public:
     void run_fused(const glb_spmv_epilogue_t *epilogue) {
         GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.f32(),
                                  mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.f32(), epilogue));
+    }
+
+    // The same launch over explicit buffers: the app loops ping-pong vector / results instead of copying.
+    void run_fused(const DeviceBuffer &vector, const DeviceBuffer &mask, const DeviceBuffer &results,
+                   const glb_spmv_epilogue_t *epilogue) {
+        GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector.f32(),
+                                 mask_type_ == graphlily::kNoMask ? nullptr : mask.f32(), results.f32(), epilogue));
     }
 
     aligned_dense_vec_t send_vector_device_to_host() {

@@ -101,6 +101,9 @@ int glb_buffer_d2h_async(glb_ctx_t ctx, void *dst_host, const void *src_dev, siz
 /* BaseModule::copy_buffer_device_to_device, base_module.h:82-85 (stream-ordered). */
 int glb_buffer_d2d(glb_ctx_t ctx, void *dst_dev, const void *src_dev, size_t bytes);
 int glb_buffer_fill_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n);
+/* dst[i] = val except dst[index] = index_val: the start vectors of the apps (bfs.h:108-112,
+ * sssp.h:153-156, sssp.h:172-176) built on the device in one launch. */
+int glb_buffer_fill_one_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n, size_t index, float index_val);
 /* page-locked host memory: the role of xcl2's aligned_allocator (xcl2.hpp:61-76). */
 int glb_host_alloc(size_t bytes, void **hptr);
 int glb_host_free(void *hptr);
