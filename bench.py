@@ -211,31 +211,18 @@ def main():
 
     x_host = np.random.default_rng(SEED).integers(0, 2, n).astype(np.float32)
     # N > 1: how each rank's slice of y reaches the other ranks before the next step.
-    #   "peer"  (default) the SpMV write-back stores every row into all ranks' copies of the vector
-    #           over NVLink (peer-mapped memory, glb_spmv_exchange); a signal / wait kernel follows
-    #   "nccl"  one in-place ncclAllGather after the kernels (GLB_EXCHANGE=nccl, or when CUDA IPC
-    #           between the per-GPU processes is not available)
-    exchange, xc = "none", None
-    if world > 1:
-        exchange = os.environ.get("GLB_EXCHANGE", "peer")
-        if exchange == "peer":
-            def all_gather_bytes(b):
-                out = [None] * world
-                dist.all_gather_object(out, b)
-                return out
-            try:
-                xc = capi.Exchange(ctx, n, rank, world, all_gather_bytes)
-            except capi.GlbError as e:
-                log(f"rank {rank}: peer exchange unavailable ({e}); using the NCCL allgather")
-                exchange = "nccl"
-            ok = torch.tensor([1 if xc is not None else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                xc, exchange = None, "nccl"
-        if exchange == "nccl":
-            uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            ctx.comm_init(uid[0], rank, world)
+    #   "multicast" (default) symmetric-memory blocks with a multicast mapping: the finished slice is
+    #           sent once with multimem.st, the NVSwitch replicates it to every rank
+    #   "peer"  CUDA-IPC blocks: the SpMV write-back stores every row into all ranks' copies of the
+    #           vector over NVLink (glb_spmv_exchange); a signal / wait kernel follows
+    #   "nccl"  one in-place ncclAllGather after the kernels
+    # (GLB_EXCHANGE selects; each falls back to the next when the system lacks it)
+    from graphlily_b200.exchange import open_exchange
+    xc, exchange = open_exchange(ctx, n, rank, world, n_vectors=2, device=dev, log=log)
+    if exchange == "nccl":
+        uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
 
     class Vec:   # a full-length device vector: a torch tensor, or a peer-mapped exchange vector
         def __init__(self, which):
@@ -353,16 +340,27 @@ def main():
     y_sync = [y[rb:re].clone() for y in yhs]
     for y in yhs:
         y.zero_()
-    A.spmv_host_batch(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xs[:ring], None, ys[:ring])
-    batch_ms = timed_host(lambda: A.spmv_host_batch(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xs, None, ys))
+    def batch_call(xv, yv):
+        if xc is not None:   # sharded: every rank uploads its 1/N slice of x, NVLink completes it
+            xc.spmv_host_batch(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xv, None, yv)
+        else:
+            A.spmv_host_batch(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xv, None, yv)
+
+    batch_call(xs[:ring], ys[:ring])
+    batch_ms = timed_host(lambda: batch_call(xs, ys))
     batch_same = all(bool(torch.equal(yhs[i][rb:re], y_sync[i])) for i in range(ring))
     if not batch_same:
         log("WARNING: glb_spmv_host_batch results differ from glb_spmv_host")
     yh = yhs[0]
-    e2e = {"value": m.nnz / (batch_ms * 1e-3) / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": 4 * n,
-           "d2h_bytes_per_step": 4 * rows_s, "ms_per_step": batch_ms, "steps": e2e_steps,
-           "api": f"glb_spmv_host_batch: {e2e_steps} vectors from a ring of {ring} pinned host x buffers -> device, SpMV, "
-                  "y slice -> pinned host y buffers; upload / kernels / download of consecutive vectors overlap",
+    sliced = xc is not None
+    e2e = {"value": m.nnz / (batch_ms * 1e-3) / 1e9, "unit": "GTEPS",
+           "h2d_bytes_per_step": 4 * n if sliced or world == 1 else 4 * n * world,     # whole job, all ranks
+           "d2h_bytes_per_step": 4 * n, "ms_per_step": batch_ms, "steps": e2e_steps,
+           "api": (f"glb_spmv_host_batch_exchange: {e2e_steps} vectors from a ring of {ring} pinned host x buffers; every rank "
+                   "uploads its 1/N slice of x, the slices meet over NVLink (peer copies), SpMV, y slice -> pinned host; "
+                   "upload / kernels / download of consecutive vectors overlap" if sliced else
+                   f"glb_spmv_host_batch: {e2e_steps} vectors from a ring of {ring} pinned host x buffers -> device, SpMV, "
+                   "y slice -> pinned host y buffers; upload / kernels / download of consecutive vectors overlap"),
            "batch_matches_single_call_bitwise": batch_same,
            "single_call": {"value": m.nnz / (sync_ms * 1e-3) / 1e9, "ms_per_step": sync_ms,
                            "api": "glb_spmv_host per vector (returns when y has landed; no overlap between vectors)"}}
@@ -387,12 +385,15 @@ def main():
             log("WARNING: GPU result differs from the CPU reference on the sample")
 
     # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup
-    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (1 if xc is not None else 0)
+    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (0 if xc is None else 2 if exchange == "multicast" else 1)
     if rank == 0:
         cfg = workload_config(world)
         if world > 1:
-            cfg["exchange"] = ("y rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped "
-                               "memory) + signal/wait kernel" if exchange == "peer" else "one in-place ncclAllGather of y per step")
+            cfg["exchange"] = {"multicast": "each rank's y slice sent once with multimem.st (16-byte stores), replicated to all "
+                                            "ranks by the NVSwitch multicast + signal/wait kernel",
+                               "peer": "y rows stored into every rank's vector by the SpMV write-back over NVLink "
+                                       "(peer-mapped memory) + signal/wait kernel",
+                               "nccl": "one in-place ncclAllGather of y per step"}[exchange]
         line = {"metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,

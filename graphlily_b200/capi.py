@@ -94,11 +94,15 @@ SIGNATURES = {
     "glb_xchg_create": (C.c_int, [_vp, C.c_uint32, C.c_int, C.POINTER(_vp)]),
     "glb_xchg_export": (C.c_int, [_vp, _vp]),
     "glb_xchg_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "glb_xchg_block_bytes": (C.c_size_t, [C.c_uint32, C.c_int]),
+    "glb_xchg_adopt": (C.c_int, [_vp, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp)]),
+    "glb_xchg_has_multicast": (C.c_int, [_vp]),
     "glb_xchg_vector": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "glb_xchg_allgather": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_size_t]),
     "glb_xchg_barrier": (C.c_int, [_vp, _vp]),
     "glb_xchg_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "glb_xchg_destroy": (C.c_int, [_vp]),
+    "glb_spmv_host_batch_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp, C.POINTER(Epilogue)]),
 }
 
@@ -398,6 +402,27 @@ class Exchange:
             raise err or GlbError("peer exchange: another rank could not export its block")
         check(lib.glb_xchg_connect(self.handle, rank, nranks, C.c_char_p(b"".join(handles))))
 
+    @classmethod
+    def adopt(cls, ctx, n_floats, rank, nranks, block_ptrs, multicast_ptr=None, n_vectors=2, keep=None):
+        """Exchange over blocks the host mapped itself (torch symmetric memory: ``hdl.buffer_ptrs``,
+        ``hdl.multicast_ptr``); ``keep`` = objects that own the mapping."""
+        self = cls.__new__(cls)
+        self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, None, int(n_floats), rank, nranks
+        self.n_vectors, self._keep = n_vectors, keep
+        arr = (C.c_void_p * nranks)(*[int(p) for p in block_ptrs])
+        h = _vp()
+        check(lib.glb_xchg_adopt(ctx.handle, int(n_floats), n_vectors, rank, nranks, arr,
+                                 _vp(int(multicast_ptr)) if multicast_ptr else None, C.byref(h)))
+        self.handle = h
+        return self
+
+    @staticmethod
+    def block_bytes(n_floats, n_vectors):
+        return int(lib.glb_xchg_block_bytes(int(n_floats), n_vectors))
+
+    def has_multicast(self):
+        return bool(lib.glb_xchg_has_multicast(self.handle))
+
     def vector(self, which):
         p = _vp()
         check(lib.glb_xchg_vector(self.handle, which, C.byref(p)))
@@ -406,6 +431,14 @@ class Exchange:
     def spmv(self, matrix, op, zero, mask_type, src_vec, dst_vec, mask=None, epilogue=None):
         check(lib.glb_spmv_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
                                     _ptr(mask), C.byref(epilogue) if epilogue is not None else None))
+
+    def spmv_host_batch(self, matrix, op, zero, mask_type, x_hosts, mask_hosts, y_hosts):
+        """glb_spmv_host_batch_exchange: every rank uploads its slice of each x, NVLink completes it."""
+        n = len(x_hosts)
+        arr = C.c_void_p * n
+        xs, ys = arr(*[_ptr(v) for v in x_hosts]), arr(*[_ptr(v) for v in y_hosts])
+        ms = arr(*[_ptr(v) for v in mask_hosts]) if mask_hosts is not None else None
+        check(lib.glb_spmv_host_batch_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, n, xs, ms, ys))
 
     def buffer(self, which):
         """Vector ``which`` as a (non-owning) DeviceBuffer."""

@@ -509,6 +509,50 @@ int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles) {
     return GLB_OK;
 }
 
+int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, void *const *blocks,
+                   void *multicast_block, glb_xchg_t *out) {
+    GLB_REQUIRE(ctx && out && blocks && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
+    GLB_REQUIRE(nranks >= 1 && nranks <= GLB_MAX_PEERS + 1 && rank >= 0 && rank < nranks, "bad rank");
+    *out = nullptr;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < nranks; ++r) GLB_REQUIRE(blocks[r], "NULL block");
+    glb_xchg_t xc = new glb_xchg_s();
+    xc->ctx = ctx;
+    glb_ctx_retain(ctx);
+    xc->n = n_floats;
+    xc->n_vectors = n_vectors;
+    xc->adopted = true;
+    xc->rank = rank;
+    xc->nranks = nranks;
+    xc->mc = static_cast<float *>(multicast_block);
+    const size_t vec_bytes = glb_xchg_block_bytes(n_floats, n_vectors) - 256;
+    for (int r = 0; r < nranks; ++r) {
+        xc->peer[r] = static_cast<float *>(blocks[r]);
+        xc->peer_flags[r] = reinterpret_cast<uint32_t *>(static_cast<char *>(blocks[r]) + vec_bytes);
+    }
+    xc->local = xc->peer[rank];
+    xc->local_flags = xc->peer_flags[rank];
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&xc->d_peer_flags), sizeof(uint32_t *) * (GLB_MAX_PEERS + 1));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_err), sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(xc->d_err, 0, sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(xc->d_peer_flags, xc->peer_flags, sizeof(uint32_t *) * (GLB_MAX_PEERS + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        glb_set_error("glb_xchg_adopt: %s", cudaGetErrorString(e));
+        glb_xchg_destroy(xc);
+        return GLB_ECUDA;
+    }
+    xc->connected = true;
+    *out = xc;
+    return GLB_OK;
+}
+
+size_t glb_xchg_block_bytes(uint32_t n_floats, int n_vectors) {
+    return ((size_t(n_floats) * size_t(n_vectors) * sizeof(float) + 255) & ~size_t(255)) + 256;
+}
+
+int glb_xchg_has_multicast(glb_xchg_t xc) { return xc && xc->mc ? 1 : 0; }
+
 int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr) {
     GLB_REQUIRE(xc && local_ptr && which >= 0 && which < xc->n_vectors, "bad argument");
     *local_ptr = xc->local + size_t(which) * xc->n;
@@ -520,13 +564,47 @@ int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc) {
     return glb_xchg_signal_wait(ctx, xc);
 }
 
+}  // extern "C"
+
+// One store, every rank: multimem.st on the multicast mapping of the blocks is replicated by the
+// NVSwitch into all ranks' copies (the issuing rank's included), so a slice leaves this GPU once
+// instead of once per peer.  16-byte stores; the unaligned head / tail go out as scalars.
+__global__ void __launch_bounds__(256) xchg_multicast_kernel(const float *__restrict__ src, float *mc, size_t count) {
+    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = size_t(gridDim.x) * blockDim.x;
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;
+    head = head / 4 < count ? head / 4 : count;
+    const size_t n4 = (count - head) / 4;
+    for (size_t i = tid; i < head; i += stride)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(src[i]) : "memory");
+    const float4 *s4 = reinterpret_cast<const float4 *>(src + head);
+    for (size_t i = tid; i < n4; i += stride) {
+        const float4 v = s4[i];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + head + 4 * i), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+    for (size_t i = head + 4 * n4 + tid; i < count; i += stride)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(src[i]) : "memory");
+}
+
+extern "C" {
+
 int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count) {
     GLB_REQUIRE(ctx && xc && xc->connected && xc->ctx == ctx, "exchange is not connected to this context");
     GLB_REQUIRE(which >= 0 && which < xc->n_vectors && offset + count <= xc->n, "slice outside the vector");
     const size_t at = size_t(which) * xc->n + offset;
-    for (int r = 0; r < xc->nranks && count; ++r)
-        if (r != xc->rank)
-            GLB_CUDA(cudaMemcpyAsync(xc->peer[r] + at, xc->local + at, count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (xc->mc && count && xc->nranks > 1) {
+        size_t blocks = (count / 4 + 255) / 256 + 1;
+        const size_t cap = size_t(ctx->num_sms) * 4;
+        if (blocks > cap) blocks = cap;
+        xchg_multicast_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(xc->local + at, xc->mc + at, count);
+        GLB_CUDA(cudaGetLastError());
+    } else {
+        for (int r = 0; r < xc->nranks && count; ++r)
+            if (r != xc->rank)
+                GLB_CUDA(cudaMemcpyAsync(xc->peer[r] + at, xc->local + at, count * sizeof(float), cudaMemcpyDeviceToDevice,
+                                         ctx->stream));
+    }
     return glb_xchg_signal_wait(ctx, xc);
 }
 
@@ -543,9 +621,11 @@ int glb_xchg_destroy(glb_xchg_t xc) {
     if (!xc) return GLB_OK;
     cudaSetDevice(xc->ctx->device);
     cudaStreamSynchronize(xc->ctx->stream);
-    for (int r = 0; r < xc->nranks; ++r)
-        if (xc->connected && r != xc->rank && xc->peer[r]) cudaIpcCloseMemHandle(xc->peer[r]);
-    cudaFree(xc->local);
+    if (!xc->adopted) {
+        for (int r = 0; r < xc->nranks; ++r)
+            if (xc->connected && r != xc->rank && xc->peer[r]) cudaIpcCloseMemHandle(xc->peer[r]);
+        cudaFree(xc->local);
+    }
     cudaFree(xc->d_peer_flags);
     cudaFree(xc->d_err);
     glb_ctx_release(xc->ctx);

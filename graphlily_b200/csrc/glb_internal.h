@@ -153,6 +153,10 @@ struct glb_xchg_s {
     uint32_t **d_peer_flags = nullptr;    // device copy of peer_flags
     uint32_t *d_err = nullptr;            // set when a wait timed out
     uint32_t epoch = 0;
+    // adopted blocks (glb_xchg_adopt): memory mapped by the host (symmetric memory), optionally with
+    // a multicast mapping -- one store to `mc` lands in every rank's block (NVSwitch multicast)
+    bool adopted = false;
+    float *mc = nullptr;
 };
 extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
 
@@ -167,6 +171,6 @@ void glb_ctx_release(glb_ctx_t ctx);  // child destroyed; frees the context if i
 
 // launchers (defined in the .cu files)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers);
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc);
 
 #endif  // GLB_INTERNAL_H_

@@ -72,6 +72,7 @@ struct SpmvParams {
     float *y;
     float *y_peer[GLB_MAX_PEERS];  // the same vector on the other GPUs of a row-sharded run (peer-mapped memory)
     int n_peers;
+    float *y_mc;  // or its multicast mapping: one store lands on every GPU (NVSwitch multicast)
     float *head_carry;
     float *tail_carry;
     uint32_t n_chunks;
@@ -126,9 +127,13 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
     P.y[row] = v;
     // fused exchange: the row also goes straight into every peer's copy over NVLink, so the
     // allgather of the next iteration's x rides inside the SpMV write-back
+    if (P.y_mc) {
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.y_mc + row), "f"(v) : "memory");
+    } else {
 #pragma unroll
-    for (int p = 0; p < GLB_MAX_PEERS; ++p)
-        if (p < P.n_peers) P.y_peer[p][row] = v;
+        for (int p = 0; p < GLB_MAX_PEERS; ++p)
+            if (p < P.n_peers) P.y_peer[p][row] = v;
+    }
     if (P.assign_inout) {
         bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? (v != 0.0f) : (v == 0.0f);
         if (hit) P.assign_inout[row] = P.assign_val;
@@ -522,9 +527,10 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 }  // namespace
 
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers) {
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
+    P.y_mc = y_mc;
     P.n_peers = n_peers;
     for (int p = 0; p < n_peers && p < GLB_MAX_PEERS; ++p) P.y_peer[p] = y_peers[p];
     P.stream = m->stream;
@@ -927,7 +933,7 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr);
 }
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
@@ -940,11 +946,26 @@ int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_t
     float *y = xc->local + size_t(dst_vec) * xc->n;
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
+    if (xc->mc) {
+        // multicast mapping available: each row leaves this GPU once and the NVSwitch replicates it.
+        // Default: the write-back itself stores to the multicast address (overlaps the kernel);
+        // GLB_XCHG_MC=kernel: the kernels write y locally and one small kernel sends the finished
+        // slice in 16-byte multicast stores.
+        static const bool separate = [] { const char *v = getenv("GLB_XCHG_MC"); return v && !strcmp(v, "kernel"); }();
+        if (separate) {
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr);
+            if (rc) return rc;
+            return glb_xchg_allgather(ctx, xc, dst_vec, m->row_begin, size_t(m->row_end - m->row_begin));
+        }
+        rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, xc->mc + size_t(dst_vec) * xc->n);
+        if (rc) return rc;
+        return glb_xchg_signal_wait(ctx, xc);
+    }
     float *peers[GLB_MAX_PEERS];
     int n_peers = 0;
     for (int r = 0; r < xc->nranks; ++r)
         if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dst_vec) * xc->n;
-    rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers);
+    rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr);
     if (rc) return rc;
     return glb_xchg_signal_wait(ctx, xc);
 }
@@ -997,14 +1018,26 @@ int glb_spmv_host(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type,
 // every result device -> host; what changes is that the three legs of consecutive vectors overlap
 // (PCIe is full duplex and the copy engines run beside the SMs).  Host buffers should be page-locked
 // (glb_host_alloc); pageable ones work but their copies do not overlap.
-int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, int n_vectors,
-                        const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts) {
+//
+// With an exchange (row-sharded run, one process per GPU) the two slots are exchange vectors 0 / 1:
+// every rank uploads only ITS slice of x over PCIe and the slices meet over NVLink
+// (glb_xchg_allgather on the kernel stream), so the host link carries each x once per job instead of
+// once per GPU.
+static int spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int n_vectors,
+                           const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts) {
     GLB_REQUIRE(ctx && m && x_hosts && y_hosts && n_vectors >= 0, "bad argument");
     GLB_REQUIRE(m->ctx == ctx, "matrix belongs to another context");
     GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask_hosts, "mask_hosts is NULL but mask_type != kNoMask");
     for (int k = 0; k < n_vectors; ++k) {
         GLB_REQUIRE(x_hosts[k] && y_hosts[k], "NULL vector in the batch");
         GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask_hosts[k], "NULL mask in the batch");
+    }
+    size_t x_off = 0, x_cnt = m->num_cols;
+    if (xc) {
+        GLB_REQUIRE(xc->connected && xc->ctx == ctx && xc->n_vectors >= 2, "exchange is not connected to this context");
+        GLB_REQUIRE(m->num_cols <= xc->n && xc->n % uint32_t(xc->nranks) == 0, "exchange vectors must divide evenly over the ranks");
+        x_cnt = xc->n / uint32_t(xc->nranks);
+        x_off = x_cnt * size_t(xc->rank);
     }
     if (n_vectors == 0) return GLB_OK;
     GLB_CUDA(cudaSetDevice(ctx->device));
@@ -1015,8 +1048,14 @@ int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask
             if (!e) GLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const bool masked = mask_type != GLB_MASK_NONE;
     float **dxs[2] = {&m->dx, &m->dx2}, **dms[2] = {&m->dmask, &m->dmask2}, **dys[2] = {&m->dy, &m->dy2};
+    float *xslot[2];
     for (int s = 0; s < 2; ++s) {
-        if (!*dxs[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dxs[s]), sizeof(float) * m->num_cols));
+        if (xc) {
+            xslot[s] = xc->local + size_t(s) * xc->n;
+        } else {
+            if (!*dxs[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dxs[s]), sizeof(float) * m->num_cols));
+            xslot[s] = *dxs[s];
+        }
         if (!*dys[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dys[s]), sizeof(float) * m->num_rows));
         if (masked && !*dms[s]) GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(dms[s]), sizeof(float) * m->num_rows));
     }
@@ -1025,18 +1064,30 @@ int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask
     // work already queued on the caller's stream (an earlier glb_spmv_host may still read slot 0) goes first
     GLB_CUDA(cudaEventRecord(computed[0], ctx->stream));
     GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, computed[0], 0));
+    if (xc) {  // no peer may still be reading what this batch overwrites
+        int rc = glb_xchg_signal_wait(ctx, xc);
+        if (rc) return rc;
+    }
     for (int k = 0; k < n_vectors; ++k) {
         const int s = k & 1;
         // upload k: slot s is free once the kernels of vector k-2 have read it
         if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, computed[s], 0));
-        GLB_CUDA(cudaMemcpyAsync(*dxs[s], x_hosts[k], sizeof(float) * m->num_cols, cudaMemcpyHostToDevice, ctx->copy_in));
-        if (masked)
-            GLB_CUDA(cudaMemcpyAsync(*dms[s], mask_hosts[k], sizeof(float) * m->num_rows, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (x_off < m->num_cols) {
+            const size_t cnt = (x_off + x_cnt <= m->num_cols) ? x_cnt : m->num_cols - x_off;
+            GLB_CUDA(cudaMemcpyAsync(xslot[s] + x_off, x_hosts[k] + x_off, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
+        if (masked)   // the mask is row-local: only the shard's rows are read
+            GLB_CUDA(cudaMemcpyAsync(*dms[s] + m->row_begin, mask_hosts[k] + m->row_begin, sizeof(float) * nr,
+                                     cudaMemcpyHostToDevice, ctx->copy_in));
         GLB_CUDA(cudaEventRecord(uploaded[s], ctx->copy_in));
         // kernels k: need the upload, and the download of result k-2 must have drained dy[s]
         GLB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[s], 0));
         if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[s], 0));
-        int rc = glb_spmv(ctx, m, op, zero, mask_type, *dxs[s], masked ? *dms[s] : nullptr, *dys[s]);
+        if (xc) {  // the slices of x meet over NVLink; the wait inside also orders slot reuse across ranks
+            int rc = glb_xchg_allgather(ctx, xc, s, x_off, x_cnt);
+            if (rc) return rc;
+        }
+        int rc = glb_spmv(ctx, m, op, zero, mask_type, xslot[s], masked ? *dms[s] : nullptr, *dys[s]);
         if (rc) return rc;
         GLB_CUDA(cudaEventRecord(computed[s], ctx->stream));
         // download k
@@ -1050,6 +1101,17 @@ int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask
     if (n_vectors >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[n_vectors & 1], 0));
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
     return GLB_OK;
+}
+
+int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, int n_vectors,
+                        const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts) {
+    return spmv_host_batch(ctx, m, op, zero, mask_type, nullptr, n_vectors, x_hosts, mask_hosts, y_hosts);
+}
+
+int glb_spmv_host_batch_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int n_vectors,
+                                 const float *const *x_hosts, const float *const *mask_hosts, float *const *y_hosts) {
+    GLB_REQUIRE(xc, "exchange is NULL");
+    return spmv_host_batch(ctx, m, op, zero, mask_type, xc, n_vectors, x_hosts, mask_hosts, y_hosts);
 }
 
 }  // extern "C"

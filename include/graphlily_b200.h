@@ -277,6 +277,14 @@ typedef struct glb_xchg_s *glb_xchg_t;
 int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t *out);
 int glb_xchg_export(glb_xchg_t xc, void *handle64);
 int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles);
+/* Blocks mapped by the host instead of CUDA IPC (e.g. torch symmetric memory): blocks[r] = rank r's
+ * block as mapped in THIS process (glb_xchg_block_bytes each, zero-filled), multicast_block = the
+ * multicast mapping of the same blocks or NULL.  With a multicast mapping the slices travel as
+ * multimem.st through the NVSwitch: one store lands on every rank. */
+size_t glb_xchg_block_bytes(uint32_t n_floats, int n_vectors);
+int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, void *const *blocks,
+                   void *multicast_block, glb_xchg_t *out);
+int glb_xchg_has_multicast(glb_xchg_t xc);
 int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr);
 int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count);
 int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc);
@@ -284,6 +292,12 @@ int glb_xchg_status(glb_xchg_t xc, int *timed_out);
 int glb_xchg_destroy(glb_xchg_t xc);
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
                       int dst_vec, const float *mask, const glb_spmv_epilogue_t *ep);
+/* glb_spmv_host_batch for a row-sharded run: called by every rank with the same full-length host
+ * vectors; each rank uploads only its 1/nranks slice of x over PCIe, the slices meet over NVLink
+ * (exchange vectors 0 and 1 are the two pipeline slots), and y_hosts[k] receives the rank's rows. */
+int glb_spmv_host_batch_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc,
+                                 int n_vectors, const float *const *x_hosts, const float *const *mask_hosts,
+                                 float *const *y_hosts);
 
 /* ------------------------------------------------------------------ launch replay ------
  * The reference drains its queue after every module run (spmv_module.h:471-475); an app

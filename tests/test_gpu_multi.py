@@ -22,28 +22,37 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port):
+def _worker(rank, world, port, kind):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    if kind == "multicast":   # torch symmetric memory rendezvous runs over the default (NCCL) group
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
     from graphlily_b200 import app, capi, datasets
+    from graphlily_b200.exchange import open_exchange
     from graphlily_b200.io import CSRMatrix
     from util import assert_close_rel
 
-    def all_gather_bytes(b):
-        out = [None] * world
-        dist.all_gather_object(out, b)
-        return out
-
     ctx = capi.Context(rank)
+
+    def make_exchange(n_floats, n_vectors):
+        xc, got = open_exchange(ctx, n_floats, rank, world, n_vectors=n_vectors, kind=kind,
+                                log=lambda *a: print("[test]", *a, flush=True))
+        assert xc is not None, "no peer-mapped exchange on this box"
+        if rank == 0:
+            print(f"[test] exchange requested {kind}: got {got}, multicast mapping {xc.has_multicast()}", flush=True)
+        return xc
+
     # ---- raw exchange: five ping-pong iterations x <- A x of each semiring ---------------------
     n = 8192
     m = datasets.powerlaw_csr(n, n, 1 << 18, seed=21, max_degree=5000, value=1.0 / 32)   # same seed on every rank
     slot = n // world
     A = capi.CsrMatrix(ctx, m, rank * slot, (rank + 1) * slot)
-    xc = capi.Exchange(ctx, n, rank, world, all_gather_bytes, n_vectors=3)
+    xc = make_exchange(n, 3)
     rng = np.random.default_rng(5)
     for op, zero, x0 in ((0, 0.0, rng.random(n).astype(np.float32)),
                          (1, 0.0, (rng.random(n) < 0.001).astype(np.float32)),
@@ -61,6 +70,21 @@ def _worker(rank, world, port):
             assert_close_rel(got, ref, 1e-4)      # five iterations of 1e-5-per-step differences
         else:
             assert got.tobytes() == ref.tobytes(), f"rank {rank} op {op}"
+    # pipelined host-buffer batch: every rank uploads its slice of x, NVLink completes it
+    xs = [capi.PinnedArray(n) for _ in range(5)]
+    ys = [capi.PinnedArray(n) for _ in range(5)]
+    mks = [capi.PinnedArray(n) for _ in range(5)]
+    for k in range(5):
+        xs[k].array[:] = np.random.default_rng(100 + k).random(n).astype(np.float32)   # same on every rank
+        mks[k].array[:] = np.random.default_rng(200 + k).integers(0, 2, n).astype(np.float32)
+        ys[k].array[:] = -3.0
+    for mt in (capi.MASK_NONE, capi.MASK_WRITE_TO_ZERO):
+        xc.spmv_host_batch(A, 0, 0.0, mt, [a.ptr for a in xs], [a.ptr for a in mks] if mt else None, [a.ptr for a in ys])
+        for k in range(5):
+            ref = oracle.port.spmv(m, 0, 0.0, mt, xs[k].array, mks[k].array if mt else None)
+            assert_close_rel(ys[k].array[rank * slot:(rank + 1) * slot], ref[rank * slot:(rank + 1) * slot], 1e-5)
+            outside = np.delete(ys[k].array, np.s_[rank * slot:(rank + 1) * slot])
+            assert (outside == -3.0).all()
     # the slice gather
     v = np.full(n, -1.0, np.float32)
     v[rank * slot:(rank + 1) * slot] = rank + 1
@@ -79,7 +103,7 @@ def _worker(rank, world, port):
         a = {"bfs": app.BFS, "pagerank": app.PageRank, "sssp": app.SSSP}[name]()
         a.set_up_runtime(None, ctx=ctx)
         a.load_and_format_matrix(*((g, 0.9) if name == "pagerank" else (g,)))
-        x2 = capi.Exchange(ctx, a.matrix_num_rows_, rank, world, all_gather_bytes, n_vectors=3)
+        x2 = make_exchange(a.matrix_num_rows_, 3)
         a.set_sharding(rank, world, x2)
         a.send_matrix_host_to_device()
         mat = a.csr_matrix_
@@ -101,8 +125,9 @@ def _worker(rank, world, port):
     dist.destroy_process_group()
 
 
-def test_peer_exchange_and_apps_on_two_gpus():
+@pytest.mark.parametrize("kind", ["peer", "multicast"])
+def test_exchange_and_apps_on_two_gpus(kind):
     from graphlily_b200 import capi
     if capi.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    mp.start_processes(_worker, args=(2, _free_port()), nprocs=2, join=True, start_method="spawn")
+    mp.start_processes(_worker, args=(2, _free_port(), kind), nprocs=2, join=True, start_method="spawn")

@@ -60,7 +60,9 @@ def main():
     ctx = capi.Context(local_rank, stream.cuda_stream)
     # N > 1: "peer" (default) = SpMV write-back stores rows into every rank's vectors over NVLink
     # (glb_spmv_exchange); GLB_EXCHANGE=nccl = one in-place ncclAllGather after every SpMV
-    exchange_kind = os.environ.get("GLB_EXCHANGE", "peer") if world > 1 else "none"
+    from graphlily_b200.exchange import open_exchange
+    exchange_kind = os.environ.get("GLB_EXCHANGE", "multicast") if world > 1 else "none"
+    exchange_used = exchange_kind
     if exchange_kind == "nccl":
         uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -134,15 +136,20 @@ def main():
             a.load_and_format_matrix(g, 0.9)
         else:
             a.load_and_format_matrix(g)
-        xc = capi.Exchange(ctx, a.matrix_num_rows_, rank, world, all_gather_bytes, n_vectors=3) if exchange_kind == "peer" else None
+        xc = None
+        if exchange_kind != "nccl" and world > 1:
+            xc, got_kind = open_exchange(ctx, a.matrix_num_rows_, rank, world, n_vectors=3, kind=exchange_kind, device=dev, log=log)
+            assert xc is not None, "exchange unavailable: rerun with GLB_EXCHANGE=nccl"
+            exchange_used = got_kind
         a.set_sharding(rank, world, xc)
         a.send_matrix_host_to_device()
         nnz = a.get_nnz()
         log(f"{name}: {n} vertices, nnz {nnz}, generated + formatted + uploaded in {time.time() - t0:.1f}s")
         cfg = {"vertices": n, "nnz": nnz, "generator": "graphlily_b200.datasets.powerlaw_graph (symmetric, Zipf 0.9)",
                "sharding": "none" if world == 1 else f"row-range x{world}, " + (
-                   "rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped memory)"
-                   if exchange_kind == "peer" else "NCCL allgather per iteration")}
+                   {"peer": "rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped memory)",
+                    "multicast": "y slice sent once with multimem.st, replicated by the NVSwitch multicast",
+                    "nccl": "NCCL allgather per iteration"}[exchange_used])}
         source = 0
         modes = {}
         results = {}
