@@ -948,10 +948,17 @@ int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_t
     if (rc) return rc;
     if (xc->mc) {
         // multicast mapping available: each row leaves this GPU once and the NVSwitch replicates it.
-        // Default: the write-back itself stores to the multicast address (overlaps the kernel);
-        // GLB_XCHG_MC=kernel: the kernels write y locally and one small kernel sends the finished
-        // slice in 16-byte multicast stores.
-        static const bool separate = [] { const char *v = getenv("GLB_XCHG_MC"); return v && !strcmp(v, "kernel"); }();
+        //   "kernel": the kernels write y locally, then one small kernel sends the finished slice in
+        //             16-byte multicast stores (default from 4 ranks on: the SpMV kernels run at their
+        //             single-GPU speed, measured 57 us vs 74 us per launch on 8 B200s);
+        //   "fused":  the write-back itself stores each row to the multicast address, overlapping the
+        //             kernel (default below 4 ranks, where slices are long and the extra launch costs more).
+        // GLB_XCHG_MC=kernel|fused overrides.
+        static const int forced = [] {
+            const char *v = getenv("GLB_XCHG_MC");
+            return !v ? 0 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : 0;
+        }();
+        const bool separate = forced ? forced == 1 : xc->nranks >= 4;
         if (separate) {
             rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr);
             if (rc) return rc;
