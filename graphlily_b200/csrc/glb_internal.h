@@ -50,6 +50,10 @@ struct glb_ctx_s {
     void *staging = nullptr;
     size_t staging_bytes = 0;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // kernel attributes already applied on this device (cudaFuncSetAttribute is per device)
+    int carveout_set[3] = {-1, -1, -1};
+    int bits_carveout_set = -1;
+    size_t tile_smem_set[3] = {0, 0, 0};
     // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]

@@ -457,7 +457,7 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
     if (P.n_chunks && m->tile_threads) {
         const uint32_t n_warps = m->tile_threads / 32;
         const size_t smem = size_t((P.tile_k + 3u) & ~3u) * 4 + size_t(n_warps) * GLB_ROW_CAP * 4 + 16;
-        static thread_local size_t attr_set[3] = {0, 0, 0};
+        size_t *attr_set = ctx->tile_smem_set;  // function attributes are per device: cached in the context
         if (attr_set[OP] < smem) {
             GLB_CUDA(cudaFuncSetAttribute(spmv_lane_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             attr_set[OP] = smem;
@@ -467,7 +467,7 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
     } else if (P.n_chunks && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        static thread_local int bits_carveout_set = -1;
+        int &bits_carveout_set = ctx->bits_carveout_set;
         if (bits_carveout_set != m->smem_carveout_pct) {
             const int pct = m->smem_carveout_pct;
             GLB_CUDA(cudaFuncSetAttribute(spmv_lane_bits_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -483,7 +483,7 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
         else spmv_lane_bits_kernel<1, false><<<grid, kThreads, 0, ctx->stream>>>(P);
     } else if (P.n_chunks) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
-        static thread_local int carveout_set[3] = {-1, -1, -1};
+        int *carveout_set = ctx->carveout_set;
         if (carveout_set[OP] != m->smem_carveout_pct) {
             GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           m->smem_carveout_pct));
