@@ -392,12 +392,14 @@ def main():
             log("WARNING: GPU result differs from the CPU reference on the sample")
 
     # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup
-    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (0 if xc is None else 2 if exchange == "multicast" else 1)
+    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (0 if xc is None else 2 if (exchange == "multicast" and world >= 4) else 1)
     if rank == 0:
         cfg = workload_config(world)
         if world > 1:
-            cfg["exchange"] = {"multicast": "each rank's y slice sent once with multimem.st (16-byte stores), replicated to all "
-                                            "ranks by the NVSwitch multicast + signal/wait kernel",
+            mc_kernel = {"kernel": True, "fused": False}.get(os.environ.get("GLB_XCHG_MC", ""), world >= 4)
+            cfg["exchange"] = {"multicast": ("each rank's finished y slice sent once by a kernel of 16-byte multimem.st stores" if mc_kernel
+                                             else "each y row stored once to the multicast address by the SpMV write-back (multimem.st)") +
+                                            ", replicated to all ranks by the NVSwitch multicast + signal/wait kernel",
                                "peer": "y rows stored into every rank's vector by the SpMV write-back over NVLink "
                                        "(peer-mapped memory) + signal/wait kernel",
                                "nccl": "one in-place ncclAllGather of y per step"}[exchange]

@@ -124,8 +124,11 @@ class SpMVModule(BaseModule):
             self.vector_buf, self.results_buf = r, v
 
     def set_vector_constant(self, value, index=None, index_value=None):
+        n = self.get_num_cols()
+        if self.vector_buf is None or not self.vector_buf.ptr or self.vector_buf.nbytes != 4 * n:
+            self.vector_buf = self.ctx.alloc(4 * n)   # allocate first, then settle the roles: the first run is canonical too
         self.home_buffers()
-        self.vector_buf = self._constant_on_device(self.get_num_cols(), value, index, index_value, self.vector_buf)
+        self.vector_buf = self._constant_on_device(n, value, index, index_value, self.vector_buf)
 
     def set_mask_constant(self, value, index=None, index_value=None):
         self.mask_buf = self._constant_on_device(self.get_num_rows(), value, index, index_value, self.mask_buf)

@@ -83,14 +83,22 @@ public:
     // The app loops ping-pong vector / results and end with the roles swapped after an odd number of
     // iterations; a new run starts from the same assignment every time (lower address = vector), so
     // the recorded launch sequence of the previous run with these arguments is found again.
+    void ensure_vector_buf() {  // allocate first, then settle the roles: the very first run is canonical too
+        if (!vector_buf.valid() || vector_buf.bytes() != sizeof(vector_data_t) * size_t(get_num_cols()))
+            vector_buf = DeviceBuffer(runtime_, sizeof(vector_data_t) * size_t(get_num_cols()));
+        home_buffers();
+    }
     void home_buffers() {
         if (vector_buf.valid() && results_buf.valid() && vector_buf.bytes() == results_buf.bytes() &&
             vector_buf.ptr() > results_buf.ptr())
             std::swap(vector_buf, results_buf);
     }
-    void set_vector_constant(vector_data_t value) { home_buffers(); vector_buf = constant_on_device(vector_buf, get_num_cols(), value); }
+    void set_vector_constant(vector_data_t value) {
+        ensure_vector_buf();
+        vector_buf = constant_on_device(vector_buf, get_num_cols(), value);
+    }
     void set_vector_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        home_buffers();
+        ensure_vector_buf();
         vector_buf = constant_on_device(vector_buf, get_num_cols(), value, true, index, index_value);
     }
     void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
