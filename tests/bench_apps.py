@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """App-level benchmarks on the BASELINE.json configs (bench_bfs / bench_pagerank / bench_sssp).
 
-    python tools/bench_apps.py [bfs] [pagerank] [sssp] [--scale S] [--no-check]
-    python -m torch.distributed.run --nproc-per-node N ... tools/bench_apps.py pagerank sssp
+    python tests/bench_apps.py [bfs] [pagerank] [sssp] [--scale S] [--no-check]
+    python -m torch.distributed.run --nproc-per-node N ... tests/bench_apps.py pagerank sssp
 
 Shapes (the real datasets are not shipped, so seeded synthetic graphs of their shape):
   bfs       C3 gplus-shaped      107 648 vertices, ~13 M nnz, or-and semiring, 7 iterations (run_bfs.sh:20)

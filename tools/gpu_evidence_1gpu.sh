@@ -11,7 +11,7 @@ python tools/launch_summary.py gpurun_out/launches_bench.csv
 ncu --set full --clock-control none --import-source on -k regex:spmv_lane_kernel -s 2 -c 1 -f -o gpurun_out/prof_v3 \
     python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_v3.log 2>&1; echo "lane full rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'spmv|gather_hot|pack_bits|fill|spmspv|assign' -c 300 --csv --log-file gpurun_out/launches_bfs.csv \
-    python tools/bench_apps.py bfs --no-check --reps 1 > gpurun_out/ncu_bfs.log 2>&1; echo "bfs list rc=$?"
+    python tests/bench_apps.py bfs --no-check --reps 1 > gpurun_out/ncu_bfs.log 2>&1; echo "bfs list rc=$?"
 mkdir -p /tmp/ds && python tools/make_dataset.py c3 /tmp/ds/c3.npz 2>&1 | tail -1
 ( echo "== bench_bfs c3 7"; timeout 300 benchmark/bin/bench_bfs 16 1024000 256000 30720 overlay.xclbin /tmp/ds/c3.npz 7 2>&1 | tail -8
   echo "== bench_sssp c3 6"; timeout 300 benchmark/bin/bench_sssp /tmp/ds/c3.npz 6 2>&1 | tail -8

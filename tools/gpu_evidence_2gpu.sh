@@ -8,8 +8,8 @@ timeout 600 $TR bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_${N}
 grep '^{' gpurun_out/bench_${N}gpu_peer.json | cut -c1-200
 GLB_EXCHANGE=nccl timeout 600 $TR bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_${N}gpu_nccl.json 2> gpurun_out/bench_${N}gpu_nccl.err; echo "bench nccl rc=$?"
 grep '^{' gpurun_out/bench_${N}gpu_nccl.json | cut -c1-200
-timeout 900 $TR tools/bench_apps.py ${APPS:-bfs pagerank sssp} ${APPFLAGS} > gpurun_out/bench_apps_${N}gpu_peer.jsonl 2> gpurun_out/bench_apps_${N}gpu_peer.err; echo "apps peer rc=$?"
+timeout 900 $TR tests/bench_apps.py ${APPS:-bfs pagerank sssp} ${APPFLAGS} > gpurun_out/bench_apps_${N}gpu_peer.jsonl 2> gpurun_out/bench_apps_${N}gpu_peer.err; echo "apps peer rc=$?"
 grep '^{' gpurun_out/bench_apps_${N}gpu_peer.jsonl | cut -c1-900
 tail -3 gpurun_out/bench_apps_${N}gpu_peer.err
-GLB_EXCHANGE=nccl timeout 900 $TR tools/bench_apps.py ${APPS:-bfs pagerank sssp} --no-check > gpurun_out/bench_apps_${N}gpu_nccl.jsonl 2> gpurun_out/bench_apps_${N}gpu_nccl.err; echo "apps nccl rc=$?"
+GLB_EXCHANGE=nccl timeout 900 $TR tests/bench_apps.py ${APPS:-bfs pagerank sssp} --no-check > gpurun_out/bench_apps_${N}gpu_nccl.jsonl 2> gpurun_out/bench_apps_${N}gpu_nccl.err; echo "apps nccl rc=$?"
 grep '^{' gpurun_out/bench_apps_${N}gpu_nccl.jsonl | cut -c1-900

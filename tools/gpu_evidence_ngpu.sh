@@ -10,7 +10,7 @@ print(d['n_gpus'], 'GTEPS', round(d['value'],1), 'ms/step', round(d['ms_per_step
 timeout 400 $TR bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_${N}gpu_mc.json 2> gpurun_out/bench_${N}gpu_mc.err; echo "bench mc rc=$?"; show gpurun_out/bench_${N}gpu_mc.json
 grep -i "unavailable" gpurun_out/bench_${N}gpu_mc.err | head -3
 GLB_XCHG_MC=kernel timeout 400 $TR bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_${N}gpu_mck.json 2> gpurun_out/bench_${N}gpu_mck.err; echo "bench mc-kernel rc=$?"; show gpurun_out/bench_${N}gpu_mck.json
-timeout 600 $TR tools/bench_apps.py bfs pagerank sssp > gpurun_out/bench_apps_${N}gpu_mc.jsonl 2> gpurun_out/bench_apps_${N}gpu_mc.err; echo "apps rc=$?"
+timeout 600 $TR tests/bench_apps.py bfs pagerank sssp > gpurun_out/bench_apps_${N}gpu_mc.jsonl 2> gpurun_out/bench_apps_${N}gpu_mc.err; echo "apps rc=$?"
 grep '^{' gpurun_out/bench_apps_${N}gpu_mc.jsonl | python -c "
 import sys, json
 for l in sys.stdin:
