@@ -8,11 +8,13 @@
 //
 // Three stream-ordered launches, none sized by device data (persistent grids read the
 // frontier length from x[0].index):
-//   1. scatter (light columns): one warp per active column, lanes stride down the column and
-//      combine a (x) v into a dense accumulator that rests at the (+)-identity:
-//      atomicAdd / benign store of 1.0f / ordered-int atomicMin;
-//      columns longer than kHeavy are queued instead;
-//   2. scatter (heavy columns): the whole grid strides down each queued column;
+//   1. scatter (column heads): one warp per active column combines the first kSeg non-zeros of
+//      the column, a (x) v, into a dense accumulator that rests at the (+)-identity
+//      (atomicAdd / benign store of 1.0f / ordered-int atomicMin) and queues the rest of a
+//      longer column as segments of kSeg non-zeros;
+//   2. scatter (queued segments): one warp per segment, so the 10^5-long columns of a power-law
+//      graph are spread over the whole grid instead of serialising one warp (or one grid-wide
+//      pass per column, as the first version did: 29 us for ~80 long columns on C3);
 //   3. compact: scan the accumulator, fold `zero`, apply the mask, reset touched entries,
 //      emit with warp-aggregated atomics on y[0].index.
 #include <math.h>
@@ -25,7 +27,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kHeavy = 2048;          // column length that goes to the grid-wide pass
+constexpr uint32_t kSeg = 512;             // non-zeros per unit of work (one warp: 16 strides of 32)
 constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
 
 template <int OP>
@@ -60,11 +62,20 @@ struct SpmspvParams {
     const float *__restrict__ mask;
     glb_idx_val_t *y;
     float *acc;
-    uint32_t *heavy;  // [0] = count, then entries (k indices into x)
+    uint32_t *heavy;  // [0] = number of queued segments, [2 + 2i], [3 + 2i] = {frontier slot k, segment number}
+    uint32_t heavy_cap;  // segments the queue holds (nnz / kSeg + 1: enough unless x repeats columns)
     uint32_t num_rows;
     float zero;
     int mask_type;
 };
+
+// one warp, non-zeros [s, t) of one column, t - s <= kSeg
+template <int OP>
+__device__ __forceinline__ void scatter_span(const SpmspvParams &P, uint32_t s, uint32_t t, float v, unsigned lane) {
+#pragma unroll 4
+    for (uint32_t i = s + lane; i < t; i += 32)
+        combine<OP>(P.acc + __ldg(P.indices + i), spmspv_mul<OP>(__ldg(P.vals + i), v));
+}
 
 template <int OP>
 __global__ void __launch_bounds__(kThreads) spmspv_scatter_light(const SpmspvParams P) {
@@ -78,26 +89,43 @@ __global__ void __launch_bounds__(kThreads) spmspv_scatter_light(const SpmspvPar
     }
     for (uint32_t k = warp; k < nnz_x; k += n_warps) {
         const glb_idx_val_t e = P.x[k + 1];
-        const uint32_t s = P.indptr[e.index], t = P.indptr[e.index + 1];
-        if (t - s > kHeavy) {
-            if (lane == 0) P.heavy[1 + atomicAdd(P.heavy, 1u)] = k;
-            continue;
+        const uint32_t s = __ldg(P.indptr + e.index), t = __ldg(P.indptr + e.index + 1);
+        const uint32_t len = t - s;
+        bool queued = false;
+        if (len > kSeg) {  // queue segments 1 .. n_extra of this column: {frontier slot, segment}
+            const uint32_t n_extra = (len - 1) / kSeg;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.heavy, n_extra);
+            base = __shfl_sync(kFull, base, 0);
+            // a frontier that lists columns more than once can outgrow the queue: then this warp walks
+            // the whole column itself and voids what it reserved
+            queued = base + n_extra <= P.heavy_cap;
+            for (uint32_t j = lane; j < n_extra && base + j < P.heavy_cap; j += 32) {
+                P.heavy[2 + 2 * (base + j)] = k;
+                P.heavy[3 + 2 * (base + j)] = queued ? j + 1 : 0xffffffffu;
+            }
         }
-        for (uint32_t i = s + lane; i < t; i += 32)
-            combine<OP>(P.acc + P.indices[i], spmspv_mul<OP>(P.vals[i], e.val));
+        if (queued) {
+            scatter_span<OP>(P, s, s + kSeg, e.val, lane);
+        } else {
+            for (uint32_t b = s; b < t; b += kSeg) scatter_span<OP>(P, b, t - b > kSeg ? b + kSeg : t, e.val, lane);
+        }
     }
 }
 
 template <int OP>
 __global__ void __launch_bounds__(kThreads) spmspv_scatter_heavy(const SpmspvParams P) {
-    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
-    const uint32_t n_threads = gridDim.x * kThreads;
-    const uint32_t n_heavy = P.heavy[0];
-    for (uint32_t h = 0; h < n_heavy; ++h) {
-        const glb_idx_val_t e = P.x[P.heavy[1 + h] + 1];
-        const uint32_t s = P.indptr[e.index], t = P.indptr[e.index + 1];
-        for (uint32_t i = s + tid; i < t; i += n_threads)
-            combine<OP>(P.acc + P.indices[i], spmspv_mul<OP>(P.vals[i], e.val));
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
+    const uint32_t n_seg = P.heavy[0] < P.heavy_cap ? P.heavy[0] : P.heavy_cap;
+    for (uint32_t h = warp; h < n_seg; h += n_warps) {
+        const glb_idx_val_t e = P.x[P.heavy[2 + 2 * h] + 1];
+        const uint32_t seg = P.heavy[3 + 2 * h];
+        if (seg == 0xffffffffu) continue;  // voided reservation
+        const uint32_t t = __ldg(P.indptr + e.index + 1);
+        const uint32_t s = __ldg(P.indptr + e.index) + seg * kSeg;
+        scatter_span<OP>(P, s, (t - s > kSeg) ? s + kSeg : t, e.val, lane);
     }
 }
 
@@ -222,7 +250,7 @@ int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     alloc(reinterpret_cast<void **>(&m->indices), sizeof(uint32_t) * nnz);
     alloc(reinterpret_cast<void **>(&m->vals), sizeof(float) * nnz);
     alloc(reinterpret_cast<void **>(&m->acc), sizeof(float) * num_rows);
-    alloc(reinterpret_cast<void **>(&m->counter), sizeof(uint32_t) * (size_t(num_cols) + 2));  // heavy-column queue
+    alloc(reinterpret_cast<void **>(&m->counter), sizeof(uint32_t) * (2 * (size_t(nnz) / kSeg + 1) + 4));  // segment queue
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->indptr, indptr, sizeof(uint32_t) * (size_t(num_cols) + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz)
@@ -266,6 +294,7 @@ int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, co
     P.y = y;
     P.acc = m->acc;
     P.heavy = m->counter;
+    P.heavy_cap = uint32_t(m->nnz / kSeg + 1);
     P.num_rows = m->num_rows;
     P.zero = zero;
     P.mask_type = mask_type;

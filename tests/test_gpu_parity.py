@@ -256,6 +256,31 @@ def test_spmspv_sparsity_sweep_heavy_columns_and_reuse(ctx, oracle, op, zero):
             check_vec(y, oracle.port.spmspv(csc, op, zero, mt, idx, val, mask), op)
 
 
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmspv_segment_boundaries_and_repeated_columns(ctx, oracle, op, zero):
+    # columns of exactly 511 / 512 / 513 / 1024 / 1025 / 5000 non-zeros (the scatter works in segments of
+    # 512), and a frontier that lists the long columns many times over (more queued segments than the
+    # queue holds: those warps walk their column themselves)
+    rng = np.random.default_rng(60 + op)
+    lens = [0, 1, 511, 512, 513, 1024, 1025, 5000, 31, 33, 2048, 6000]
+    n_rows = 7000
+    ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    ix = np.concatenate([np.sort(rng.choice(n_rows, ln, replace=False)) for ln in lens]).astype(np.uint32)
+    d = (np.ones(len(ix)) if op else rng.random(len(ix))).astype(np.float32)
+    csc = CSRMatrix(n_rows, len(lens), d, ix, ip)
+    mask = np.where(rng.random(n_rows) < 0.5, np.float32(zero), np.float32(1)).astype(np.float32)
+    idx = np.arange(len(lens), dtype=np.uint32)
+    val = (1 + rng.integers(0, 5, len(lens))).astype(np.float32)
+    for mt in MASKS:
+        check_vec(gpu_spmspv(ctx, csc, op, zero, mt, idx, val, mask, runs=2),
+                  oracle.port.spmspv(csc, op, zero, mt, idx, val, mask), op)
+    if op != 0:   # repeats change a plus-times result, or-and / min-plus are idempotent: same answer as the oracle's loop
+        idx = np.tile(np.array([7, 11, 10, 5], np.uint32), 40)
+        val = np.tile(np.array([1.0, 2.0, 3.0, 1.0], np.float32), 40)
+        check_vec(gpu_spmspv(ctx, csc, op, zero, 0, idx, val, mask, runs=2),
+                  oracle.port.spmspv(csc, op, zero, 0, idx, val, mask), op)
+
+
 def test_spmspv_empty_frontier_and_rectangular(ctx, oracle):
     rng = np.random.default_rng(50)
     m = random_csr(rng, 70, 40, 0.2, values="small")           # as CSC: 40 rows, 70 columns
