@@ -83,6 +83,8 @@ class ModuleCollection:
         assert xc.n == self.matrix_num_rows_ and xc.n_vectors >= 3, "exchange must hold 3 vectors of the padded dimension"
         self.SpMV_.exchange = xc
         self.SpMV_.vector_buf, self.SpMV_.results_buf, self.SpMV_.mask_buf = xc.buffer(0), xc.buffer(1), xc.buffer(2)
+        if hasattr(self, "SpMSpV_"):   # the distance vector both directions update lives in the exchange too
+            self.SpMSpV_.mask_buf = xc.buffer(2)
 
     def _begin_run(self):
         """No rank starts writing into the peers' vectors before every rank has finished reading the
@@ -104,6 +106,28 @@ class ModuleCollection:
             self.exchange_.allgather(buf.tag[1], self.rank_ * slot, slot)
         else:
             self.ctx.allgather_f32(buf, n // self.world_)
+
+    def _push_begin(self):
+        """Row-sharded push: the dense vector the frontier travels in is the SpMV module's vector."""
+        if self.world_ > 1:
+            n = self.matrix_num_rows_
+            self.SpMV_.home_buffers()
+            if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes != 4 * n:
+                self.SpMV_.vector_buf = self.ctx.alloc(4 * n)
+
+    def _exchange_frontier(self, list_buf, zero):
+        """Row-sharded push: every rank's SpMSpV listed only the rows it owns.  The
+        lists meet as ONE dense vector -- own slice reset and scattered, slices exchanged, the full
+        vector listed again on every rank (into the same list buffer) -- so what follows (the sparse
+        assign on the replicated distance vector, the next SpMSpV) sees the whole frontier."""
+        if self.world_ == 1:
+            return
+        n = self.matrix_num_rows_
+        dense = self.SpMV_.vector_buf
+        rb, re = self._row_range(n)
+        capi.sparse_to_dense_rows(self.ctx, list_buf, dense, rb, re, zero)
+        self._gather(dense, n)
+        capi.dense_to_sparse(self.ctx, dense, n, zero, list_buf)
 
     # -- launch replay: the iteration loop of an app is a fixed launch sequence ------------------
     use_graphs_ = True
@@ -172,8 +196,7 @@ class BFS(ModuleCollection):
     def send_matrix_host_to_device(self):
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
         self._bind_exchange()
-        if self.world_ == 1:   # the push direction is single-GPU in this round
-            self.SpMSpV_.send_matrix_host_to_device()
+        self.SpMSpV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
 
     # -- pull ------------------------------------------------------------------------
     def _pull_loop(self, first_iter, num_iterations, fused):
@@ -218,6 +241,8 @@ class BFS(ModuleCollection):
 
     # -- push ------------------------------------------------------------------------
     def _push_setup(self, source):
+        self._begin_run()
+        self._push_begin()
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [1.0]))
         self.SpMSpV_.set_mask_constant(0.0, source, 1.0)      # distance, bfs.h:138-141
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
@@ -226,6 +251,7 @@ class BFS(ModuleCollection):
         # SpMSpV.run(); results -> vector (the reference copies 1+nnz entries, bfs.h:147-151;
         # here the two list buffers swap roles); SparseAssign.run(iter + 1)
         self.SpMSpV_.run()
+        self._exchange_frontier(self.SpMSpV_.results_buf, self.semiring_[2])
         self.SpMSpV_.vector_buf, self.SpMSpV_.results_buf = self.SpMSpV_.results_buf, self.SpMSpV_.vector_buf
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.vector_buf)
         self.SparseAssign_.run(float(it + 1))
@@ -251,11 +277,13 @@ class BFS(ModuleCollection):
         self.push_iterations_ = it - 1
         # switch: the last frontier becomes the dense SpMV input, on the device
         self.SpMV_.bind_mask_buf(self.SpMSpV_.mask_buf)
-        self.SpMV_.home_buffers()
-        if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
-            self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
-        capi.sparse_to_dense(self.ctx, self.SpMSpV_.vector_buf, self.SpMV_.vector_buf, n, LogicalSemiring[2])
+        if self.world_ == 1:   # (sharded: the frontier already sits in vector_buf, it travelled as a dense vector)
+            self.SpMV_.home_buffers()
+            if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
+                self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
+            capi.sparse_to_dense(self.ctx, self.SpMSpV_.vector_buf, self.SpMV_.vector_buf, n, LogicalSemiring[2])
         self._pull_loop(it, num_iterations, fused)
+        self._gather(self.SpMSpV_.mask_buf, n)    # the pull levels updated the distance shard by shard
         return self.SpMSpV_.send_mask_device_to_host()
 
 
@@ -357,8 +385,7 @@ class SSSP(ModuleCollection):
     def send_matrix_host_to_device(self):
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
         self._bind_exchange()
-        if self.world_ == 1:   # the push direction is single-GPU in this round
-            self.SpMSpV_.send_matrix_host_to_device()
+        self.SpMSpV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
 
     def _pull_loop(self, first_iter, num_iterations, fused):
         n = self.matrix_num_rows_
@@ -392,6 +419,8 @@ class SSSP(ModuleCollection):
         return self.SpMV_.send_vector_device_to_host()
 
     def _push_setup(self, source):
+        self._begin_run()
+        self._push_begin()
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [0.0]))
         self.SpMSpV_.set_mask_constant(self.semiring_[2], source, 0.0)   # distance, sssp.h:172-176
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.results_buf)
@@ -403,6 +432,7 @@ class SSSP(ModuleCollection):
         self._push_setup(source)
         for _ in range(num_iterations):
             self.SpMSpV_.run()
+            self._exchange_frontier(self.SpMSpV_.results_buf, self.semiring_[2])
             self.SparseAssign_.run()
         return self.SpMSpV_.send_mask_device_to_host()
 
@@ -413,6 +443,7 @@ class SSSP(ModuleCollection):
         it = 1
         while True:
             self.SpMSpV_.run()
+            self._exchange_frontier(self.SpMSpV_.results_buf, self.semiring_[2])
             self.SparseAssign_.run()
             vector_nnz = self.SpMSpV_.get_results_nnz()
             it += 1

@@ -70,6 +70,7 @@ SIGNATURES = {
                                       C.POINTER(HostLayout)]),
     "glb_host_layout_free": (C.c_int, [C.POINTER(HostLayout)]),
     "glb_csc_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "glb_csc_create_rows": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "glb_csc_destroy": (C.c_int, [_vp]),
     "glb_spmv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_fused": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.POINTER(Epilogue)]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "glb_spmv_host_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glb_spmspv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "glb_sparse_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    "glb_sparse_to_dense_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float]),
+    "glb_dense_to_sparse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, _vp]),
     "glb_sparse_to_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float]),
     "glb_ewise_add": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float]),
     "glb_assign_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float, C.c_int]),
@@ -464,12 +467,13 @@ class Exchange:
 class CscMatrix:
     """Device-resident CSC (glb_csc_t); ``m.indptr`` runs over columns, ``m.indices`` are row ids."""
 
-    def __init__(self, ctx, m):
+    def __init__(self, ctx, m, row_begin=0, row_end=None):
         ip, ix, d = (np.ascontiguousarray(m.indptr, np.uint32), np.ascontiguousarray(m.indices, np.uint32),
                      np.ascontiguousarray(m.data, np.float32))
+        row_end = int(m.num_rows) if row_end is None else row_end
         h = _vp()
-        check(lib.glb_csc_create(ctx.handle, int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data,
-                                 d.ctypes.data, C.byref(h)))
+        check(lib.glb_csc_create_rows(ctx.handle, int(m.num_rows), int(m.num_cols), ip.ctypes.data, ix.ctypes.data,
+                                      d.ctypes.data, row_begin, row_end, C.byref(h)))
         self.ctx, self.handle = ctx, h
         self.num_rows, self.num_cols = int(m.num_rows), int(m.num_cols)
 
@@ -513,6 +517,14 @@ def sparse_count(ctx, sparse_list):
 
 def sparse_to_dense(ctx, sparse_list, dense, length, zero):
     check(lib.glb_sparse_to_dense(ctx.handle, _ptr(sparse_list), _ptr(dense), length, zero))
+
+
+def sparse_to_dense_rows(ctx, sparse_list, dense, row_begin, row_end, zero):
+    check(lib.glb_sparse_to_dense_rows(ctx.handle, _ptr(sparse_list), _ptr(dense), row_begin, row_end, zero))
+
+
+def dense_to_sparse(ctx, dense, length, zero, sparse_list):
+    check(lib.glb_dense_to_sparse(ctx.handle, _ptr(dense), length, zero, _ptr(sparse_list)))
 
 
 def d2d(ctx, dst, src, nbytes):

@@ -129,7 +129,8 @@ struct glb_csr_s {
 struct glb_csc_s {
     glb_ctx_t ctx = nullptr;
     uint32_t num_rows = 0, num_cols = 0;
-    uint64_t nnz = 0;
+    uint32_t row_begin = 0, row_end = 0;  // output rows this shard owns (all rows when not sharded)
+    uint64_t nnz = 0;                     // non-zeros kept (rows inside the shard)
     uint32_t *indptr = nullptr;   // num_cols + 1
     uint32_t *indices = nullptr;  // row ids
     float *vals = nullptr;

@@ -20,6 +20,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "glb_internal.h"
 #include "semiring.cuh"
 
@@ -63,6 +65,7 @@ struct SpmspvParams {
     glb_idx_val_t *y;
     float *acc;
     uint32_t *heavy;  // [0] = number of queued segments, [2 + 2i], [3 + 2i] = {frontier slot k, segment number}
+    uint32_t row_begin, row_end;  // output rows of this shard: the compaction scans only these
     uint32_t heavy_cap;  // segments the queue holds (nnz / kSeg + 1: enough unless x repeats columns)
     uint32_t num_rows;
     float zero;
@@ -134,11 +137,12 @@ __global__ void __launch_bounds__(kThreads) spmspv_compact(const SpmspvParams P)
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n_threads = gridDim.x * kThreads;
     if (blockIdx.x == 0 && threadIdx.x == 0) P.heavy[0] = 0;  // ready for the next run
-    const uint32_t n_round = (P.num_rows + 31u) & ~31u;       // keep warps converged for the ballots
-    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_round; r += n_threads) {
+    const uint32_t n_round = (P.row_end - P.row_begin + 31u) & ~31u;  // keep warps converged for the ballots
+    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n_round; q += n_threads) {
+        const uint32_t r = P.row_begin + q;
         bool emit = false;
         float val = 0.0f;
-        if (r < P.num_rows) {
+        if (r < P.row_end) {
             const float a = P.acc[r];
             if (a != Semi<OP>::ident()) {
                 P.acc[r] = Semi<OP>::ident();
@@ -185,6 +189,37 @@ __global__ void sparse_scatter_kernel(const glb_idx_val_t *__restrict__ list, fl
     }
 }
 
+// dense -> sparse list {count, zero}, entries != zero (the inverse of sparse_scatter_kernel): the
+// row-sharded push direction exchanges its frontier as a dense vector and lists it again on every rank
+__global__ void __launch_bounds__(kThreads) dense_to_sparse_kernel(const float *__restrict__ dense, uint32_t len, float zero,
+                                                                 glb_idx_val_t *list) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_threads = gridDim.x * kThreads;
+    const uint32_t n_round = (len + 31u) & ~31u;
+    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_round; r += n_threads) {
+        const float v = r < len ? dense[r] : zero;
+        const bool emit = r < len && v != zero;
+        const unsigned b = __ballot_sync(kFull, emit);
+        if (b) {
+            uint32_t base = 0;
+            const int leader = __ffs(int(b)) - 1;
+            if (int(lane) == leader) base = atomicAdd(&list[0].index, uint32_t(__popc(b)));
+            base = __shfl_sync(kFull, base, leader);
+            if (emit) {
+                glb_idx_val_t o;
+                o.index = r;
+                o.val = v;
+                list[1 + base + __popc(b & ((1u << lane) - 1u))] = o;
+            }
+        }
+    }
+}
+
+__global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
+    list[0].index = 0;
+    list[0].val = zero;
+}
+
 template <int OP>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
     const float ident = (OP == GLB_OP_ADD_MIN) ? HUGE_VALF : 0.0f;
@@ -229,18 +264,49 @@ int glb_buffer_fill_one_f32(glb_ctx_t ctx, float *dst_dev, float val, size_t n, 
 
 int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
                    const float *data, glb_csc_t *out) {
+    return glb_csc_create_rows(ctx, num_rows, num_cols, indptr, indices, data, 0, num_rows, out);
+}
+
+int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr, const uint32_t *indices,
+                        const float *data, uint32_t row_begin, uint32_t row_end, glb_csc_t *out) {
     GLB_REQUIRE(ctx && out && indptr, "NULL argument");
+    GLB_REQUIRE(row_begin <= row_end && row_end <= num_rows, "bad row range");
     *out = nullptr;
-    const uint64_t nnz = indptr[num_cols];
-    GLB_REQUIRE(nnz == 0 || (indices && data), "NULL indices/data");
+    const uint64_t nnz_all = indptr[num_cols];
+    GLB_REQUIRE(nnz_all == 0 || (indices && data), "NULL indices/data");
     for (uint32_t c = 0; c < num_cols; ++c) GLB_REQUIRE(indptr[c + 1] >= indptr[c], "indptr not monotone");
-    for (uint64_t i = 0; i < nnz; ++i) GLB_REQUIRE(indices[i] < num_rows, "row index out of range");
+    for (uint64_t i = 0; i < nnz_all; ++i) GLB_REQUIRE(indices[i] < num_rows, "row index out of range");
+    // a row shard keeps, of every column, the entries whose row it owns (the reference's row tiles,
+    // data_formatter.h:621,665, with the tile = the GPU)
+    std::vector<uint32_t> s_indptr, s_indices;
+    std::vector<float> s_data;
+    if (row_begin != 0 || row_end != num_rows) {
+        s_indptr.assign(size_t(num_cols) + 1, 0);
+        for (uint32_t c = 0; c < num_cols; ++c) {
+            uint32_t kept = 0;
+            for (uint32_t i = indptr[c]; i < indptr[c + 1]; ++i) kept += (indices[i] >= row_begin && indices[i] < row_end);
+            s_indptr[c + 1] = s_indptr[c] + kept;
+        }
+        s_indices.resize(s_indptr[num_cols]);
+        s_data.resize(s_indptr[num_cols]);
+        for (uint32_t c = 0; c < num_cols; ++c) {
+            uint32_t w = s_indptr[c];
+            for (uint32_t i = indptr[c]; i < indptr[c + 1]; ++i)
+                if (indices[i] >= row_begin && indices[i] < row_end) { s_indices[w] = indices[i]; s_data[w] = data[i]; ++w; }
+        }
+        indptr = s_indptr.data();
+        indices = s_indices.data();
+        data = s_data.data();
+    }
+    const uint64_t nnz = indptr[num_cols];
     GLB_CUDA(cudaSetDevice(ctx->device));
     glb_csc_t m = new glb_csc_s();
     m->ctx = ctx;
     glb_ctx_retain(ctx);
     m->num_rows = num_rows;
     m->num_cols = num_cols;
+    m->row_begin = row_begin;
+    m->row_end = row_end;
     m->nnz = nnz;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) {
@@ -295,6 +361,8 @@ int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, co
     P.acc = m->acc;
     P.heavy = m->counter;
     P.heavy_cap = uint32_t(m->nnz / kSeg + 1);
+    P.row_begin = m->row_begin;
+    P.row_end = m->row_end;
     P.num_rows = m->num_rows;
     P.zero = zero;
     P.mask_type = mask_type;
@@ -322,6 +390,28 @@ int glb_sparse_to_dense(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, 
     int rc = glb_buffer_fill_f32(ctx, dense, zero, len);
     if (rc) return rc;
     sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, len);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+// Row-sharded push: the frontier travels as a dense vector.  glb_sparse_to_dense_rows resets rows
+// [row_begin, row_end) of `dense` to `zero` and scatters the list entries that fall inside;
+// glb_dense_to_sparse lists the entries != zero of a dense vector ({count, zero} head, order unspecified).
+int glb_sparse_to_dense_rows(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, uint32_t row_begin, uint32_t row_end,
+                             float zero) {
+    GLB_REQUIRE(ctx && list && dense && row_begin <= row_end, "bad argument");
+    if (row_begin == row_end) return GLB_OK;
+    int rc = glb_buffer_fill_f32(ctx, dense + row_begin, zero, row_end - row_begin);
+    if (rc) return rc;
+    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, row_end);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_dense_to_sparse(glb_ctx_t ctx, const float *dense, uint32_t len, float zero, glb_idx_val_t *list) {
+    GLB_REQUIRE(ctx && list && (len == 0 || dense), "NULL argument");
+    sparse_head_kernel<<<1, 1, 0, ctx->stream>>>(list, zero);
+    if (len) dense_to_sparse_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(dense, len, zero, list);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }

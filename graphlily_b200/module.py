@@ -190,9 +190,10 @@ class SpMSpVModule(BaseModule):
     def load_and_format_matrix(self, csc_matrix_float):
         self.csc_matrix_float_ = csc_matrix_float             # spmspv_module.h:264-286
 
-    def send_matrix_host_to_device(self):
-        """spmspv_module.h:290-370: matrix upload + results (rows+1) and vector (cols+1) lists."""
-        self.matrix = capi.CscMatrix(self.ctx, self.csc_matrix_float_)
+    def send_matrix_host_to_device(self, row_begin=0, row_end=None):
+        """spmspv_module.h:290-370: matrix upload + results (rows+1) and vector (cols+1) lists.
+        A row range uploads the row shard of a multi-GPU run (the entries whose row lies inside)."""
+        self.matrix = capi.CscMatrix(self.ctx, self.csc_matrix_float_, row_begin, row_end)
         self.results_buf = self.ctx.to_device(np.zeros(self.get_num_rows() + 1, capi.IDX_VAL))
         self.vector_buf = self.ctx.to_device(np.zeros(self.get_num_cols() + 1, capi.IDX_VAL))
 

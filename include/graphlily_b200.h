@@ -161,6 +161,11 @@ int glb_host_layout_free(glb_host_layout_t *layout);
  * host CSC (CSCMatrix<float>, data_loader.h:92-104; indptr has num_cols+1 entries). */
 int glb_csc_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr,
                    const uint32_t *indices, const float *data, glb_csc_t *out);
+/* Row shard of the push direction (multi-GPU): keeps, of every column, the entries whose row lies
+ * in [row_begin, row_end) -- the reference's row tiles (data_formatter.h:621,665) with the tile =
+ * the GPU.  glb_spmspv on it lists only rows of the shard; row ids stay global. */
+int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *indptr,
+                        const uint32_t *indices, const float *data, uint32_t row_begin, uint32_t row_end, glb_csc_t *out);
 int glb_csc_destroy(glb_csc_t m);
 
 /* ------------------------------------------------------------------ overlay mode 1
@@ -218,6 +223,13 @@ int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count);
 /* convert_sparse_vec_to_dense_vec (global.h:153-164) done on the device (the reference does it
  * on the host at the push->pull switch, bfs.h:195-201). dense[0..len) = zero, then scatter. */
 int glb_sparse_to_dense(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, uint32_t len, float zero);
+/* The row-sharded push direction exchanges its frontier as a dense vector (north_star: one dense
+ * exchange per iteration): _rows resets rows [row_begin, row_end) of `dense` to `zero` and scatters the
+ * list entries inside that range; glb_dense_to_sparse lists the entries != zero of a dense vector
+ * ({count, zero} head, order unspecified). */
+int glb_sparse_to_dense_rows(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, uint32_t row_begin,
+                             uint32_t row_end, float zero);
+int glb_dense_to_sparse(glb_ctx_t ctx, const float *dense, uint32_t len, float zero, glb_idx_val_t *list);
 
 /* ------------------------------------------------------------------ overlay mode 3
  * kernel_add_scalar_vector_dense_impl.h:6-27: out[i] = in[i] + val. in may equal out. */

@@ -160,10 +160,9 @@ def main():
                              "loop_only_gteps": nnz / (loop_ms / iters * 1e-3) / 1e9}
             results["pull"] = out.copy()
         else:
-            run_modes = [("pull", lambda: a.pull(source, iters))]
-            if world == 1:
-                run_modes += [("pull_push", lambda: a.pull_push(source, iters, 0.001 if name == "bfs" else 0.05)),
-                              ("push", lambda: a.push(source, iters))]
+            run_modes = [("pull", lambda: a.pull(source, iters)),
+                         ("pull_push", lambda: a.pull_push(source, iters, 0.001 if name == "bfs" else 0.05)),
+                         ("push", lambda: a.push(source, iters))]
             for mode, fn in run_modes:
                 loop_ev[2] = False
                 ms, out, loop_ms = timed(fn, args.reps)

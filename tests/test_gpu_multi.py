@@ -116,8 +116,14 @@ def _worker(rank, world, port, kind):
                 got, ref = a.pull(rep, 4), oracle.port.sssp(mat, rep, 4, 255.0)
             if name == "pagerank":
                 assert_close_rel(got, ref, 1e-5)
-            else:
-                assert got.tobytes() == ref.tobytes(), f"rank {rank} {name} run {rep}"
+                continue
+            assert got.tobytes() == ref.tobytes(), f"rank {rank} {name} run {rep}"
+            # the push direction on row shards of the CSC (frontier exchanged as a dense vector), and the
+            # direction switch, against the same oracle result
+            iters = 5 if name == "bfs" else 4
+            assert a.push(rep, iters).tobytes() == ref.tobytes(), f"rank {rank} {name} push run {rep}"
+            for thr in (0.002, 0.2, 1.1):
+                assert a.pull_push(rep, iters, thr).tobytes() == ref.tobytes(), f"rank {rank} {name} pull_push {thr} run {rep}"
         assert not x2.timed_out()
         dist.barrier()
         x2.close()

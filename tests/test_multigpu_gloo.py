@@ -83,3 +83,56 @@ def test_row_range_partition():
     mc.set_sharding(1, 8)
     with pytest.raises(AssertionError):
         mc._row_range(1001)
+
+
+def _worker_push(rank, world, port, out_dir):
+    """The row-sharded PUSH protocol (app._exchange_frontier) with the per-rank SpMSpV played by the
+    oracle on the rank's row shard of the CSC: own rows listed -> own slice of a dense vector ->
+    allgather -> listed again on every rank -> sparse assign on the replicated distance vector."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from graphlily_b200 import datasets
+    from graphlily_b200.app import ModuleCollection
+    from graphlily_b200.io import CSRMatrix
+
+    g = datasets.powerlaw_graph(1024, 12000, seed=4)
+    g.data = np.ones(g.nnz, np.float32)
+    n = g.num_rows
+    ip, ix, d = oracle.port.csr2csc(g)
+    mc = ModuleCollection()
+    mc.set_sharding(rank, world)
+    rb, re = mc._row_range(n)
+    # row shard of the CSC: of every column the entries whose row the rank owns (glb_csc_create_rows)
+    keep = (ix >= rb) & (ix < re)
+    s_ip = np.concatenate([[0], np.cumsum(np.add.reduceat(keep, ip[:-1].astype(np.int64)) * (np.diff(ip.astype(np.int64)) > 0))])
+    shard = CSRMatrix(n, g.num_cols, d[keep], ix[keep], s_ip.astype(np.uint32))
+    distance = np.zeros(n, np.float32)
+    distance[0] = 1.0
+    f_idx, f_val = np.array([0], np.uint32), np.array([1.0], np.float32)
+    for it in range(1, 6):
+        y = oracle.port.spmspv(shard, 1, 0.0, 1, f_idx, f_val, distance)       # or-and, WriteToZero on the distance
+        assert not y[:rb].any() and not y[re:].any()                          # a shard lists only its own rows
+        dense = torch.zeros(n, dtype=torch.float32)
+        dense[rb:re] = torch.from_numpy(y[rb:re])
+        slots = list(dense.view(world, -1).unbind(0))
+        dist.all_gather(slots, dense[rb:re].clone())
+        f_idx = np.nonzero(dense.numpy())[0].astype(np.uint32)
+        f_val = dense.numpy()[f_idx]
+        distance[f_idx] = it + 1
+    np.save(os.path.join(out_dir, f"d{rank}.npy"), distance)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_push_protocol_matches_oracle(tmp_path, oracle):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_push, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, ROOT)
+    from graphlily_b200 import datasets
+    g = datasets.powerlaw_graph(1024, 12000, seed=4)
+    g.data = np.ones(g.nnz, np.float32)
+    ref = oracle.port.bfs(g, 0, 5)
+    got = [np.load(tmp_path / f"d{r}.npy") for r in range(world)]
+    assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], ref)
