@@ -420,14 +420,26 @@ int glb_graph_destroy(glb_graph_t g) {
 // A row-sharded iteration needs every rank's slice of y on every rank before the next SpMV.
 // Instead of an allgather after the kernel, the SpMV write-back stores each row into all peers'
 // copies (glb_spmv_exchange); what is left of the collective is this signal / wait step.
-__global__ void xchg_signal_wait_kernel(uint32_t *const *peer_flags, uint32_t *local_flags, int rank, int nranks,
-                                        uint32_t epoch, uint32_t *err) {
+__global__ void xchg_signal_wait_kernel(uint32_t *const *peer_flags, uint32_t *local_flags, uint32_t *mc_flags, int rank,
+                                        int nranks, uint32_t epoch, uint32_t *err) {
     const int p = int(threadIdx.x);
-    if (p >= nranks || p == rank) return;
-    // all SpMV stores of this rank were issued by kernels that completed before this one started
-    // (stream order); publish, then wait for the peer's slice
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
+    // all stores of this rank were issued by kernels that completed before this one started (stream
+    // order); publish, then wait for the peers' slices
+    if (mc_flags) {
+        // Data that travelled as multicast stores is published by a multicast store too, so the flag
+        // follows the data through the switch on every destination -- this rank included: its own
+        // slice comes back through the switch as well, and nothing may overwrite it locally before
+        // that copy has landed.  Hence the wait below covers all ranks, not only the peers.
+        if (p == 0) {
+            __threadfence_system();
+            asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_flags + rank), "r"(epoch) : "memory");
+        }
+        if (p >= nranks) return;
+    } else {
+        if (p >= nranks || p == rank) return;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
+    }
     const long long t0 = clock64();
     uint32_t seen;
     do {
@@ -441,8 +453,8 @@ __global__ void xchg_signal_wait_kernel(uint32_t *const *peer_flags, uint32_t *l
 
 int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc) {
     xc->epoch++;
-    xchg_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(xc->d_peer_flags, xc->local_flags, xc->rank, xc->nranks, xc->epoch,
-                                                      xc->d_err);
+    xchg_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(xc->d_peer_flags, xc->local_flags, xc->mc_flags, xc->rank, xc->nranks,
+                                                      xc->epoch, xc->d_err);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
@@ -532,6 +544,7 @@ int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, in
     }
     xc->local = xc->peer[rank];
     xc->local_flags = xc->peer_flags[rank];
+    if (xc->mc) xc->mc_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->mc) + vec_bytes);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&xc->d_peer_flags), sizeof(uint32_t *) * (GLB_MAX_PEERS + 1));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_err), sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(xc->d_err, 0, sizeof(uint32_t));

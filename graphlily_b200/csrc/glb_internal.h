@@ -162,6 +162,7 @@ struct glb_xchg_s {
     // a multicast mapping -- one store to `mc` lands in every rank's block (NVSwitch multicast)
     bool adopted = false;
     float *mc = nullptr;
+    uint32_t *mc_flags = nullptr;  // multicast mapping of the flag words
 };
 extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
 

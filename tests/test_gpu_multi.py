@@ -90,6 +90,7 @@ def _worker(rank, world, port, kind):
     v[rank * slot:(rank + 1) * slot] = rank + 1
     xc.barrier()
     xc.buffer(2).write(v)
+    xc.barrier()     # every rank has placed its full vector before any slice arrives from a peer
     xc.allgather(2, rank * slot, slot)
     got = xc.buffer(2).read(np.float32, n)
     assert (got.reshape(world, slot) == np.arange(1, world + 1, dtype=np.float32)[:, None]).all()
