@@ -342,3 +342,104 @@ def test_apply_shapes_of_reference_tests(ctx, oracle):
     nf = ctx.to_device(np.zeros(4, capi.IDX_VAL))
     capi.assign_sparse_relax(ctx, empty, dense, nf)
     assert capi.sparse_count(ctx, nf) == 0 and dense.read(np.float32, 4096).tobytes() == ref.tobytes()
+
+
+# ------------------------------------------------------------- pieces of the row-sharded runs, on one GPU
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmspv_row_shards_tile_the_result(ctx, oracle, op, zero):
+    # glb_csc_create_rows: each shard lists only its own rows and together they give the full result;
+    # the frontier round trip of the sharded push (list -> dense rows -> list) loses nothing
+    rng = np.random.default_rng(70 + op)
+    g = datasets.powerlaw_csr(6000, 5000, 150_000, seed=17, max_degree=4000)
+    ip, ix, d = oracle.port.csr2csc(g)
+    csc = CSRMatrix(g.num_rows, g.num_cols, np.ones_like(d) if op else rng.random(len(d)).astype(np.float32), ix, ip)
+    n = csc.num_rows
+    k = 300
+    idx = np.sort(rng.choice(csc.num_cols, k, replace=False)).astype(np.uint32)
+    val = (1 + rng.integers(0, 9, k)).astype(np.float32)
+    mask = np.where(rng.random(n) < 0.5, np.float32(zero), np.float32(1)).astype(np.float32)
+    ref = oracle.port.spmspv(csc, op, zero, 1, idx, val, mask)
+    dx = ctx.to_device(capi.sparse_to_numpy(idx, val, csc.num_cols + 1))
+    dm = ctx.to_device(mask)
+    dense = ctx.to_device(np.full(n, -9.0, np.float32))
+    bounds = [0, 1000, 1001, 4096, n]
+    for rb, re in zip(bounds[:-1], bounds[1:]):
+        S = capi.CscMatrix(ctx, csc, rb, re)
+        dy = ctx.to_device(np.zeros(n + 1, capi.IDX_VAL))
+        for _ in range(2):   # second run: the accumulator was left clean
+            S.spmspv(op, zero, 1, dx, dm, dy)
+        oi, ov = dy.read_sparse()
+        assert ((oi >= rb) & (oi < re)).all() and len(np.unique(oi)) == len(oi)
+        got = densify(oi, ov, n, zero)
+        if op == 0:
+            assert_close_rel(got[rb:re], ref[rb:re], 1e-5)
+        else:
+            assert got[rb:re].tobytes() == ref[rb:re].tobytes()
+        capi.sparse_to_dense_rows(ctx, dy, dense, rb, re, zero)
+        S.close()
+    full = dense.read(np.float32, n)
+    check_vec(full, ref, op)
+    relisted = ctx.to_device(np.zeros(n + 1, capi.IDX_VAL))
+    capi.dense_to_sparse(ctx, dense, n, zero, relisted)
+    oi, ov = relisted.read_sparse()
+    assert len(np.unique(oi)) == len(oi) and not (ov == np.float32(zero)).any()
+    assert densify(oi, ov, n, zero).tobytes() == full.tobytes()
+    assert relisted.read(capi.IDX_VAL, 1)["val"][0] == np.float32(zero)
+
+
+def test_exchange_api_with_a_single_rank(ctx, oracle):
+    # the peer-mapped exchange degenerates cleanly to one rank: same results as glb_spmv, and every
+    # entry point of the family (create / export / connect / vector / spmv / allgather / barrier /
+    # host batch / status / destroy) runs on a one-GPU box
+    rng = np.random.default_rng(80)
+    m = datasets.powerlaw_csr(4096, 4096, 1 << 16, seed=19, max_degree=2000)
+    n = m.num_rows
+    A = capi.CsrMatrix(ctx, m)
+    xc = capi.Exchange(ctx, n, 0, 1, lambda b: [b], n_vectors=3)
+    assert not xc.has_multicast()
+    x = rng.random(n).astype(np.float32)
+    xc.barrier()
+    xc.buffer(0).write(x)
+    ref = x
+    for it in range(3):
+        xc.spmv(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, it % 2, (it + 1) % 2)
+        ref = oracle.port.spmv(m, 0, 0.0, 0, ref)
+    assert_close_rel(xc.buffer(1).read(np.float32, n), ref, 1e-4)
+    xc.allgather(1, 0, n)
+    xs, ys = [capi.PinnedArray(n) for _ in range(3)], [capi.PinnedArray(n) for _ in range(3)]
+    for k in range(3):
+        xs[k].array[:] = np.random.default_rng(90 + k).random(n).astype(np.float32)
+    xc.spmv_host_batch(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, [a.ptr for a in xs], None, [a.ptr for a in ys])
+    for k in range(3):
+        assert_close_rel(ys[k].array, oracle.port.spmv(m, 0, 0.0, 0, xs[k].array), 1e-5)
+    assert not xc.timed_out()
+    xc.close()
+    A.close()
+
+
+def test_host_batch_matches_single_calls(ctx, oracle):
+    # glb_spmv_host_batch (three-stream pipeline) against glb_spmv_host and the oracle, masked and not,
+    # odd batch sizes, pageable and page-locked buffers
+    rng = np.random.default_rng(85)
+    m = datasets.powerlaw_csr(5000, 3000, 1 << 16, seed=23, max_degree=2500)
+    A = capi.CsrMatrix(ctx, m)
+    for count, pinned in ((1, True), (2, True), (5, True), (3, False)):
+        mk = (lambda k: capi.PinnedArray(k).array) if pinned else (lambda k: np.empty(k, np.float32))
+        hold = [capi.PinnedArray(max(m.num_rows, m.num_cols)) for _ in range(3 * count)] if pinned else None
+        xs, ms, ys = [], [], []
+        for k in range(count):
+            xa = hold[3 * k].array[:m.num_cols] if pinned else mk(m.num_cols)
+            ma = hold[3 * k + 1].array[:m.num_rows] if pinned else mk(m.num_rows)
+            ya = hold[3 * k + 2].array[:m.num_rows] if pinned else mk(m.num_rows)
+            xa[:] = rng.random(m.num_cols).astype(np.float32)
+            ma[:] = rng.integers(0, 2, m.num_rows).astype(np.float32)
+            ya[:] = np.nan
+            xs.append(xa), ms.append(ma), ys.append(ya)
+        for mt in (capi.MASK_NONE, capi.MASK_WRITE_TO_ONE):
+            A.spmv_host_batch(capi.OP_MUL_ADD, 0.0, mt, xs, ms if mt else None, ys)
+            single = np.empty(m.num_rows, np.float32)
+            for k in range(count):
+                assert_close_rel(ys[k], oracle.port.spmv(m, 0, 0.0, mt, xs[k], ms[k] if mt else None), 1e-5)
+                A.spmv_host(capi.OP_MUL_ADD, 0.0, mt, xs[k], ms[k] if mt else None, single)
+                assert single.tobytes() == ys[k].tobytes()      # same kernels, same order: bit-identical
+    A.close()
