@@ -86,6 +86,10 @@ class ModuleCollection:
         if hasattr(self, "SpMSpV_"):   # the distance vector both directions update lives in the exchange too
             self.SpMSpV_.mask_buf = xc.buffer(2)
 
+    def _matrix_changed(self):
+        """A new matrix went to the device: recorded launch sequences of the old one are void."""
+        self.__dict__.pop("graphs_", None)
+
     def _begin_run(self):
         """No rank starts writing into the peers' vectors before every rank has finished reading the
         previous run's results out of them."""
@@ -141,6 +145,8 @@ class ModuleCollection:
         if not self.use_graphs_ or self.world_ > 1:
             launches()
             return
+        # a recorded sequence holds the device addresses of the matrix it was recorded with
+        key = key + (self.SpMV_.matrix.handle.value,)
         cache = self.__dict__.setdefault("graphs_", {})
         g = cache.get(key)
         if g is None:
@@ -194,6 +200,7 @@ class BFS(ModuleCollection):
         assert m.num_rows == m.num_cols
 
     def send_matrix_host_to_device(self):
+        self._matrix_changed()
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
         self._bind_exchange()
         self.SpMSpV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
@@ -316,6 +323,7 @@ class PageRank(ModuleCollection):
         assert m.num_rows == m.num_cols
 
     def send_matrix_host_to_device(self):
+        self._matrix_changed()
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
         self._bind_exchange()
 
@@ -383,6 +391,7 @@ class SSSP(ModuleCollection):
         assert m.num_rows == m.num_cols
 
     def send_matrix_host_to_device(self):
+        self._matrix_changed()
         self.SpMV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))
         self._bind_exchange()
         self.SpMSpV_.send_matrix_host_to_device(*self._row_range(self.matrix_num_rows_))

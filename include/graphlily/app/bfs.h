@@ -51,7 +51,7 @@ private:
         const uint32_t n = matrix_num_rows_;
         if (fused_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf, mask = SpMV_->mask_buf;
-            replay({1, first_iter, num_iterations, key_of(vec.ptr()), key_of(res.ptr()), key_of(mask.ptr())}, [&] {
+            replay({1, key_of(SpMV_->device_matrix()), first_iter, num_iterations, key_of(vec.ptr()), key_of(res.ptr()), key_of(mask.ptr())}, [&] {
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
                     glb_spmv_epilogue_t ep = {0, 0.0f, mask.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
@@ -131,6 +131,7 @@ public:
     }
 
     void send_matrix_host_to_device() {
+        drop_recorded_sequences();
         SpMV_->send_matrix_host_to_device();
         SpMSpV_->send_matrix_host_to_device();
     }

@@ -51,6 +51,11 @@ protected:
         graphs_.emplace_back(key, g);
         GLB_CHECK(glb_graph_launch(runtime_->ctx(), g));
     }
+    // a new matrix went to the device: sequences recorded with the old one are void
+    void drop_recorded_sequences() {
+        for (auto &kv : graphs_) glb_graph_destroy(kv.second);
+        graphs_.clear();
+    }
     static uint64_t key_of(const void *p) { return uint64_t(reinterpret_cast<uintptr_t>(p)); }
     static uint64_t key_of(float v) { uint32_t b; memcpy(&b, &v, sizeof(b)); return b; }
 

@@ -58,7 +58,10 @@ public:
         load_and_format_matrix(graphlily::io::load_csr_matrix_from_float_npz(csr_float_npz_path), damping, skip_empty_rows);
     }
 
-    void send_matrix_host_to_device() { SpMV_->send_matrix_host_to_device(); }
+    void send_matrix_host_to_device() {
+        drop_recorded_sequences();
+        SpMV_->send_matrix_host_to_device();
+    }
 
     aligned_dense_vec_t pull(float damping, uint32_t num_iterations) {
         const uint32_t n = matrix_num_rows_;
@@ -66,7 +69,7 @@ public:
         SpMV_->set_vector_constant(float(1.0 / n));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
         if (fused_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
-            replay({2, key_of(teleport), num_iterations, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
+            replay({2, key_of(SpMV_->device_matrix()), key_of(teleport), num_iterations, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
                 glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t iter = 1; iter <= num_iterations; iter++) {

@@ -88,7 +88,7 @@ private:
         if (fused_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
             const uint32_t count = num_iterations >= first_iter ? num_iterations - first_iter + 1 : 0;
-            replay({3, count, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
+            replay({3, key_of(SpMV_->device_matrix()), count, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t k = 0; k < count; k++) {
                     SpMV_->run_fused(v, DeviceBuffer(), r, nullptr);
@@ -156,6 +156,7 @@ public:
     }
 
     void send_matrix_host_to_device() {
+        drop_recorded_sequences();
         SpMV_->send_matrix_host_to_device();
         SpMSpV_->send_matrix_host_to_device();
     }
