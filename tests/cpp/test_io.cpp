@@ -35,6 +35,36 @@ TEST(DataLoader, LoadCSRMatrixFromFloatNpz) {
     EXPECT_EQ(line.adj_indptr[8], 7u);
 }
 
+// Files scipy.sparse.save_npz wrote (compressed or not, int32 or int64 index arrays): the Python test
+// tests/test_cpp_host.py::test_cpp_npz_reader_on_scipy_files writes them with their expected sums into
+// $GLB_NPZ_CASES/<name>.npz + <name>.txt ("rows cols nnz sum(indices) sum(indptr) sum(data)").
+TEST(DataLoader, ScipyWrittenNpzVariants) {
+    const char *dir = getenv("GLB_NPZ_CASES");
+    if (!dir) return;  // only driven from the Python test
+    for (const char *name : {"compressed_i32", "stored_i32", "compressed_i64", "stored_i64", "empty_rows", "no_nnz"}) {
+        const std::string base = std::string(dir) + "/" + name;
+        FILE *f = fopen((base + ".txt").c_str(), "r");
+        ASSERT_TRUE(f != nullptr);
+        unsigned long rows, cols, nnz;
+        double s_indices, s_indptr, s_data;
+        ASSERT_EQ(fscanf(f, "%lu %lu %lu %lf %lf %lf", &rows, &cols, &nnz, &s_indices, &s_indptr, &s_data), 6);
+        fclose(f);
+        auto m = graphlily::io::load_csr_matrix_from_float_npz(base + ".npz");
+        EXPECT_EQ(m.num_rows, uint32_t(rows));
+        EXPECT_EQ(m.num_cols, uint32_t(cols));
+        EXPECT_EQ(m.adj_data.size(), size_t(nnz));
+        EXPECT_EQ(m.adj_indices.size(), size_t(nnz));
+        EXPECT_EQ(m.adj_indptr.size(), size_t(rows) + 1);
+        double a = 0, b = 0, c = 0;
+        for (auto v : m.adj_indices) a += v;
+        for (auto v : m.adj_indptr) b += v;
+        for (auto v : m.adj_data) c += v;
+        EXPECT_EQ(a, s_indices);
+        EXPECT_EQ(b, s_indptr);
+        EXPECT_TRUE(std::fabs(c - s_data) <= 1e-9 * (1 + std::fabs(s_data)));
+    }
+}
+
 TEST(DataLoader, Csr2Csc) {
     auto csc = graphlily::io::csr2csc(csr_matrix_1());
     std::vector<float> data = {1, 5, 2, 7, 3, 6, 4, 8};

@@ -20,11 +20,11 @@ def _build():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "all"], stdout=subprocess.DEVNULL)
 
 
-def _run(name):
+def _run(name, **extra_env):
     exe = os.path.join(BIN, name)
     if not os.path.exists(exe):
         _build()
-    env = dict(os.environ, GLB_TEST_DATA=os.path.join(ROOT, "tests", "golden"))
+    env = dict(os.environ, GLB_TEST_DATA=os.path.join(ROOT, "tests", "golden"), **extra_env)
     p = subprocess.run([exe], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, f"{name} failed:\n{p.stdout[-4000:]}\n{p.stderr[-2000:]}"
     assert "0 test(s) failed" in p.stdout
@@ -35,6 +35,41 @@ def test_cpp_io_layer():
     _build()   # the C++ host mirror must compile against the public headers
     out = _run("test_io")
     assert out.count("[  OK  ]") >= 7
+
+
+def test_cpp_npz_reader_on_scipy_files(tmp_path):
+    """the real datasets are scipy.sparse.save_npz files (compressed, int32 index
+    arrays -- int64 for huge matrices -- and an int64 shape).  The in-repo C++ reader (io/npz.h over
+    zlib, replacing cnpy) and the Python loader read every variant scipy writes."""
+    import numpy as np
+    import scipy.sparse as sp
+    import sys
+    sys.path.insert(0, ROOT)
+    from graphlily_b200 import io
+    _build()
+    rng = np.random.default_rng(3)
+    base = sp.random(300, 200, density=0.05, format="csr", dtype=np.float32, random_state=5)
+    base.sort_indices()
+    holes = base.copy().tolil()
+    holes[10:40] = 0
+    holes = holes.tocsr().astype(np.float32)
+    cases = {"compressed_i32": (base, True, np.int32), "stored_i32": (base, False, np.int32),
+             "compressed_i64": (base, True, np.int64), "stored_i64": (base, False, np.int64),
+             "empty_rows": (holes, True, np.int32), "no_nnz": (sp.csr_matrix((7, 9), dtype=np.float32), True, np.int32)}
+    for name, (m, compressed, idt) in cases.items():
+        m = m.copy()
+        m.indices, m.indptr = m.indices.astype(idt), m.indptr.astype(idt)
+        path = str(tmp_path / f"{name}.npz")
+        sp.save_npz(path, m, compressed=compressed)
+        with open(tmp_path / f"{name}.txt", "w") as f:
+            f.write(f"{m.shape[0]} {m.shape[1]} {m.nnz} {float(m.indices.astype(np.float64).sum())!r} "
+                    f"{float(m.indptr.astype(np.float64).sum())!r} {float(m.data.astype(np.float64).sum())!r}\n")
+        r = io.load_csr_matrix_from_float_npz(path)          # the Python loader reads the same files
+        assert (r.num_rows, r.num_cols, r.nnz) == (m.shape[0], m.shape[1], m.nnz)
+        assert r.indices.tolist() == m.indices.tolist() and r.indptr.tolist() == m.indptr.tolist()
+        assert r.data.tobytes() == m.data.astype(np.float32).tobytes()
+    out = _run("test_io", GLB_NPZ_CASES=str(tmp_path))
+    assert "[  OK  ] DataLoader.ScipyWrittenNpzVariants" in out
 
 
 @pytest.mark.gpu
