@@ -443,3 +443,19 @@ def test_host_batch_matches_single_calls(ctx, oracle):
                 A.spmv_host(capi.OP_MUL_ADD, 0.0, mt, xs[k], ms[k] if mt else None, single)
                 assert single.tobytes() == ys[k].tobytes()      # same kernels, same order: bit-identical
     A.close()
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmv_tma_tile_variant(ctx, oracle, op, zero, monkeypatch):
+    # the optional persistent kernel that keeps the hot vector in shared memory (TMA bulk load +
+    # mbarrier, GLB_SPMV_TILE_THREADS): same results as the default path, masked and not
+    monkeypatch.setenv("GLB_SPMV_TILE_THREADS", "512")
+    monkeypatch.setenv("GLB_SPMV_TILE_K", "8192")
+    rng = np.random.default_rng(95 + op)
+    m = datasets.powerlaw_csr(20_000, 60_000, 600_000, seed=29, max_degree=30_000)
+    if op == 2:
+        m.data = rng.integers(0, 3, m.nnz).astype(np.float32)
+    x = (rng.integers(0, 3, m.num_cols) * (0.5 + rng.random(m.num_cols))).astype(np.float32)
+    mask = (rng.random(m.num_rows) < 0.3).astype(np.float32)
+    for mt in MASKS:
+        check_vec(gpu_spmv(ctx, m, op, zero, mt, x, mask), oracle.port.spmv(m, op, zero, mt, x, mask), op)
