@@ -42,9 +42,33 @@ __global__ void __launch_bounds__(kThreads) ewise_add_kernel(const float *in, fl
 __global__ void __launch_bounds__(kThreads) assign_dense_kernel(const float *mask, float *inout, uint32_t len, float val,
                                                               int write_to_one) {
     const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
+    const bool want = write_to_one != 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(inout)) & 15u) == 0;
+    uint32_t done = 0;
+    if (aligned) {  // 128-bit mask loads; a group of four that is assigned entirely goes out as one 128-bit store
+        const uint32_t n4 = len >> 2;
+        const float4 *m4 = reinterpret_cast<const float4 *>(mask);
+        float4 *io4 = reinterpret_cast<float4 *>(inout);
+        for (uint32_t i = tid; i < n4; i += stride) {
+            const float4 m = m4[i];
+            const bool h0 = (m.x != 0.0f) == want, h1 = (m.y != 0.0f) == want, h2 = (m.z != 0.0f) == want,
+                       h3 = (m.w != 0.0f) == want;
+            if (h0 & h1 & h2 & h3) {
+                io4[i] = make_float4(val, val, val, val);
+            } else {
+                float *p = inout + 4 * size_t(i);
+                if (h0) p[0] = val;
+                if (h1) p[1] = val;
+                if (h2) p[2] = val;
+                if (h3) p[3] = val;
+            }
+        }
+        done = n4 << 2;
+    }
+    for (uint32_t i = done + tid; i < len; i += stride) {
         const bool nz = mask[i] != 0.0f;
-        if (nz == (write_to_one != 0)) inout[i] = val;
+        if (nz == want) inout[i] = val;
     }
 }
 
@@ -108,7 +132,7 @@ int glb_assign_dense(glb_ctx_t ctx, const float *mask, float *inout, uint32_t le
     GLB_REQUIRE(mask_type == GLB_MASK_WRITE_TO_ZERO || mask_type == GLB_MASK_WRITE_TO_ONE,
                 "dense assign needs kMaskWriteToZero or kMaskWriteToOne");
     if (len == 0) return GLB_OK;
-    assign_dense_kernel<<<grid_for(ctx, len, 8), kThreads, 0, ctx->stream>>>(mask, inout, len, val,
+    assign_dense_kernel<<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(mask, inout, len, val,
                                                                              mask_type == GLB_MASK_WRITE_TO_ONE);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;

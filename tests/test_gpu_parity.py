@@ -459,3 +459,30 @@ def test_spmv_tma_tile_variant(ctx, oracle, op, zero, monkeypatch):
     mask = (rng.random(m.num_rows) < 0.3).astype(np.float32)
     for mt in MASKS:
         check_vec(gpu_spmv(ctx, m, op, zero, mt, x, mask), oracle.port.spmv(m, op, zero, mt, x, mask), op)
+
+
+def test_assign_dense_vector_path_and_tails(ctx, oracle):
+    # the dense assign reads the mask in 128-bit words and stores a fully assigned group of four as one
+    # 128-bit word: odd lengths, all-hit / no-hit / mixed groups, unaligned views, mask aliasing inout
+    rng = np.random.default_rng(97)
+    for n in (1, 2, 5, 127, 128, 1001, 65536 + 3):
+        for density in (0.0, 0.5, 1.0):
+            mask = (rng.random(n) < density).astype(np.float32) * np.float32(-2.0)
+            inout = rng.random(n).astype(np.float32)
+            for mt in (capi.MASK_WRITE_TO_ZERO, capi.MASK_WRITE_TO_ONE):
+                dm, dio = ctx.to_device(mask), ctx.to_device(inout)
+                capi.assign_dense(ctx, dm, dio, n, 23.0, mt)
+                ref = inout.copy()
+                ref[(mask == 0) if mt == capi.MASK_WRITE_TO_ZERO else (mask != 0)] = 23.0
+                assert dio.read(np.float32, n).tobytes() == ref.tobytes(), (n, density, mt)
+    n = 4099
+    mask, inout = (rng.random(n + 1) < 0.5).astype(np.float32), rng.random(n + 1).astype(np.float32)
+    dm, dio = ctx.to_device(mask), ctx.to_device(inout)
+    capi.assign_dense(ctx, dm.ptr + 4, dio.ptr + 4, n, 7.0, capi.MASK_WRITE_TO_ONE)     # 4-byte-aligned views
+    ref = inout.copy()
+    ref[1:][mask[1:] != 0] = 7.0
+    assert dio.read(np.float32, n + 1).tobytes() == ref.tobytes()
+    v = (rng.random(1000) < 0.5).astype(np.float32)
+    d = ctx.to_device(v)
+    capi.assign_dense(ctx, d, d, 1000, 9.0, capi.MASK_WRITE_TO_ZERO)                   # mask is inout
+    assert d.read(np.float32, 1000).tobytes() == np.where(v == 0, np.float32(9.0), v).tobytes()
