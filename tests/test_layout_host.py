@@ -110,3 +110,19 @@ def test_invalid_inputs_rejected():
     bad2 = io.CSRMatrix(4, 4, m.data, m.indices, np.array([0, 2, 1, 3, 4], np.uint32))
     with pytest.raises(capi.GlbError):
         capi.format_host(bad2)
+
+
+def test_formatter_fuzz_row_lengths_shards_and_hot_sets(oracle):
+    """Randomised: row lengths drawn around the lane / group / chunk sizes (31..33, 127..129,
+    1023..1025, 3000), random shards and hot-set sizes from 0 to 'every column'.  (The same loop ran
+    clean under AddressSanitizer with the library built -fsanitize=address.)"""
+    rng = np.random.default_rng(123)
+    for trial in range(25):
+        rows, cols = int(rng.integers(1, 1500)), int(rng.integers(1, 4000))
+        degs = np.minimum(rng.choice([0, 0, 1, 2, 5, 31, 32, 33, 127, 128, 129, 1023, 1024, 1025, 3000], rows), cols)
+        ip = np.concatenate([[0], np.cumsum(degs)]).astype(np.uint32)
+        ix = np.concatenate([np.sort(rng.choice(cols, d, replace=False)) for d in degs] + [np.zeros(0, np.int64)])
+        m = io.CSRMatrix(rows, cols, rng.integers(1, 3, len(ix)).astype(np.float32), ix.astype(np.uint32), ip)
+        rb = int(rng.integers(0, rows))
+        re = int(rng.integers(rb, rows + 1))
+        check(oracle, m, rb, re, seed=trial, tile_k=int(rng.choice([0, 1, 7, 64, 4096, 10**6])))
