@@ -486,3 +486,26 @@ def test_assign_dense_vector_path_and_tails(ctx, oracle):
     d = ctx.to_device(v)
     capi.assign_dense(ctx, d, d, 1000, 9.0, capi.MASK_WRITE_TO_ZERO)                   # mask is inout
     assert d.read(np.float32, 1000).tobytes() == np.where(v == 0, np.float32(9.0), v).tobytes()
+
+
+@pytest.mark.parametrize("op,zero", SEMIRINGS)
+def test_spmspv_conflict_matrix_and_dense_1k(ctx, oracle, op, zero):
+    # the reference's "bank conflict" case (tests/test_module_spmv_spmspv.cpp:268-284: 1024 columns of 128
+    # non-zeros, column i holding rows j * 8 + i % 8 -- every eighth column hits the same rows, i.e.
+    # maximal contention on the accumulator) at sparsity 0, and dense_1K at sparsity 0 / 0.5 / 0.99
+    n = 1024
+    ip = (np.arange(n + 1) * (n // 8)).astype(np.uint32)
+    ix = np.concatenate([np.arange(n // 8) * 8 + i % 8 for i in range(n)]).astype(np.uint32)
+    conflict = CSRMatrix(n, n, np.full(len(ix), 1.0 / n, np.float32), ix, ip)
+    dense = CSRMatrix(n, n, np.full(n * n, 1.0 / n, np.float32), np.tile(np.arange(n, dtype=np.uint32), n),
+                      (np.arange(n + 1) * n).astype(np.uint32))
+    rng = np.random.default_rng(99 + op)
+    mask = np.where(rng.random(n) < 0.5, np.float32(zero), np.float32(1)).astype(np.float32)
+    for csc, sparsities in ((conflict, (0.0,)), (dense, (0.0, 0.5, 0.99))):
+        for sparsity in sparsities:
+            k = max(1, int(n * (1 - sparsity)))
+            idx = (np.arange(k) * (n // k)).astype(np.uint32)
+            val = (rng.integers(0, 10, k) / 10).astype(np.float32)
+            for mt in MASKS:
+                y = gpu_spmspv(ctx, csc, op, zero, mt, idx, val, mask, runs=2)
+                check_vec(y, oracle.port.spmspv(csc, op, zero, mt, idx, val, mask), op)
