@@ -1,25 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- SpMV GTEPS on the BASELINE.json configs[1] workload (bench_spmv).
+"""bench.py -- SpMV GTEPS on the BASELINE.json configs[1] workload (bench_spmv), plus one record per
+app (bench_bfs / bench_pagerank / bench_sssp on the C3 / C4 / C5 shapes) in the same JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-apps]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Workload: synthetic power-law CSR, 4 194 304 x 4 194 304, 134 217 728 nnz
-(32 / row), fp32 plus-times, A[:] = 1/N, x in {0, 1} -- the shape of the reference's
-benchmark/bench_spmv.cpp:37-113 (GTEPS = nnz / seconds / 1e9, :106-112).
+(32 / row), fp32 plus-times -- the shape of the reference's benchmark/bench_spmv.cpp:37-113
+(GTEPS = nnz / seconds / 1e9, :106-112).  Values are row-stochastic (A[r, c] = 1 / nnz(r)) and the
+first x is random in {0, 1}: the steps iterate x <- A x as the apps do, and with these values the
+iterates neither vanish nor overflow, so the LAST timed step can be checked (round 1 used A = 1/N,
+whose iterates underflow to exactly 0 after nine steps).
 
-One step = one SpMV over the whole matrix.  With N > 1 the CSR is row-range sharded (equal
-row counts), every rank computes its slice of y straight into the gather buffer and one NCCL
-allgather per step makes it the next x (strong scaling: total work fixed).
+One step = one SpMV over the whole matrix.  With N > 1 the CSR is row-range sharded (cuts balanced
+by nnz), every rank computes its slice of y and the slices meet on every rank before the next step
+(NVSwitch multicast / peer stores / one NCCL allgather): strong scaling, total work fixed.  The K
+timed steps are ONE recorded launch sequence (CUDA graph) per rank, replayed once.
 
 Reported on one JSON line by rank 0:
   value        device-timed GTEPS, inputs resident in HBM (matrix 1.07 GB >> 126 MB L2, so every
                step streams it from HBM; the 16 MB x is meant to live in L2)
-  e2e          GTEPS through glb_spmv_host with pinned HOST x / y: H2D x, kernels, D2H y per step
+  parity       the last timed step checked on EVERY rank: rows of the rank's shard against the
+               reference's compute_reference_results, the checksum identity sum(y) = sum(colsum * x) over
+               the whole exchanged vector, bit-identical vectors across ranks; rc 3 on mismatch
+  e2e          GTEPS through glb_spmv_host_batch with pinned HOST x / y: H2D x, kernels, D2H y per step
   roofline     spmv_lane_kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline the reference's own compute_reference_results (oracle/_ref) on one host thread,
                on a bounded row sample of the same matrix (N = 1 only)
-`--impl reference` runs only that CPU path (the reference has no threading: 1 thread).
+  bfs / pagerank / sssp   tests/bench_apps.run_app records (levels/s, GTEPS, parity vs the reference)
+`--impl reference` runs only the CPU path (the reference has no threading: 1 thread).
 """
 import argparse
 import json
@@ -27,6 +36,7 @@ import os
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -98,18 +108,21 @@ def make_matrix(device):
     from graphlily_b200 import datasets
     t0 = time.time()
     m = datasets.powerlaw_csr(ROWS, ROWS, NNZ, seed=SEED, device=device)
+    deg = np.diff(m.indptr.astype(np.int64))
+    m.data = np.repeat((1.0 / np.maximum(deg, 1)).astype(np.float32), deg)     # row-stochastic
     log(f"generated power-law CSR {m.num_rows} x {m.num_cols}, nnz {m.nnz} on {device} in {time.time() - t0:.1f}s")
     return m
 
 
-def row_sample(m, rows):
+def row_sample(m, begin, rows):
     from graphlily_b200.io import CSRMatrix
-    end = int(m.indptr[rows])
-    return CSRMatrix(rows, m.num_cols, m.data[:end], m.indices[:end], m.indptr[:rows + 1].copy())
+    ip = m.indptr.astype(np.int64)
+    s, e = int(ip[begin]), int(ip[begin + rows])
+    return CSRMatrix(rows, m.num_cols, m.data[s:e], m.indices[s:e], (ip[begin:begin + rows + 1] - s).astype(np.uint32))
 
 
 def cpu_reference_backend():
-    import oracle  # the ONLY use of oracle/ here: as the timed CPU baseline / reference arm
+    import oracle  # the ONLY use of oracle/ here: as the timed CPU baseline / reference arm and as the parity checker
     if oracle.ref is not None:
         return oracle.ref, "reference"
     return oracle.port, "port"
@@ -117,7 +130,7 @@ def cpu_reference_backend():
 
 def workload_config(n_gpus):
     return {"workload": "bench_spmv: synthetic power-law CSR 4194304 x 4194304, 134217728 nnz (32/row), "
-                        "fp32 plus-times SpMV, A=1/N, x in {0,1}",
+                        "fp32 plus-times SpMV, row-stochastic values A[r,c] = 1/nnz(r), x0 in {0,1}, steps iterate x <- A x",
             "generator": f"graphlily_b200.datasets.powerlaw_csr(seed={SEED}): Pareto(2.1) row degrees 1..2^20, "
                          "Zipf(0.9) column popularity, random column labels",
             "rows": ROWS, "nnz": NNZ, "semiring": "plus-times",
@@ -134,15 +147,14 @@ def run_reference(args, rank):
     backend, kind = cpu_reference_backend()
     m = make_matrix("cuda" if torch.cuda.is_available() else "cpu")
     x = np.random.default_rng(SEED).integers(0, 2, m.num_cols).astype(np.float32)
-    probe = row_sample(m, min(65536, m.num_rows))
+    probe = row_sample(m, 0, min(65536, m.num_rows))
     t_probe, _ = backend.spmv_timed(probe, 0, 0.0, x, reps=2)
     per_nnz = t_probe / max(probe.nnz, 1)
     budget = 60.0 / max(args.steps + args.warmup, 1)               # seconds per step
-    rows = 65536
-    rows = min(rows, m.num_rows)
+    rows = min(65536, m.num_rows)
     while rows * 2 <= min(1_048_576, m.num_rows) and per_nnz * int(m.indptr[rows * 2]) * 2.0 < budget:
         rows *= 2
-    s = row_sample(m, rows)
+    s = row_sample(m, 0, rows)
     for _ in range(args.warmup):
         backend.spmv_timed(s, 0, 0.0, x, reps=1)
     # each step times one compute_reference_results(vector) call (spmv_module.h:488-510); building the
@@ -166,7 +178,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-apps", action="store_true", help="skip the BFS / PageRank / SSSP records")
+    ap.add_argument("--app-reps", type=int, default=5)
     ap.add_argument("--rows", type=int, default=ROWS, help=argparse.SUPPRESS)   # debugging only
+    ap.add_argument("--app-scale", type=float, default=1.0, help=argparse.SUPPRESS)   # debugging only
     args = ap.parse_args()
     if args.rows != ROWS:   # scaled-down debugging run, never a bench line of record
         globals().update(ROWS=args.rows, NNZ=args.rows * 32)
@@ -207,12 +222,12 @@ def main():
     #   "multicast" (default) symmetric-memory blocks with a multicast mapping: the finished slice is
     #           sent once with multimem.st, the NVSwitch replicates it to every rank
     #   "peer"  CUDA-IPC blocks: the SpMV write-back stores every row into all ranks' copies of the
-    #           vector over NVLink (glb_spmv_exchange); a signal / wait kernel follows
+    #           vector over NVLink; a 32-thread kernel publishes the epoch
     #   "nccl"  one in-place ncclAllGather after the kernels
     # (GLB_EXCHANGE selects; each falls back to the next when the system lacks it)
     from graphlily_b200.exchange import open_exchange
     xc, exchange = open_exchange(ctx, n, rank, world, n_vectors=2, device=dev, log=log)
-    if exchange == "nccl":
+    if world > 1 and (exchange == "nccl" or os.environ.get("GLB_EXCHANGE") == "nccl"):
         uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
@@ -242,22 +257,25 @@ def main():
         def load(self, host):
             capi.check(capi.lib.glb_buffer_h2d(ctx.handle, self.ptr(), host.ctypes.data, host.nbytes))
 
-    xa, xb = Vec(0), Vec(1)
-    xa.load(x_host)
+        def read(self):
+            out = np.empty(n, np.float32)
+            capi.check(capi.lib.glb_buffer_d2h(ctx.handle, out.ctypes.data, self.ptr(), out.nbytes))
+            return out
 
-    def step(src, dst):
+    vecs = [Vec(0), Vec(1)]
+
+    def enqueue_steps(k, first):
+        """k steps x <- A x starting from vecs[first]; returns the index of the vector written last."""
         if xc is not None:
-            xc.spmv(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.which, dst.which)
+            xc.spmv_iterate(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, first, 1 - first, k)
         else:
-            A.spmv(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, src.ptr(), None, dst.ptr())
-            if world > 1:
-                ctx.allgather_f32(dst.ptr(), slot)
-
-    def run_steps(k, src, dst):
-        for _ in range(k):
-            step(src, dst)
-            src, dst = dst, src
-        return src, dst
+            s = first
+            for _ in range(k):
+                A.spmv(capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, vecs[s].ptr(), None, vecs[1 - s].ptr())
+                if world > 1:
+                    ctx.allgather_f32(vecs[1 - s].ptr(), slot)
+                s = 1 - s
+        return first if k % 2 == 0 else 1 - first
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,28 +291,86 @@ def main():
         return float(t.item())
 
     sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # ---- device-resident timing ------------------------------------------------------------
-    src, dst = run_steps(args.warmup, xa, xb)
+    vecs[0].load(x_host)
+    barrier()
+    cur = enqueue_steps(args.warmup, 0)                    # W warm-up steps, launch by launch
+    recordable = world == 1 or xc is not None               # (the NCCL allgather is issued launch by launch)
+    # The recorded sequence starts from vecs[cur] whenever it is replayed; with an odd K a replay leaves the
+    # newest iterate in the other vector and the next replay restarts from the one before it -- still a
+    # proper iterate of x <- A x, so nothing needs re-aligning between replays.
+    graph = ctx.record(lambda: enqueue_steps(args.steps, cur)) if recordable else None
+    if graph is not None:
+        graph.launch()                                      # first replay (uploads the sequence): K more warm-up steps
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    src, dst = run_steps(args.steps, src, dst)
+    if graph is not None:
+        graph.launch()
+        last = cur if args.steps % 2 == 0 else 1 - cur
+    else:
+        last = enqueue_steps(args.steps, cur)
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     gteps = m.nnz / (ms_step * 1e-3) / 1e9
+    # the last timed step read vecs[1 - last] and wrote vecs[last]; both are complete on every rank
+    x_in, y_out = vecs[1 - last].read(), vecs[last].read()
+    # launch by launch from the host, for comparison (the same K steps, not recorded)
+    barrier()
+    e0.record(stream)
+    enqueue_steps(args.steps, last)
+    e1.record(stream)
+    barrier()
+    ms_step_host_launched = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # ---- parity of the LAST step, on every rank --------------------------------------------
+    backend, kind = cpu_reference_backend()
+    rows_c = min(262_144, re - rb)
+    s = row_sample(m, rb, rows_c)
+    y_ref = backend.spmv(s, 0, 0.0, 0, x_in)
+    got = y_out[rb:rb + rows_c]
+    err = np.abs(got - y_ref) / np.maximum(np.abs(y_ref), 1e-30)
+    rows_ok = bool(((err <= 1e-5) | (np.abs(got - y_ref) < 1e-12)).all())
+    colsum = np.bincount(m.indices, weights=m.data.astype(np.float64), minlength=n)
+    lhs, rhs = float(y_out.astype(np.float64).sum()), float(colsum @ x_in.astype(np.float64))
+    checksum_rel = abs(lhs - rhs) / max(abs(rhs), 1e-300)
+    del colsum
+    sig = (zlib.crc32(x_in.tobytes()), zlib.crc32(y_out.tobytes()))
+    sigs = [sig]
+    if world > 1:
+        sigs = [None] * world
+        dist.all_gather_object(sigs, sig)
+    mine = {"rows_ok": rows_ok, "max_rel_err": float(err.max()), "checksum_rel_err": checksum_rel,
+            "nonzero_outputs": int((y_out != 0).sum())}
+    alls = [mine]
+    if world > 1:
+        alls = [None] * world
+        dist.all_gather_object(alls, mine)
+    parity = {"ok": bool(all(a["rows_ok"] and a["checksum_rel_err"] <= 1e-5 and a["nonzero_outputs"] > n // 2 for a in alls)
+                         and all(sg == sigs[0] for sg in sigs)),
+              "checked": f"output of the last step: on every rank, rows [row_begin, row_begin + {rows_c}) of its shard vs "
+                         f"compute_reference_results ({kind}) at 1e-5 relative; sum(y) = sum(colsum * x) over the whole "
+                         "vector in float64 (covers every rank's exchanged slice); vectors bit-identical across ranks",
+              "rows_checked_per_rank": rows_c, "max_rel_err_vs_reference": max(a["max_rel_err"] for a in alls),
+              "checksum_rel_err_max": max(a["checksum_rel_err"] for a in alls),
+              "nonzero_outputs_min": min(a["nonzero_outputs"] for a in alls),
+              "ranks_agree_bitwise": bool(all(sg == sigs[0] for sg in sigs))}
+    if not parity["ok"]:
+        log(f"rank {rank}: PARITY FAILURE {parity} {alls}")
 
     # ---- dominant kernel alone (events inside the C ABI, same stream) --------------------------
     barrier()
-    xa.load(x_host)
+    vecs[0].load(x_host)
     barrier()
     ctx.kernel_timing(True)
-    run_steps(args.steps, xa, xb)
+    enqueue_steps(args.steps, 0)
     ms_main, ms_fix, launches = ctx.kernel_timing_read()
     ctx.kernel_timing(False)
     ms_kernel = ms_main / max(launches, 1)
+    ms_fixup = ms_fix / max(launches, 1)
     rows_s = re - rb
     alg_bytes = 8 * info["nnz"] + 4 * (rows_s + 1) + 4 * m.num_cols + 4 * rows_s
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
@@ -310,8 +386,13 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": "spmv_lane_kernel<plus-times>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fix / max(launches, 1)}
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if world == 1 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fixup}
+    ms_kernels_max = max_over_ranks(ms_kernel + ms_fixup)
+    step_breakdown = {"main_plus_fixup_ms_max_over_ranks": ms_kernels_max,
+                      "other_ms": ms_step - ms_kernels_max,
+                      "other_is": "hot-column pack + launch gaps" + ("" if world == 1 else " + slice exchange (push / signal) + acquire + rank skew"),
+                      "host_launched_ms_per_step": ms_step_host_launched}
 
     # ---- end to end through the host-buffer entry points --------------------------------------
     # Every step uploads that step's x from pinned host memory and reads its y slice back into pinned
@@ -321,7 +402,7 @@ def main():
     ring = 4
     rng = np.random.default_rng(SEED + 1)
     xhs = [torch.from_numpy(x_host).pin_memory()] + \
-          [torch.from_numpy(rng.integers(0, 2, n).astype(np.float32)).pin_memory() for _ in range(ring - 1)]
+          [torch.from_numpy(rng.random(n).astype(np.float32)).pin_memory() for _ in range(ring - 1)]
     yhs = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(ring)]
     e2e_steps = max(12, min(args.steps, 48)) // ring * ring
     xs = [xhs[i % ring].data_ptr() for i in range(e2e_steps)]
@@ -347,6 +428,7 @@ def main():
     y_sync = [y[rb:re].clone() for y in yhs]
     for y in yhs:
         y.zero_()
+
     def batch_call(xv, yv):
         if xc is not None:   # sharded: every rank uploads its 1/N slice of x, NVLink completes it
             xc.spmv_host_batch(A, capi.OP_MUL_ADD, 0.0, capi.MASK_NONE, xv, None, yv)
@@ -356,15 +438,26 @@ def main():
     batch_call(xs[:ring], ys[:ring])
     batch_ms = timed_host(lambda: batch_call(xs, ys))
     batch_same = all(bool(torch.equal(yhs[i][rb:re], y_sync[i])) for i in range(ring))
-    if not batch_same:
-        log("WARNING: glb_spmv_host_batch results differ from glb_spmv_host")
-    yh = yhs[0]
+    # the e2e results against the reference, on the same row sample of every rank's shard
+    e2e_ok = True
+    for i in (0, ring - 1):
+        ref_i = backend.spmv(s, 0, 0.0, 0, xhs[i].numpy())
+        got_i = yhs[i][rb:rb + rows_c].numpy()
+        e_i = np.abs(got_i - ref_i) / np.maximum(np.abs(ref_i), 1e-30)
+        e2e_ok = e2e_ok and bool(((e_i <= 1e-5) | (np.abs(got_i - ref_i) < 1e-12)).all())
+    e2e_flags = [(batch_same, e2e_ok)]
+    if world > 1:
+        e2e_flags = [None] * world
+        dist.all_gather_object(e2e_flags, (batch_same, e2e_ok))
+    batch_same, e2e_ok = all(f[0] for f in e2e_flags), all(f[1] for f in e2e_flags)
+    parity["e2e_matches_reference_on_sample"] = e2e_ok
+    parity["ok"] = bool(parity["ok"] and e2e_ok and batch_same)
     sliced = xc is not None
     e2e = {"value": m.nnz / (batch_ms * 1e-3) / 1e9, "unit": "GTEPS",
            "h2d_bytes_per_step": 4 * n if sliced or world == 1 else 4 * n * world,     # whole job, all ranks
            "d2h_bytes_per_step": 4 * n, "ms_per_step": batch_ms, "steps": e2e_steps,
            "api": (f"glb_spmv_host_batch_exchange: {e2e_steps} vectors from a ring of {ring} pinned host x buffers; every rank "
-                   "uploads its 1/N slice of x, the slices meet over NVLink (peer copies), SpMV, y slice -> pinned host; "
+                   "uploads its 1/N slice of x, the slices meet over NVLink, SpMV, y slice -> pinned host; "
                    "upload / kernels / download of consecutive vectors overlap" if sliced else
                    f"glb_spmv_host_batch: {e2e_steps} vectors from a ring of {ring} pinned host x buffers -> device, SpMV, "
                    "y slice -> pinned host y buffers; upload / kernels / download of consecutive vectors overlap"),
@@ -372,45 +465,67 @@ def main():
            "single_call": {"value": m.nnz / (sync_ms * 1e-3) / 1e9, "ms_per_step": sync_ms,
                            "api": "glb_spmv_host per vector (returns when y has landed; no overlap between vectors)"}}
     clocks = sampler.stop()
-    checksum = float(yh[rb:re].double().sum())
 
     # ---- CPU baseline beside it (rank 0, N = 1) ----------------------------------------------
     cpu = None
     if world == 1:
-        backend, kind = cpu_reference_backend()
-        rows_c = min(1_048_576, m.num_rows)
-        s = row_sample(m, rows_c)
-        sec, y_ref = backend.spmv_timed(s, 0, 0.0, x_host, reps=3)
-        got = yh[:rows_c].numpy()
-        err = np.abs(got - y_ref) / np.maximum(np.abs(y_ref), 1e-30)
-        ok = bool(((err <= 1e-5) | (np.abs(got - y_ref) < 1e-12)).all())
-        cpu = {"value": s.nnz / sec / 1e9, "unit": "GTEPS", "cores": 1, "kind": kind,
-               "sample": f"rows [0, {rows_c}) of the same matrix ({s.nnz} nnz), best of 3, 1 thread "
+        rows_b = min(1_048_576, m.num_rows)
+        sb = row_sample(m, 0, rows_b)
+        sec, _ = backend.spmv_timed(sb, 0, 0.0, x_host, reps=3)
+        cpu = {"value": sb.nnz / sec / 1e9, "unit": "GTEPS", "cores": 1, "kind": kind,
+               "sample": f"rows [0, {rows_b}) of the same matrix ({sb.nnz} nnz), best of 3, 1 thread "
                          "(the reference has no threading)",
-               "host_cpus": os.cpu_count(), "gpu_result_matches_on_sample_1e-5_rel": ok}
-        if not ok:
-            log("WARNING: GPU result differs from the CPU reference on the sample")
+               "host_cpus": os.cpu_count()}
 
-    # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup
-    launches_per_step = 2 + (1 if 0 < info["tile_k"] < m.num_cols else 0) + (0 if xc is None else 2 if (exchange == "multicast" and world >= 4) else 1)
+    # kernels of ours per step: gather_hot (when hot columns are packed), spmv_lane, spmv_fixup, + the exchange's
+    # push / signal kernel; one acquire kernel closes the recorded sequence
+    hot = 1 if 0 < info["tile_k"] < m.num_cols else 0
+    launches_per_step = 2 + hot + (0 if xc is None else 1)
+    gpu_launches = launches_per_step * args.steps + (1 if xc is not None else 0)
+
+    # ---- release the C2 matrix, then the app records ----------------------------------------
+    A.close()
+    del A, m, vecs, xhs, yhs, y_sync
+    torch.cuda.empty_cache()
+    apps = {}
+    if not args.no_apps:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import bench_apps
+        env = bench_apps.Env(ctx, stream, dev, rank, world, log)
+        for name in bench_apps.APPS:
+            try:
+                apps[name] = bench_apps.run_app(name, env, scale=args.app_scale, reps=args.app_reps, check=True,
+                                                hbm_peak_gbs=peak)
+            except Exception as exc:  # noqa: BLE001 -- an app failure must not lose the SpMV line
+                log(f"app {name} failed: {type(exc).__name__}: {exc}")
+                apps[name] = {"app": name, "error": f"{type(exc).__name__}: {exc}", "parity": {"ok": False}}
+            if rank == 0 and apps[name].get("parity") and not apps[name]["parity"]["ok"]:
+                parity["ok"] = False
+
     if rank == 0:
         cfg = workload_config(world)
         if world > 1:
-            mc_kernel = {"kernel": True, "fused": False}.get(os.environ.get("GLB_XCHG_MC", ""), world >= 4)
-            cfg["exchange"] = {"multicast": ("each rank's finished y slice sent once by a kernel of 16-byte multimem.st stores" if mc_kernel
-                                             else "each y row stored once to the multicast address by the SpMV write-back (multimem.st)") +
-                                            ", replicated to all ranks by the NVSwitch multicast + signal/wait kernel",
-                               "peer": "y rows stored into every rank's vector by the SpMV write-back over NVLink "
-                                       "(peer-mapped memory) + signal/wait kernel",
+            cfg["exchange"] = {"multicast": "each rank's finished y slice sent once by a kernel of 16-byte multimem.st stores whose last CTA "
+                                            "publishes the epoch; replicated to all ranks by the NVSwitch; the acquire sits at the head of "
+                                            "the next step's first kernel",
+                               "peer": "y rows stored into every rank's vector by the SpMV write-back over NVLink (peer-mapped memory), "
+                                       "a 32-thread kernel publishes the epoch, acquire at the head of the next step's first kernel",
                                "nccl": "one in-place ncclAllGather of y per step"}[exchange]
+        cfg["timed_region"] = ("one recorded launch sequence (CUDA graph) of K steps, replayed once" if graph is not None
+                               else "K steps launched one by one")
         line = {"metric": "spmv_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-                "cpu_baseline": cpu, "y_checksum": checksum, "nnz": m.nnz}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                "step_breakdown": step_breakdown, "parity": parity, "cpu_baseline": cpu, "nnz": NNZ}
+        line.update(apps)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    ctx.close()
+    if not parity["ok"]:
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

@@ -70,10 +70,31 @@ class ModuleCollection:
         assert 0 <= rank < world
         self.rank_, self.world_, self.exchange_ = rank, world, exchange
 
+    def _cuts(self, n):
+        """Row cuts of the ranks.  Over an exchange the slices need not be equal, so they are cut where
+        the nnz prefix of the CSR crosses r / world (32-row aligned): every rank streams the same
+        share of the matrix.  The NCCL allgather needs equal slots."""
+        cuts = self.__dict__.get("cuts_")
+        if cuts is not None and cuts[-1] == n and len(cuts) == self.world_ + 1:
+            return cuts
+        w = self.world_
+        if w == 1:
+            cuts = [0, n]
+        elif self.exchange_ is None:
+            assert n % w == 0, "padded dimension must divide by the number of ranks"
+            cuts = [r * (n // w) for r in range(w + 1)]
+        else:
+            ip = np.asarray(self.csr_matrix_.indptr, dtype=np.int64)
+            cuts = [int(np.searchsorted(ip, ip[-1] * r // w)) // 32 * 32 for r in range(w + 1)]
+            cuts[0], cuts[-1] = 0, n
+            for r in range(1, w + 1):
+                cuts[r] = max(cuts[r], cuts[r - 1])
+        self.cuts_ = cuts
+        return cuts
+
     def _row_range(self, n):
-        assert n % self.world_ == 0, "padded dimension must divide by the number of ranks"
-        slot = n // self.world_
-        return self.rank_ * slot, (self.rank_ + 1) * slot
+        cuts = self._cuts(n)
+        return cuts[self.rank_], cuts[self.rank_ + 1]
 
     def _bind_exchange(self):
         """After the matrix upload: vector / results / mask of the SpMV module become exchange vectors."""
@@ -89,6 +110,7 @@ class ModuleCollection:
     def _matrix_changed(self):
         """A new matrix went to the device: recorded launch sequences of the old one are void."""
         self.__dict__.pop("graphs_", None)
+        self.__dict__.pop("cuts_", None)
 
     def _begin_run(self):
         """No rank starts writing into the peers' vectors before every rank has finished reading the
@@ -106,32 +128,43 @@ class ModuleCollection:
         if self.world_ == 1:
             return
         if self.exchange_ is not None:
-            slot = n // self.world_
-            self.exchange_.allgather(buf.tag[1], self.rank_ * slot, slot)
+            rb, re = self._row_range(n)
+            self.exchange_.allgather(buf.tag[1], rb, re - rb)
         else:
             self.ctx.allgather_f32(buf, n // self.world_)
 
     def _push_begin(self):
-        """Row-sharded push: the dense vector the frontier travels in is the SpMV module's vector."""
+        """Row-sharded push: the dense vectors the frontier travels in are the SpMV module's vector and
+        results buffers (both idle while the push direction runs)."""
         if self.world_ > 1:
             n = self.matrix_num_rows_
             self.SpMV_.home_buffers()
             if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes != 4 * n:
                 self.SpMV_.vector_buf = self.ctx.alloc(4 * n)
+            if self.SpMV_.results_buf is None or self.SpMV_.results_buf.nbytes != 4 * n:
+                self.SpMV_.results_buf = self.ctx.alloc(4 * n)
 
     def _exchange_frontier(self, list_buf, zero):
         """Row-sharded push: every rank's SpMSpV listed only the rows it owns.  The
         lists meet as ONE dense vector -- own slice reset and scattered, slices exchanged, the full
         vector listed again on every rank (into the same list buffer) -- so what follows (the sparse
-        assign on the replicated distance vector, the next SpMSpV) sees the whole frontier."""
+        assign on the replicated distance vector, the next SpMSpV) sees the whole frontier.
+
+        The dense vector ALTERNATES between two buffers: over a peer / multicast exchange the
+        signal / wait step only says "every rank has written its slice of step k", not "every rank
+        has finished reading step k", so a fast rank's slice of step k + 1 must not land in the
+        vector a slow rank is still listing.  With two vectors a rank can only be overwritten two
+        steps later, which its own signal of step k + 1 (issued after its listing of step k, in
+        stream order) gates.  After the call the fresh frontier is ``SpMV_.vector_buf``."""
         if self.world_ == 1:
             return
         n = self.matrix_num_rows_
-        dense = self.SpMV_.vector_buf
+        dense = self.SpMV_.results_buf
         rb, re = self._row_range(n)
         capi.sparse_to_dense_rows(self.ctx, list_buf, dense, rb, re, zero)
         self._gather(dense, n)
         capi.dense_to_sparse(self.ctx, dense, n, zero, list_buf)
+        self.SpMV_.vector_buf, self.SpMV_.results_buf = dense, self.SpMV_.vector_buf
 
     # -- launch replay: the iteration loop of an app is a fixed launch sequence ------------------
     use_graphs_ = True
@@ -141,8 +174,9 @@ class ModuleCollection:
         """Run ``launches()`` -- a loop of glb_* launches over fixed buffers and scalars -- as one
         recorded CUDA graph (recorded at the first call with this ``key``, replayed afterwards): a
         7-iteration BFS is 21 launches of 5-50 us kernels, which the host cannot enqueue fast enough
-        one by one.  Single-GPU only (the exchange step of a sharded run is not recorded)."""
-        if not self.use_graphs_ or self.world_ > 1:
+        one by one.  Row-sharded runs over an exchange are recorded too (the exchange's epoch lives in
+        device memory); with the NCCL allgather the launches are issued one by one."""
+        if not self.use_graphs_ or (self.world_ > 1 and self.exchange_ is None):
             launches()
             return
         # a recorded sequence holds the device addresses of the matrix it was recorded with
@@ -213,9 +247,12 @@ class BFS(ModuleCollection):
             iters = range(first_iter, num_iterations + 1)
 
             def launches():
+                eps = [Epilogue(0, 0.0, mask.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE) for it in iters]
+                if self.exchange_ is not None:   # the whole loop in one call: no acquire launch between steps
+                    self.SpMV_.iterate_with(vec, mask, res, eps)
+                    return
                 v, r = vec, res
-                for it in iters:
-                    ep = Epilogue(0, 0.0, mask.ptr, float(it + 1), capi.MASK_WRITE_TO_ONE)
+                for ep in eps:
                     self.SpMV_.run_with(v, mask, r, ep)
                     self._exchange(r, n)   # distance stays row-local until the end
                     v, r = r, v
@@ -337,6 +374,9 @@ class PageRank(ModuleCollection):
             vec, res = self.SpMV_.vector_buf, self.SpMV_.results_buf
 
             def launches():
+                if self.exchange_ is not None:
+                    self.SpMV_.iterate_with(vec, None, res, [Epilogue(1, teleport, None, 0.0, 0)] * num_iterations)
+                    return
                 v, r = vec, res
                 for _ in range(num_iterations):
                     self.SpMV_.run_with(v, None, r, Epilogue(1, teleport, None, 0.0, 0))
@@ -403,6 +443,9 @@ class SSSP(ModuleCollection):
             iters = range(first_iter, num_iterations + 1)
 
             def launches():
+                if self.exchange_ is not None:
+                    self.SpMV_.iterate_with(vec, None, res, None, len(iters))
+                    return
                 v, r = vec, res
                 for _ in iters:
                     self.SpMV_.run_with(v, None, r)

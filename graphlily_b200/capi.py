@@ -107,6 +107,8 @@ SIGNATURES = {
     "glb_xchg_destroy": (C.c_int, [_vp]),
     "glb_spmv_host_batch_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp, C.POINTER(Epilogue)]),
+    "glb_spmv_exchange_iterate": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp,
+                                            C.POINTER(Epilogue), C.c_int]),
 }
 
 
@@ -434,6 +436,16 @@ class Exchange:
     def spmv(self, matrix, op, zero, mask_type, src_vec, dst_vec, mask=None, epilogue=None):
         check(lib.glb_spmv_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
                                     _ptr(mask), C.byref(epilogue) if epilogue is not None else None))
+
+    def spmv_iterate(self, matrix, op, zero, mask_type, src_vec, dst_vec, n_steps, mask=None, epilogues=None):
+        """glb_spmv_exchange_iterate: ``n_steps`` ping-pong iterations src -> dst -> src ...;
+        ``epilogues``: None or one Epilogue per step."""
+        eps = None
+        if epilogues is not None:
+            assert len(epilogues) == n_steps
+            eps = (Epilogue * n_steps)(*epilogues)
+        check(lib.glb_spmv_exchange_iterate(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
+                                            _ptr(mask), eps, n_steps))
 
     def spmv_host_batch(self, matrix, op, zero, mask_type, x_hosts, mask_hosts, y_hosts):
         """glb_spmv_host_batch_exchange: every rank uploads its slice of each x, NVLink completes it."""

@@ -79,6 +79,26 @@ __global__ void __launch_bounds__(kThreads) assign_sparse_kernel(const glb_idx_v
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) inout[list[i + 1].index] = val;
 }
 
+// inout[idx] = min(inout[idx], val) with the reference's test `inout[idx] > val`
+// (assign_vector_sparse_module.h:318-335); true when THIS entry lowered the value.  A compare-and-
+// swap loop instead of a plain compare-then-store so that lists naming an index more than once
+// end with the minimum whatever the interleaving (NaN never wins the comparison, as in the host loop).
+__device__ __forceinline__ bool relax_min(float *addr, float val) {
+    float old = *addr;
+    while (old > val) {
+        const int seen = atomicCAS(reinterpret_cast<int *>(addr), __float_as_int(old), __float_as_int(val));
+        if (seen == __float_as_int(old)) return true;
+        old = __int_as_float(seen);
+    }
+    return false;
+}
+
+// Overlay mode 6.  With distinct indices (what SpMSpV emits and the apps feed) the result equals
+// the reference's sequential loop: same inout, same set of new-frontier entries (order
+// unspecified).  With repeated indices inout is still the reference's (the minimum); the new
+// frontier then holds every entry that lowered the value at the moment it was applied -- always
+// including the one carrying the final minimum -- where the reference lists the record lows in
+// list order.
 __global__ void __launch_bounds__(kThreads) assign_sparse_relax_kernel(const glb_idx_val_t *__restrict__ list,
                                                                      float *inout, glb_idx_val_t *new_frontier) {
     const unsigned lane = threadIdx.x & 31u;
@@ -90,10 +110,7 @@ __global__ void __launch_bounds__(kThreads) assign_sparse_relax_kernel(const glb
         glb_idx_val_t e = {0u, 0.0f};
         if (i < n) {
             e = list[i + 1];
-            if (inout[e.index] > e.val) {
-                inout[e.index] = e.val;
-                emit = true;
-            }
+            emit = relax_min(inout + e.index, e.val);
         }
         const unsigned b = __ballot_sync(kFull, emit);
         if (b) {

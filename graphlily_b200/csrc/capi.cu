@@ -416,234 +416,4 @@ int glb_graph_destroy(glb_graph_t g) {
     return GLB_OK;
 }
 
-// ------------------------------------------------------------------------ peer exchange
-// A row-sharded iteration needs every rank's slice of y on every rank before the next SpMV.
-// Instead of an allgather after the kernel, the SpMV write-back stores each row into all peers'
-// copies (glb_spmv_exchange); what is left of the collective is this signal / wait step.
-__global__ void xchg_signal_wait_kernel(uint32_t *const *peer_flags, uint32_t *local_flags, uint32_t *mc_flags, int rank,
-                                        int nranks, uint32_t epoch, uint32_t *err) {
-    const int p = int(threadIdx.x);
-    // all stores of this rank were issued by kernels that completed before this one started (stream
-    // order); publish, then wait for the peers' slices
-    if (mc_flags) {
-        // Data that travelled as multicast stores is published by a multicast store too, so the flag
-        // follows the data through the switch on every destination -- this rank included: its own
-        // slice comes back through the switch as well, and nothing may overwrite it locally before
-        // that copy has landed.  Hence the wait below covers all ranks, not only the peers.
-        if (p == 0) {
-            __threadfence_system();
-            asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc_flags + rank), "r"(epoch) : "memory");
-        }
-        if (p >= nranks) return;
-    } else {
-        if (p >= nranks || p == rank) return;
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
-    }
-    const long long t0 = clock64();
-    uint32_t seen;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + p) : "memory");
-        if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; fail loudly at the next sync
-            *err = 1;
-            break;
-        }
-    } while (seen < epoch);
-}
-
-int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc) {
-    xc->epoch++;
-    xchg_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(xc->d_peer_flags, xc->local_flags, xc->mc_flags, xc->rank, xc->nranks,
-                                                      xc->epoch, xc->d_err);
-    GLB_CUDA(cudaGetLastError());
-    return GLB_OK;
-}
-
-int glb_xchg_create(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, glb_xchg_t *out) {
-    GLB_REQUIRE(ctx && out && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
-    *out = nullptr;
-    GLB_CUDA(cudaSetDevice(ctx->device));
-    glb_xchg_t xc = new glb_xchg_s();
-    xc->ctx = ctx;
-    glb_ctx_retain(ctx);
-    xc->n = n_floats;
-    xc->n_vectors = n_vectors;
-    const size_t vec_bytes = (size_t(n_floats) * n_vectors * sizeof(float) + 255) & ~size_t(255);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&xc->local), vec_bytes + 256);  // plain cudaMalloc: IPC-exportable
-    if (e == cudaSuccess) e = cudaMemset(xc->local, 0, vec_bytes + 256);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_peer_flags), sizeof(uint32_t *) * (GLB_MAX_PEERS + 1));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_err), sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(xc->d_err, 0, sizeof(uint32_t));
-    if (e != cudaSuccess) {
-        glb_set_error("glb_xchg_create: %s", cudaGetErrorString(e));
-        glb_xchg_destroy(xc);
-        return e == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA;
-    }
-    xc->local_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->local) + vec_bytes);
-    *out = xc;
-    return GLB_OK;
-}
-
-int glb_xchg_export(glb_xchg_t xc, void *handle64) {
-    GLB_REQUIRE(xc && handle64, "NULL argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == GLB_IPC_HANDLE_BYTES, "IPC handle size");
-    cudaIpcMemHandle_t h;
-    GLB_CUDA(cudaIpcGetMemHandle(&h, xc->local));
-    memcpy(handle64, &h, sizeof(h));
-    return GLB_OK;
-}
-
-int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles) {
-    GLB_REQUIRE(xc && handles && nranks >= 1 && nranks <= GLB_MAX_PEERS + 1 && rank >= 0 && rank < nranks, "bad argument");
-    GLB_CUDA(cudaSetDevice(xc->ctx->device));
-    const size_t vec_bytes = (size_t(xc->n) * xc->n_vectors * sizeof(float) + 255) & ~size_t(255);
-    xc->rank = rank;
-    xc->nranks = nranks;
-    for (int r = 0; r < nranks; ++r) {
-        if (r == rank) {
-            xc->peer[r] = xc->local;
-        } else {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, static_cast<const char *>(handles) + size_t(r) * GLB_IPC_HANDLE_BYTES, sizeof(h));
-            void *p = nullptr;
-            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) {
-                glb_set_error("glb_xchg_connect: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
-                cudaGetLastError();
-                return GLB_ECUDA;
-            }
-            xc->peer[r] = static_cast<float *>(p);
-        }
-        xc->peer_flags[r] = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->peer[r]) + vec_bytes);
-    }
-    GLB_CUDA(cudaMemcpy(xc->d_peer_flags, xc->peer_flags, sizeof(uint32_t *) * (GLB_MAX_PEERS + 1), cudaMemcpyHostToDevice));
-    xc->connected = true;
-    return GLB_OK;
-}
-
-int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, void *const *blocks,
-                   void *multicast_block, glb_xchg_t *out) {
-    GLB_REQUIRE(ctx && out && blocks && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
-    GLB_REQUIRE(nranks >= 1 && nranks <= GLB_MAX_PEERS + 1 && rank >= 0 && rank < nranks, "bad rank");
-    *out = nullptr;
-    GLB_CUDA(cudaSetDevice(ctx->device));
-    for (int r = 0; r < nranks; ++r) GLB_REQUIRE(blocks[r], "NULL block");
-    glb_xchg_t xc = new glb_xchg_s();
-    xc->ctx = ctx;
-    glb_ctx_retain(ctx);
-    xc->n = n_floats;
-    xc->n_vectors = n_vectors;
-    xc->adopted = true;
-    xc->rank = rank;
-    xc->nranks = nranks;
-    xc->mc = static_cast<float *>(multicast_block);
-    const size_t vec_bytes = glb_xchg_block_bytes(n_floats, n_vectors) - 256;
-    for (int r = 0; r < nranks; ++r) {
-        xc->peer[r] = static_cast<float *>(blocks[r]);
-        xc->peer_flags[r] = reinterpret_cast<uint32_t *>(static_cast<char *>(blocks[r]) + vec_bytes);
-    }
-    xc->local = xc->peer[rank];
-    xc->local_flags = xc->peer_flags[rank];
-    if (xc->mc) xc->mc_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->mc) + vec_bytes);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&xc->d_peer_flags), sizeof(uint32_t *) * (GLB_MAX_PEERS + 1));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&xc->d_err), sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(xc->d_err, 0, sizeof(uint32_t));
-    if (e == cudaSuccess)
-        e = cudaMemcpy(xc->d_peer_flags, xc->peer_flags, sizeof(uint32_t *) * (GLB_MAX_PEERS + 1), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        glb_set_error("glb_xchg_adopt: %s", cudaGetErrorString(e));
-        glb_xchg_destroy(xc);
-        return GLB_ECUDA;
-    }
-    xc->connected = true;
-    *out = xc;
-    return GLB_OK;
-}
-
-size_t glb_xchg_block_bytes(uint32_t n_floats, int n_vectors) {
-    return ((size_t(n_floats) * size_t(n_vectors) * sizeof(float) + 255) & ~size_t(255)) + 256;
-}
-
-int glb_xchg_has_multicast(glb_xchg_t xc) { return xc && xc->mc ? 1 : 0; }
-
-int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr) {
-    GLB_REQUIRE(xc && local_ptr && which >= 0 && which < xc->n_vectors, "bad argument");
-    *local_ptr = xc->local + size_t(which) * xc->n;
-    return GLB_OK;
-}
-
-int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc) {
-    GLB_REQUIRE(ctx && xc && xc->connected && xc->ctx == ctx, "exchange is not connected to this context");
-    return glb_xchg_signal_wait(ctx, xc);
-}
-
-}  // extern "C"
-
-// One store, every rank: multimem.st on the multicast mapping of the blocks is replicated by the
-// NVSwitch into all ranks' copies (the issuing rank's included), so a slice leaves this GPU once
-// instead of once per peer.  16-byte stores; the unaligned head / tail go out as scalars.
-__global__ void __launch_bounds__(256) xchg_multicast_kernel(const float *__restrict__ src, float *mc, size_t count) {
-    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = size_t(gridDim.x) * blockDim.x;
-    size_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;
-    head = head / 4 < count ? head / 4 : count;
-    const size_t n4 = (count - head) / 4;
-    for (size_t i = tid; i < head; i += stride)
-        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(src[i]) : "memory");
-    const float4 *s4 = reinterpret_cast<const float4 *>(src + head);
-    for (size_t i = tid; i < n4; i += stride) {
-        const float4 v = s4[i];
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + head + 4 * i), "f"(v.x),
-                     "f"(v.y), "f"(v.z), "f"(v.w)
-                     : "memory");
-    }
-    for (size_t i = head + 4 * n4 + tid; i < count; i += stride)
-        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(src[i]) : "memory");
-}
-
-extern "C" {
-
-int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count) {
-    GLB_REQUIRE(ctx && xc && xc->connected && xc->ctx == ctx, "exchange is not connected to this context");
-    GLB_REQUIRE(which >= 0 && which < xc->n_vectors && offset + count <= xc->n, "slice outside the vector");
-    const size_t at = size_t(which) * xc->n + offset;
-    if (xc->mc && count && xc->nranks > 1) {
-        size_t blocks = (count / 4 + 255) / 256 + 1;
-        const size_t cap = size_t(ctx->num_sms) * 4;
-        if (blocks > cap) blocks = cap;
-        xchg_multicast_kernel<<<unsigned(blocks), 256, 0, ctx->stream>>>(xc->local + at, xc->mc + at, count);
-        GLB_CUDA(cudaGetLastError());
-    } else {
-        for (int r = 0; r < xc->nranks && count; ++r)
-            if (r != xc->rank)
-                GLB_CUDA(cudaMemcpyAsync(xc->peer[r] + at, xc->local + at, count * sizeof(float), cudaMemcpyDeviceToDevice,
-                                         ctx->stream));
-    }
-    return glb_xchg_signal_wait(ctx, xc);
-}
-
-int glb_xchg_status(glb_xchg_t xc, int *timed_out) {
-    GLB_REQUIRE(xc && timed_out, "NULL argument");
-    uint32_t e = 0;
-    GLB_CUDA(cudaStreamSynchronize(xc->ctx->stream));
-    GLB_CUDA(cudaMemcpy(&e, xc->d_err, sizeof(e), cudaMemcpyDeviceToHost));
-    *timed_out = int(e);
-    return GLB_OK;
-}
-
-int glb_xchg_destroy(glb_xchg_t xc) {
-    if (!xc) return GLB_OK;
-    cudaSetDevice(xc->ctx->device);
-    cudaStreamSynchronize(xc->ctx->stream);
-    if (!xc->adopted) {
-        for (int r = 0; r < xc->nranks; ++r)
-            if (xc->connected && r != xc->rank && xc->peer[r]) cudaIpcCloseMemHandle(xc->peer[r]);
-        cudaFree(xc->local);
-    }
-    cudaFree(xc->d_peer_flags);
-    cudaFree(xc->d_err);
-    glb_ctx_release(xc->ctx);
-    delete xc;
-    return GLB_OK;
-}
-
 }  // extern "C"

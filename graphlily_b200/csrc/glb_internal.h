@@ -134,9 +134,8 @@ struct glb_csc_s {
     uint32_t *indptr = nullptr;   // num_cols + 1
     uint32_t *indices = nullptr;  // row ids
     float *vals = nullptr;
-    float *acc = nullptr;         // dense accumulator, num_rows, kept at `acc_zero` between runs
-    float acc_zero = 0.0f;
-    bool acc_valid = false;
+    float *acc = nullptr;         // dense accumulator of plus-times / or-and, num_rows, at rest 0.0f between runs
+    float *acc_inf = nullptr;     // dense accumulator of min-plus, at rest +inf
     uint32_t *counter = nullptr;  // output cursor
 };
 
@@ -156,8 +155,9 @@ struct glb_xchg_s {
     float *peer[GLB_MAX_PEERS + 1] = {};        // blocks of all ranks (peer[rank] == local)
     uint32_t *peer_flags[GLB_MAX_PEERS + 1] = {};
     uint32_t **d_peer_flags = nullptr;    // device copy of peer_flags
-    uint32_t *d_err = nullptr;            // set when a wait timed out
-    uint32_t epoch = 0;
+    // device-resident state: [0] epoch this rank published last (advanced by the publishing kernel, so
+    // recorded launch sequences replay), [1] CTA ticket of the push kernel, [2] set when a wait timed out
+    uint32_t *d_state = nullptr;
     // adopted blocks (glb_xchg_adopt): memory mapped by the host (symmetric memory), optionally with
     // a multicast mapping -- one store to `mc` lands in every rank's block (NVSwitch multicast)
     bool adopted = false;
@@ -165,6 +165,12 @@ struct glb_xchg_s {
     uint32_t *mc_flags = nullptr;  // multicast mapping of the flag words
 };
 extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
+struct GlbXchgWait;                                        // exchange.cuh
+GlbXchgWait glb_xchg_wait_desc(glb_xchg_t xc);
+int glb_xchg_signal(glb_ctx_t ctx, glb_xchg_t xc, bool wait);
+int glb_xchg_wait(glb_ctx_t ctx, glb_xchg_t xc);
+int glb_xchg_wait_launch(glb_ctx_t ctx, const GlbXchgWait &w);
+int glb_xchg_push(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count);
 
 struct glb_graph_s {
     cudaGraphExec_t exec = nullptr;
@@ -176,7 +182,9 @@ void glb_ctx_retain(glb_ctx_t ctx);
 void glb_ctx_release(glb_ctx_t ctx);  // child destroyed; frees the context if it was destroyed meanwhile
 
 // launchers (defined in the .cu files)
+// `wait`: acquire of the previous step's exchange, folded into the head of the launch's first kernel (or NULL)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc);
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc,
+                    const GlbXchgWait *wait);
 
 #endif  // GLB_INTERNAL_H_

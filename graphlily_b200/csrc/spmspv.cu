@@ -67,7 +67,7 @@ struct SpmspvParams {
     uint32_t *heavy;  // [0] = number of queued segments, [2 + 2i], [3 + 2i] = {frontier slot k, segment number}
     uint32_t row_begin, row_end;  // output rows of this shard: the compaction scans only these
     uint32_t heavy_cap;  // segments the queue holds (nnz / kSeg + 1: enough unless x repeats columns)
-    uint32_t num_rows;
+    uint32_t num_rows, num_cols;
     float zero;
     int mask_type;
 };
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kThreads) spmspv_scatter_light(const SpmspvPar
     }
     for (uint32_t k = warp; k < nnz_x; k += n_warps) {
         const glb_idx_val_t e = P.x[k + 1];
+        if (e.index >= P.num_cols) continue;  // not a column of this matrix: ignored (warp-uniform)
         const uint32_t s = __ldg(P.indptr + e.index), t = __ldg(P.indptr + e.index + 1);
         const uint32_t len = t - s;
         bool queued = false;
@@ -180,12 +181,12 @@ __global__ void fill_one_f32_kernel(float *dst, float val, size_t n, size_t inde
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i == index) ? index_val : val;
 }
 
-__global__ void sparse_scatter_kernel(const glb_idx_val_t *__restrict__ list, float *dense, uint32_t len) {
+__global__ void sparse_scatter_kernel(const glb_idx_val_t *__restrict__ list, float *dense, uint32_t begin, uint32_t end) {
     const uint32_t n = list[0].index;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const glb_idx_val_t e = list[i + 1];
-        if (e.index < len) dense[e.index] = e.val;
+        if (e.index >= begin && e.index < end) dense[e.index] = e.val;
     }
 }
 
@@ -222,13 +223,7 @@ __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
 
 template <int OP>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
-    const float ident = (OP == GLB_OP_ADD_MIN) ? HUGE_VALF : 0.0f;
     const int grid = ctx->num_sms * 8;
-    if (!m->acc_valid || memcmp(&m->acc_zero, &ident, sizeof(float)) != 0) {
-        fill_f32_kernel<<<grid, kThreads, 0, ctx->stream>>>(m->acc, ident, m->num_rows);
-        m->acc_zero = ident;
-        m->acc_valid = true;
-    }
     spmspv_scatter_light<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
     spmspv_scatter_heavy<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
     spmspv_compact<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
@@ -316,6 +311,7 @@ int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, con
     alloc(reinterpret_cast<void **>(&m->indices), sizeof(uint32_t) * nnz);
     alloc(reinterpret_cast<void **>(&m->vals), sizeof(float) * nnz);
     alloc(reinterpret_cast<void **>(&m->acc), sizeof(float) * num_rows);
+    alloc(reinterpret_cast<void **>(&m->acc_inf), sizeof(float) * num_rows);
     alloc(reinterpret_cast<void **>(&m->counter), sizeof(uint32_t) * (2 * (size_t(nnz) / kSeg + 1) + 4));  // segment queue
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->indptr, indptr, sizeof(uint32_t) * (size_t(num_cols) + 1), cudaMemcpyHostToDevice, ctx->stream);
@@ -324,6 +320,11 @@ int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, con
     if (e == cudaSuccess && nnz)
         e = cudaMemcpyAsync(m->vals, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->counter, 0, sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess && num_rows) {
+        fill_f32_kernel<<<ctx->num_sms * 8, kThreads, 0, ctx->stream>>>(m->acc, 0.0f, num_rows);
+        fill_f32_kernel<<<ctx->num_sms * 8, kThreads, 0, ctx->stream>>>(m->acc_inf, HUGE_VALF, num_rows);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         glb_set_error("glb_csc_create: %s", cudaGetErrorString(e));
@@ -338,7 +339,7 @@ int glb_csc_destroy(glb_csc_t m) {
     if (!m) return GLB_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->counter);
+    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf); cudaFree(m->counter);
     glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
@@ -358,12 +359,15 @@ int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, co
     P.x = x;
     P.mask = mask;
     P.y = y;
-    P.acc = m->acc;
+    // one accumulator per (+)-identity, both filled when the matrix was created and left at rest by
+    // every run: no launch depends on host-side state (launch sequences can be recorded at any time)
+    P.acc = (op == GLB_OP_ADD_MIN) ? m->acc_inf : m->acc;
     P.heavy = m->counter;
     P.heavy_cap = uint32_t(m->nnz / kSeg + 1);
     P.row_begin = m->row_begin;
     P.row_end = m->row_end;
     P.num_rows = m->num_rows;
+    P.num_cols = m->num_cols;
     P.zero = zero;
     P.mask_type = mask_type;
     switch (op) {
@@ -389,7 +393,7 @@ int glb_sparse_to_dense(glb_ctx_t ctx, const glb_idx_val_t *list, float *dense, 
     if (len == 0) return GLB_OK;
     int rc = glb_buffer_fill_f32(ctx, dense, zero, len);
     if (rc) return rc;
-    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, len);
+    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, 0u, len);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
@@ -403,7 +407,7 @@ int glb_sparse_to_dense_rows(glb_ctx_t ctx, const glb_idx_val_t *list, float *de
     if (row_begin == row_end) return GLB_OK;
     int rc = glb_buffer_fill_f32(ctx, dense + row_begin, zero, row_end - row_begin);
     if (rc) return rc;
-    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, row_end);
+    sparse_scatter_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, dense, row_begin, row_end);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }

@@ -43,6 +43,7 @@
 #include <thread>
 #include <vector>
 
+#include "exchange.cuh"
 #include "glb_internal.h"
 #include "semiring.cuh"
 
@@ -320,16 +321,19 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_
 // xbits: bit w = truth value of the x entry that stored column word w refers to.  Words below
 // tile_k are hot ranks (x[hot_cols[w]], or x[w] under the identity numbering), the others are
 // tile_k + column.  One warp packs 32 consecutive words with a ballot.
-__global__ void __launch_bounds__(kThreads) pack_bits_kernel(const float *__restrict__ x, const uint32_t *__restrict__ hot_cols,
+// `wait`: in a row-sharded run x is complete only once every rank's slice of the previous step has
+// landed (glb_xchg_wait_head); x is then read around L1 (ld.cg) -- peers wrote it.
+__global__ void __launch_bounds__(kThreads) pack_bits_kernel(const float *x, const uint32_t *__restrict__ hot_cols,
                                                            uint32_t *__restrict__ xbits, uint32_t tile_k, uint32_t n_hot,
-                                                           uint32_t num_cols, uint32_t n_words32) {
+                                                           uint32_t num_cols, uint32_t n_words32, const GlbXchgWait wait) {
+    glb_xchg_wait_head(wait);
     const uint32_t w = blockIdx.x * kThreads + threadIdx.x;  // grid covers n_words32 * 32 exactly
     bool t = false;
     if (w < tile_k) {
         const uint32_t c = n_hot ? __ldg(hot_cols + w) : w;
-        t = (c < num_cols) && __ldg(x + c) != 0.0f;
+        t = (c < num_cols) && __ldcg(x + c) != 0.0f;
     } else if (w - tile_k < num_cols) {
-        t = __ldg(x + (w - tile_k)) != 0.0f;
+        t = __ldcg(x + (w - tile_k)) != 0.0f;
     }
     const unsigned b = __ballot_sync(kFull, t);
     if ((threadIdx.x & 31u) == 0 && (w >> 5) < n_words32) xbits[w >> 5] = b;
@@ -403,11 +407,11 @@ __global__ void __launch_bounds__(1024, 1) spmv_lane_tile_kernel(const SpmvParam
 }
 
 // hot_x[i] = x[hot_cols[i]]: the x values of the most referenced columns, packed.
-__global__ void __launch_bounds__(kThreads) gather_hot_kernel(const float *__restrict__ x,
-                                                            const uint32_t *__restrict__ hot_cols,
-                                                            float *__restrict__ hot_x, uint32_t n) {
+__global__ void __launch_bounds__(kThreads) gather_hot_kernel(const float *x, const uint32_t *__restrict__ hot_cols,
+                                                            float *__restrict__ hot_x, uint32_t n, const GlbXchgWait wait) {
+    glb_xchg_wait_head(wait);  // row-sharded run: the peers' slices of x must have landed (see pack_bits_kernel)
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) hot_x[i] = __ldg(x + __ldg(hot_cols + i));
+    if (i < n) hot_x[i] = __ldcg(x + __ldg(hot_cols + i));
 }
 
 // Rows touching a chunk boundary: total = tail[c_begin .. c_last] (+) head[c_end].
@@ -527,9 +531,19 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 }  // namespace
 
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc) {
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc,
+                    const GlbXchgWait *wait) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
+    GlbXchgWait w;
+    memset(&w, 0, sizeof(w));
+    if (wait) w = *wait;
+    const bool head_is_pack = op == GLB_OP_LOGICAL_AND_OR && m->xbits && m->n_chunks && !m->tile_threads;
+    const bool head_is_gather = !head_is_pack && m->n_hot && m->n_chunks;
+    if (wait && !head_is_pack && !head_is_gather) {  // no kernel of this launch opens with the acquire: its own launch
+        int rc = glb_xchg_wait_launch(ctx, w);
+        if (rc) return rc;
+    }
     P.y_mc = y_mc;
     P.n_peers = n_peers;
     for (int p = 0; p < n_peers && p < GLB_MAX_PEERS; ++p) P.y_peer[p] = y_peers[p];
@@ -544,12 +558,12 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
         const uint32_t n_words32 = (m->tile_k + m->num_cols + 31u) / 32u;
         const uint32_t threads = n_words32 * 32u;
         pack_bits_kernel<<<(threads + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->xbits, m->tile_k,
-                                                                                          m->n_hot, m->num_cols, n_words32);
+                                                                                          m->n_hot, m->num_cols, n_words32, w);
         P.xbits = m->xbits;
         P.hot_x = x;
     } else if (m->n_hot && m->n_chunks) {  // pack the x values of the hot columns
         gather_hot_kernel<<<(m->n_hot + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->hot_x,
-                                                                                            m->n_hot);
+                                                                                            m->n_hot, w);
         P.hot_x = m->hot_x;
     } else {
         P.hot_x = x;  // tile_k == num_cols (every column hot, identity numbering) or tile_k == 0
@@ -933,48 +947,62 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr);
 }
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
                       const float *mask, const glb_spmv_epilogue_t *ep) {
+    return glb_spmv_exchange_iterate(ctx, m, op, zero, mask_type, xc, src_vec, dst_vec, mask, ep, 1);
+}
+
+// n_steps row-sharded iterations x -> y -> x ... over two exchange vectors.  Per step: the SpMV
+// kernels, whose first kernel opens with the acquire of the previous step's exchange, then the
+// slice goes out:
+//   multicast mapping:  one push kernel (16-byte multimem.st of the finished slice; its last CTA
+//                       publishes the epoch).  GLB_XCHG_MC=fused stores each row to the multicast
+//                       address from the SpMV write-back instead (measured slower: 4-byte remote stores);
+//   peer mapping:       the write-back stored every row into all peers' blocks; one 32-thread kernel
+//                       publishes the epoch.
+// Only the last step is followed by an acquire of its own (so that whatever comes next on the
+// stream sees the complete vector).  All launches are graph-recordable.
+int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
+                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps) {
     GLB_REQUIRE(xc && xc->connected, "exchange is not connected");
     GLB_REQUIRE(src_vec >= 0 && src_vec < xc->n_vectors && dst_vec >= 0 && dst_vec < xc->n_vectors && src_vec != dst_vec,
                 "bad vector index");
     GLB_REQUIRE(m && m->num_rows <= xc->n && m->num_cols <= xc->n, "matrix larger than the exchange vectors");
-    const float *x = xc->local + size_t(src_vec) * xc->n;
-    float *y = xc->local + size_t(dst_vec) * xc->n;
-    int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
-    if (rc) return rc;
-    if (xc->mc) {
-        // multicast mapping available: each row leaves this GPU once and the NVSwitch replicates it.
-        //   "kernel": the kernels write y locally, then one small kernel sends the finished slice in
-        //             16-byte multicast stores (default from 4 ranks on: the SpMV kernels run at their
-        //             single-GPU speed, measured 57 us vs 74 us per launch on 8 B200s);
-        //   "fused":  the write-back itself stores each row to the multicast address, overlapping the
-        //             kernel (default below 4 ranks, where slices are long and the extra launch costs more).
-        // GLB_XCHG_MC=kernel|fused overrides.
-        static const int forced = [] {
-            const char *v = getenv("GLB_XCHG_MC");
-            return !v ? 0 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : 0;
-        }();
-        const bool separate = forced ? forced == 1 : xc->nranks >= 4;
-        if (separate) {
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr);
-            if (rc) return rc;
-            return glb_xchg_allgather(ctx, xc, dst_vec, m->row_begin, size_t(m->row_end - m->row_begin));
-        }
-        rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, xc->mc + size_t(dst_vec) * xc->n);
-        if (rc) return rc;
-        return glb_xchg_signal_wait(ctx, xc);
-    }
+    GLB_REQUIRE(n_steps >= 0, "negative step count");
+    static const int forced = [] {
+        const char *v = getenv("GLB_XCHG_MC");
+        return !v ? 0 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : 0;
+    }();
+    const bool mc_fused = xc->mc && forced == 2;
+    const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
-    int n_peers = 0;
-    for (int r = 0; r < xc->nranks; ++r)
-        if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dst_vec) * xc->n;
-    rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr);
-    if (rc) return rc;
-    return glb_xchg_signal_wait(ctx, xc);
+    for (int k = 0; k < n_steps; ++k) {
+        const int sv = (k & 1) ? dst_vec : src_vec, dv = (k & 1) ? src_vec : dst_vec;
+        const float *x = xc->local + size_t(sv) * xc->n;
+        float *y = xc->local + size_t(dv) * xc->n;
+        const glb_spmv_epilogue_t *ep = eps ? eps + k : nullptr;
+        int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
+        if (rc) return rc;
+        const GlbXchgWait *w = k > 0 ? &wait : nullptr;
+        if (xc->mc && !mc_fused) {
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w);
+            if (!rc) rc = glb_xchg_push(ctx, xc, dv, m->row_begin, size_t(m->row_end - m->row_begin));
+        } else if (xc->mc) {
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, xc->mc + size_t(dv) * xc->n, w);
+            if (!rc) rc = glb_xchg_signal(ctx, xc, false);
+        } else {
+            int n_peers = 0;
+            for (int r = 0; r < xc->nranks; ++r)
+                if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w);
+            if (!rc) rc = glb_xchg_signal(ctx, xc, false);
+        }
+        if (rc) return rc;
+    }
+    return n_steps ? glb_xchg_wait(ctx, xc) : GLB_OK;
 }
 
 int glb_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,

@@ -8,7 +8,13 @@ are not shipped, so every bench / parity input is generated:
 * ``powerlaw_csr``    C2: power-law row degrees (Pareto, alpha 2.1, 1 .. 2^20, rescaled to the
                       requested nnz) and Zipf-skewed column popularity (s = 0.9) under a
                       random column permutation -- the hard, locality-free case
-* ``powerlaw_graph``  C3 / C4 / C5: symmetric power-law graph, optional full diagonal
+* ``social_graph``    C3 / C4 / C5: symmetric graph with a truncated power-law degree sequence
+                      (configuration model), hub degree capped at what the real datasets show
+                      (gplus ~2e4, ogbn-products 17 481, orkut 33 313); ``c3_gplus`` /
+                      ``c4_ogbn_products`` / ``c5_orkut`` are the named shapes every bench and test uses
+* ``powerlaw_graph``  symmetric graph with one Zipf-drawn endpoint: hubs of 10^5-10^6 edges, far
+                      beyond any of the named datasets -- kept as a labelled STRESS case (giant
+                      rows: chunk-spanning fix-ups, fp32 summation order), optional full diagonal
 
 Column indices are sorted and distinct inside each row.  Generation runs in torch on the
 given device (CPU here, CUDA on the GPU box for the 128 M-nnz cases) because it is only
@@ -129,6 +135,55 @@ def powerlaw_graph(n, nnz, seed=42, skew=0.9, diagonal=False, value=1.0, device=
         d = torch.arange(n, device=device, dtype=torch.int64)
         keys = torch.unique(torch.cat([keys, d * n + d]))
     return _finish(keys, n, n, np.float32(value), device)
+
+
+def social_graph(n, nnz, max_degree, seed=42, alpha=2.1, diagonal=False, value=1.0, device="cpu"):
+    """Symmetric graph whose degrees follow a Pareto(alpha) law truncated at ``max_degree``.
+
+    Configuration model: vertex u gets d[u] stubs (d ~ Pareto, rescaled so that the stubs sum to
+    nnz / 2, capped at max_degree / 2, at least 1), the stub list is paired with a random
+    permutation of itself, self-pairs are dropped, the pattern is symmetrised and de-duplicated --
+    so a vertex ends up with about 2 d[u] <= max_degree neighbours and ``nnz`` is met within a few
+    percent.  Degrees are independent of the vertex id (no relabelling needed)."""
+    device = torch.device(device)
+    gen = _gen(seed, device)
+    u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
+    pareto = torch.pow(1.0 - u, -1.0 / (alpha - 1.0))
+    cap = max(int(max_degree) // 2, 1)
+    target = nnz / 2 * 1.02
+    scale = target / float(pareto.sum())
+    for _ in range(6):   # the cap removes mass from the tail: re-fit the scale
+        d = torch.clamp(torch.round(pareto * scale), min=1, max=cap)
+        scale *= target / float(d.sum())
+    d = torch.clamp(torch.round(pareto * scale), min=1, max=cap).to(torch.int64)
+    stubs = torch.repeat_interleave(torch.arange(n, device=device), d)
+    partner = stubs[torch.randperm(stubs.numel(), generator=gen, device=device)]
+    ok = stubs != partner
+    a, b = stubs[ok], partner[ok]
+    keys = torch.unique(torch.cat([a * n + b, b * n + a]))
+    if diagonal:
+        dg = torch.arange(n, device=device, dtype=torch.int64)
+        keys = torch.unique(torch.cat([keys, dg * n + dg]))
+    return _finish(keys, n, n, np.float32(value), device)
+
+
+def _pad128(n):
+    return (int(n) + 127) // 128 * 128
+
+
+def c3_gplus(scale=1.0, device="cpu"):
+    """bench_bfs shape: 107 648 vertices, ~13 M nnz, hub degree <= 20 000."""
+    return social_graph(_pad128(107_648 * scale), int(13_000_000 * scale), 20_000, seed=3, device=device)
+
+
+def c4_ogbn_products(scale=1.0, device="cpu"):
+    """bench_pagerank shape (C4): 2 449 024 vertices, ~124 M nnz, hub degree <= 17 481 (the real graph's maximum)."""
+    return social_graph(_pad128(2_449_024 * scale), int(124_000_000 * scale), 17_481, seed=4, device=device)
+
+
+def c5_orkut(scale=1.0, device="cpu"):
+    """bench_sssp shape (C5): 3 072 512 vertices, ~117 M nnz + the full diagonal, hub degree <= 33 313."""
+    return social_graph(_pad128(3_072_512 * scale), int(117_000_000 * scale), 33_313, seed=5, diagonal=True, device=device)
 
 
 def line_graph(n):

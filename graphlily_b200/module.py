@@ -151,6 +151,15 @@ class SpMVModule(BaseModule):
         else:
             self.matrix.spmv(op, zero, self.mask_type_, vector_buf, mask, results_buf, epilogue)
 
+    def iterate_with(self, vector_buf, mask_buf, results_buf, epilogues=None, n_steps=None):
+        """Row-sharded pull loop in one call (glb_spmv_exchange_iterate): vector -> results -> vector ..."""
+        assert self.exchange is not None and vector_buf.tag and results_buf.tag
+        op, _one, zero = self.semiring_
+        mask = mask_buf if self.mask_type_ != capi.MASK_NONE else None
+        n_steps = len(epilogues) if n_steps is None else n_steps
+        self.exchange.spmv_iterate(self.matrix, op, zero, self.mask_type_, vector_buf.tag[1], results_buf.tag[1], n_steps,
+                                   mask, epilogues)
+
     def send_vector_device_to_host(self):
         return self._read_dense(self.vector_buf, self.get_num_cols())
 

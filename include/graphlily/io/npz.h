@@ -69,22 +69,29 @@ inline void parse_npy(const std::vector<unsigned char> &raw, Array &out) {
 
     size_t p = hdr.find("'descr'");
     if (p == std::string::npos) fail("no descr");
-    p = hdr.find('\'', hdr.find(':', p));
-    size_t q = hdr.find('\'', p + 1);
+    p = hdr.find(':', p);
+    if (p != std::string::npos) p = hdr.find('\'', p);
+    size_t q = (p == std::string::npos) ? p : hdr.find('\'', p + 1);
+    if (p == std::string::npos || q == std::string::npos) fail("malformed descr");
     out.descr = hdr.substr(p + 1, q - p - 1);
     if (out.descr.size() < 3) fail("unsupported descr " + out.descr);
     if (out.descr[0] == '>') fail("big-endian arrays unsupported");
+    for (size_t k = 2; k < out.descr.size(); k++)
+        if (out.descr[k] < '0' || out.descr[k] > '9') fail("unsupported descr " + out.descr);
     out.word_size = size_t(std::stoul(out.descr.substr(2)));
     if (out.descr[1] == 'U') out.word_size *= 4;
 
     p = hdr.find("'fortran_order'");
     if (p == std::string::npos) fail("no fortran_order");
-    out.fortran_order = hdr.compare(hdr.find_first_not_of(" :", p + 15), 4, "True") == 0;
+    p = hdr.find_first_not_of(" :", p + 15);
+    if (p == std::string::npos) fail("malformed fortran_order");
+    out.fortran_order = hdr.compare(p, 4, "True") == 0;
 
     p = hdr.find("'shape'");
     if (p == std::string::npos) fail("no shape");
     p = hdr.find('(', p);
-    q = hdr.find(')', p);
+    q = (p == std::string::npos) ? p : hdr.find(')', p);
+    if (p == std::string::npos || q == std::string::npos) fail("malformed shape");
     out.shape.clear();
     std::string dims = hdr.substr(p + 1, q - p - 1);
     size_t i = 0;
@@ -95,8 +102,16 @@ inline void parse_npy(const std::vector<unsigned char> &raw, Array &out) {
         while (i < dims.size() && dims[i] >= '0' && dims[i] <= '9') v = v * 10 + size_t(dims[i++] - '0');
         out.shape.push_back(v);
     }
-    size_t payload = out.num_elements() * out.word_size;
-    if (hoff + hlen + payload > raw.size()) fail("truncated .npy payload");
+    size_t payload = 0, limit = raw.size() - hoff - hlen;
+    {   // the product must not wrap: every partial product is checked against what the member can hold
+        size_t n = out.word_size ? 1 : 0;
+        for (size_t d : out.shape) {
+            if (d != 0 && n > limit / d) fail("shape larger than the .npy payload");
+            n *= d;
+        }
+        if (out.word_size != 0 && n > limit / out.word_size) fail("truncated .npy payload");
+        payload = n * out.word_size;
+    }
     out.bytes.assign(raw.begin() + long(hoff + hlen), raw.begin() + long(hoff + hlen + payload));
 }
 
@@ -166,24 +181,31 @@ inline Archive load(const std::string &path) {
         uint64_t usize = rd32(&buf[p + 24]);
         uint16_t nlen = rd16(&buf[p + 28]), xlen = rd16(&buf[p + 30]), clen = rd16(&buf[p + 32]);
         uint64_t lho = rd32(&buf[p + 42]);
+        if (p + 46 + size_t(nlen) + xlen + clen > fsize) fail("central directory entry overruns the file");
         std::string name(reinterpret_cast<const char *>(&buf[p + 46]), nlen);
         // zip64 extended information (header id 0x0001): fields present only for saturated values
         size_t x = p + 46 + nlen, xend = x + xlen;
         while (x + 4 <= xend) {
             uint16_t id = rd16(&buf[x]), sz = rd16(&buf[x + 2]);
+            if (x + 4 + size_t(sz) > xend) fail("extra field overruns its entry: " + name);
             if (id == 0x0001) {
-                size_t q = x + 4;
-                if (usize == 0xFFFFFFFFu) { usize = rd64(&buf[q]); q += 8; }
-                if (csize == 0xFFFFFFFFu) { csize = rd64(&buf[q]); q += 8; }
-                if (lho == 0xFFFFFFFFu) { lho = rd64(&buf[q]); q += 8; }
+                size_t q = x + 4, qend = x + 4 + sz;
+                auto take64 = [&](uint64_t &v) {
+                    if (q + 8 > qend) fail("truncated zip64 extra field: " + name);
+                    v = rd64(&buf[q]);
+                    q += 8;
+                };
+                if (usize == 0xFFFFFFFFu) take64(usize);
+                if (csize == 0xFFFFFFFFu) take64(csize);
+                if (lho == 0xFFFFFFFFu) take64(lho);
             }
             x += 4 + sz;
         }
         p = xend + clen;
 
-        if (lho + 30 > fsize || rd32(&buf[lho]) != 0x04034b50u) fail("bad local header for " + name);
+        if (lho > fsize || lho + 30 > fsize || rd32(&buf[lho]) != 0x04034b50u) fail("bad local header for " + name);
         size_t data_off = size_t(lho) + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
-        if (data_off + csize > fsize) fail("member overruns file: " + name);
+        if (data_off > fsize || csize > fsize - data_off) fail("member overruns file: " + name);
 
         std::vector<unsigned char> raw;
         if (method == 0) raw.assign(buf.begin() + long(data_off), buf.begin() + long(data_off + csize));
@@ -219,6 +241,8 @@ public:
 
         uint64_t total = hdr.size() + nbytes;
         if (total >= 0xFFFFFFFFull) detail::fail("member too large for zip32 writer: " + name);
+        if (dict.size() > 0xFFFF) detail::fail("header too long for a version-1 .npy: " + name);
+        if (entries_.size() >= 0xFFFE) detail::fail("too many members for the zip32 writer");
         uLong crc = crc32(0L, Z_NULL, 0);
         crc = crc32(crc, hdr.data(), uInt(hdr.size()));
         const unsigned char *p = static_cast<const unsigned char *>(data);

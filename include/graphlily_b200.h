@@ -304,6 +304,13 @@ int glb_xchg_status(glb_xchg_t xc, int *timed_out);
 int glb_xchg_destroy(glb_xchg_t xc);
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
                       int dst_vec, const float *mask, const glb_spmv_epilogue_t *ep);
+/* n_steps iterations of a pull loop (pagerank.h:80-90, bfs.h:117-124, sssp.h:157-163) in one call: step k
+ * reads vector src_vec (k even) / dst_vec (k odd) and writes the other one on every rank; eps (NULL or
+ * n_steps entries) = the fused epilogue of each step.  Between steps the acquire of the exchange rides
+ * in the head of the next SpMV's first kernel instead of a launch of its own; the call ends with the
+ * acquire of the last step.  Graph-recordable (glb_graph_begin). */
+int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
+                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps);
 /* glb_spmv_host_batch for a row-sharded run: called by every rank with the same full-length host
  * vectors; each rank uploads only its 1/nranks slice of x over PCIe, the slices meet over NVLink
  * (exchange vectors 0 and 1 are the two pipeline slots), and y_hosts[k] receives the rank's rows. */
@@ -318,7 +325,8 @@ int glb_spmv_host_batch_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero,
  * recorded once as a CUDA graph and replayed with one call:
  *   glb_graph_begin   every glb_* launch on this context that follows is recorded, not executed
  *                     (no blocking call -- copies to / from the host, glb_ctx_sync, glb_sparse_count,
- *                     buffer allocation, glb_spmv_exchange -- may be made while recording)
+ *                     buffer allocation -- may be made while recording; the exchange steps of a
+ *                     row-sharded run ARE recordable: their epoch lives in device memory)
  *   glb_graph_end     stops recording and returns the executable sequence
  *   glb_graph_launch  enqueues the whole sequence on the context's stream */
 typedef struct glb_graph_s *glb_graph_t;

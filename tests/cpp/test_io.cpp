@@ -1,6 +1,11 @@
 // CPU-only tests of the host IO layer (include/graphlily/io), restating the golden vectors of the
 // reference's tests/test_io.cpp (create_csr_matrix :68-80, npz load :83-93, convert :96-107, csr2csc
 // :110-118, round dim :121-130, normalise :133-140) and pinning sssp_preprocess to the oracle.
+#include <unistd.h>
+
+#include <fstream>
+#include <iterator>
+
 #include "graphlily/app/sssp.h"
 #include "test_util.h"
 
@@ -63,6 +68,57 @@ TEST(DataLoader, ScipyWrittenNpzVariants) {
         EXPECT_EQ(b, s_indptr);
         EXPECT_TRUE(std::fabs(c - s_data) <= 1e-9 * (1 + std::fabs(s_data)));
     }
+}
+
+// A damaged archive must end in a clean "npz: ..." exception (or load, if the damage hit a
+// don't-care byte) -- never an out-of-bounds read: every truncation length and 1200 random byte
+// corruptions of a stored and of a deflated archive.  Run under -fsanitize=address when changed.
+TEST(DataLoader, MalformedNpzFailsCleanly) {
+    if (std::getenv("GLB_NPZ_CASES")) return;   // the scipy-variants invocation of this binary: covered by the plain one
+    const char *tmpdir = std::getenv("TMPDIR");
+    const std::string base = std::string(tmpdir ? tmpdir : "/tmp") + "/glb_npz_fuzz_" + std::to_string(long(getpid()));
+    std::vector<std::string> sources;
+    {
+        const std::string good = base + "_good.npz";
+        graphlily::io::npz::Writer w(good);
+        std::vector<int32_t> ix = {0, 2, 1, 3, 0}, ip = {0, 2, 4, 5};
+        std::vector<float> d = {1, 2, 3, 4, 5};
+        std::vector<int64_t> shape = {3, 4};
+        w.add("indices", "<i4", {ix.size()}, ix.data(), ix.size() * 4);
+        w.add("indptr", "<i4", {ip.size()}, ip.data(), ip.size() * 4);
+        w.add("data", "<f4", {d.size()}, d.data(), d.size() * 4);
+        w.add("shape", "<i8", {2}, shape.data(), 16);
+        w.close();
+        sources.push_back(good);
+    }
+    const char *data_dir = std::getenv("GLB_TEST_DATA");
+    if (data_dir) sources.push_back(std::string(data_dir) + "/eye_10_csr_float32.npz");   // deflated members
+    unsigned long long rng = 88172645463325252ull;
+    auto next = [&rng] { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    size_t clean_failures = 0, loads = 0;
+    for (const std::string &src : sources) {
+        std::ifstream f(src, std::ios::binary);
+        std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        ASSERT_TRUE(bytes.size() > 100);
+        const std::string bad = base + "_bad.npz";
+        auto attempt = [&](const std::vector<char> &b) {
+            { std::ofstream o(bad, std::ios::binary | std::ios::trunc); o.write(b.data(), std::streamsize(b.size())); }
+            try { graphlily::io::npz::load(bad); loads++; }
+            catch (const std::runtime_error &e) { EXPECT_TRUE(std::string(e.what()).compare(0, 4, "npz:") == 0); clean_failures++; }
+        };
+        for (size_t len = 0; len < bytes.size(); len += (bytes.size() > 2000 ? 7 : 1))
+            attempt(std::vector<char>(bytes.begin(), bytes.begin() + long(len)));
+        for (int k = 0; k < 1200; k++) {
+            std::vector<char> b = bytes;
+            const int flips = 1 + int(next() % 3);
+            for (int j = 0; j < flips; j++) b[next() % b.size()] = char(next());
+            attempt(b);
+        }
+        std::remove(bad.c_str());
+    }
+    std::remove((base + "_good.npz").c_str());
+    EXPECT_TRUE(clean_failures > 500);
+    std::printf("  %zu damaged archives rejected cleanly, %zu still loaded\n", clean_failures, loads);
 }
 
 TEST(DataLoader, Csr2Csc) {

@@ -70,6 +70,24 @@ def _worker(rank, world, port, kind):
             assert_close_rel(got, ref, 1e-4)      # five iterations of 1e-5-per-step differences
         else:
             assert got.tobytes() == ref.tobytes(), f"rank {rank} op {op}"
+    # the same loop in ONE call (acquire folded into the head of the next SpMV), directly and as a
+    # recorded launch sequence replayed twice (the epoch lives in device memory)
+    x0 = rng.random(n).astype(np.float32)
+    ref = x0
+    for it in range(6):
+        ref = oracle.port.spmv(m, 0, 0.0, 0, ref)
+    xc.barrier()
+    xc.buffer(0).write(x0)
+    xc.barrier()
+    xc.spmv_iterate(A, 0, 0.0, capi.MASK_NONE, 0, 1, 6)
+    assert_close_rel(xc.buffer(0).read(np.float32, n), ref, 1e-4)
+    g6 = ctx.record(lambda: xc.spmv_iterate(A, 0, 0.0, capi.MASK_NONE, 0, 1, 6))
+    for _ in range(2):
+        xc.barrier()
+        xc.buffer(0).write(x0)
+        xc.barrier()
+        g6.launch()
+        assert_close_rel(xc.buffer(0).read(np.float32, n), ref, 1e-4)
     # pipelined host-buffer batch: every rank uploads its slice of x, NVLink completes it
     xs = [capi.PinnedArray(n) for _ in range(5)]
     ys = [capi.PinnedArray(n) for _ in range(5)]

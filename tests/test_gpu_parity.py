@@ -344,6 +344,39 @@ def test_apply_shapes_of_reference_tests(ctx, oracle):
     assert capi.sparse_count(ctx, nf) == 0 and dense.read(np.float32, 4096).tobytes() == ref.tobytes()
 
 
+def test_sparse_relax_repeated_indices(ctx, oracle):
+    # assign_vector_sparse_module.h:318-335 walks the list in order; the device applies the entries
+    # concurrently with compare-and-swap, so with REPEATED indices: inout must still equal the
+    # reference's (the minimum wins whatever the interleaving), every improved index appears in the
+    # new frontier with its final minimum, and every listed entry is an input entry that lowered the
+    # value it found (val < the value before the call).  Distinct-index lists are covered bit-for-bit
+    # by test_apply_golden_fixture.
+    rng = np.random.default_rng(61)
+    n = 5000
+    for trial in range(4):
+        base = rng.integers(0, 40, n).astype(np.float32)
+        cnt = 60000
+        idx = rng.integers(0, n // (1 + trial * 3), cnt).astype(np.uint32)    # heavy repetition
+        val = rng.integers(0, 40, cnt).astype(np.float32)
+        ref_inout, ref_idx, ref_val = oracle.port.assign_sparse_relax(idx, val, base)
+        dl, dio = ctx.to_device(capi.sparse_to_numpy(idx, val)), ctx.to_device(base)
+        dnf = ctx.to_device(np.zeros(cnt + 1, capi.IDX_VAL))
+        capi.assign_sparse_relax(ctx, dl, dio, dnf)
+        got = dio.read(np.float32, n)
+        assert got.tobytes() == ref_inout.tobytes()
+        fi, fv = dnf.read_sparse()
+        assert (fv < base[fi]).all()                                   # each entry lowered what it found ...
+        pairs = set(zip(idx.tolist(), val.tolist()))
+        assert all((int(i), float(v)) in pairs for i, v in zip(fi, fv))   # ... and is an input entry
+        improved = np.nonzero(ref_inout < base)[0]
+        best = {}
+        for i, v in zip(fi.tolist(), fv.tolist()):
+            best[i] = min(best.get(i, np.inf), v)
+        assert sorted(best) == improved.tolist()
+        assert all(best[i] == ref_inout[i] for i in improved.tolist())
+        assert set(ref_idx.tolist()) == set(improved.tolist())         # the reference improves the same indices
+
+
 # ------------------------------------------------------------- pieces of the row-sharded runs, on one GPU
 @pytest.mark.parametrize("op,zero", SEMIRINGS)
 def test_spmspv_row_shards_tile_the_result(ctx, oracle, op, zero):

@@ -11,9 +11,9 @@ from graphlily_b200 import datasets, io  # noqa: E402
 SHAPES = {
     "c1": lambda s, dev: datasets.uniform_csr(10000, 10000, 10, seed=1),
     "c2": lambda s, dev: datasets.powerlaw_csr(int(4_194_304 * s), int(4_194_304 * s), int(134_217_728 * s), seed=42, device=dev),
-    "c3": lambda s, dev: datasets.powerlaw_graph(int(107_648 * s), int(13_000_000 * s), seed=3, device=dev),
-    "c4": lambda s, dev: datasets.powerlaw_graph(int(2_449_024 * s), int(124_000_000 * s), seed=4, device=dev),
-    "c5": lambda s, dev: datasets.powerlaw_graph(int(3_072_512 * s), int(117_000_000 * s), seed=5, diagonal=True, device=dev),
+    "c3": lambda s, dev: datasets.c3_gplus(s, device=dev),
+    "c4": lambda s, dev: datasets.c4_ogbn_products(s, device=dev),
+    "c5": lambda s, dev: datasets.c5_orkut(s, device=dev),
     "tiny": lambda s, dev: datasets.powerlaw_graph(4096, 60000, seed=2),
 }
 
