@@ -108,7 +108,7 @@ SIGNATURES = {
     "glb_spmv_host_batch_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_exchange": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp, C.POINTER(Epilogue)]),
     "glb_spmv_exchange_iterate": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, C.c_int, C.c_int, _vp,
-                                            C.POINTER(Epilogue), C.c_int]),
+                                            C.POINTER(Epilogue), C.c_int, C.POINTER(C.c_int)]),
 }
 
 
@@ -437,15 +437,19 @@ class Exchange:
         check(lib.glb_spmv_exchange(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
                                     _ptr(mask), C.byref(epilogue) if epilogue is not None else None))
 
-    def spmv_iterate(self, matrix, op, zero, mask_type, src_vec, dst_vec, n_steps, mask=None, epilogues=None):
+    def spmv_iterate(self, matrix, op, zero, mask_type, src_vec, dst_vec, n_steps, mask=None, epilogues=None, plan=None):
         """glb_spmv_exchange_iterate: ``n_steps`` ping-pong iterations src -> dst -> src ...;
-        ``epilogues``: None or one Epilogue per step."""
+        ``epilogues``: None or one Epilogue per step; ``plan``: None or [(read, written)] per step."""
         eps = None
         if epilogues is not None:
             assert len(epilogues) == n_steps
             eps = (Epilogue * n_steps)(*epilogues)
+        vp = None
+        if plan is not None:
+            assert len(plan) == n_steps
+            vp = (C.c_int * (2 * n_steps))(*[v for pair in plan for v in pair])
         check(lib.glb_spmv_exchange_iterate(self.ctx.handle, matrix.handle, op, zero, mask_type, self.handle, src_vec, dst_vec,
-                                            _ptr(mask), eps, n_steps))
+                                            _ptr(mask), eps, n_steps, vp))
 
     def spmv_host_batch(self, matrix, op, zero, mask_type, x_hosts, mask_hosts, y_hosts):
         """glb_spmv_host_batch_exchange: every rank uploads its slice of each x, NVLink completes it."""

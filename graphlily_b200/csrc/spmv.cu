@@ -608,7 +608,7 @@ struct HostLayout {
     std::vector<uint32_t> flags, chunk_goff, chunk_first, nz_rows, empty_rows, hot_cols;
     std::vector<glb_fixup_t> fix_short, fix_long;
     uint64_t nnz = 0, sb = 0;
-    uint32_t n_chunks = 0, n_groups = 0, tile_k = 0;
+    uint32_t n_chunks = 0, n_groups = 0, tile_k = 0, max_groups = GLB_MAX_GROUPS;
     bool all_nonzero = false;  // no stored value is 0.0f: or-and may skip the value stream
     ~HostLayout() { free(stream); }
 };
@@ -683,7 +683,22 @@ static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *ind
     count.shrink_to_fit();
 
     // ---- chunking: up to 8 groups of 128 non-zeros, at most GLB_ROW_CAP row ends ---------------
-    constexpr uint64_t kChunkMax = uint64_t(GLB_GROUP) * GLB_MAX_GROUPS;
+    // Chunk size: 8 groups (1024 non-zeros) amortise the per-chunk scan and write-back best, but one
+    // warp owns one chunk and a B200 holds 148 SMs x 5 CTAs x 8 warps = 5920 of them at a time: a shard
+    // of a few million non-zeros (the BFS graph; 1/8 of C2 on 8 GPUs) would run 2-3 waves and lose up
+    // to a third of the machine to the last, partly filled wave.  Small shards therefore get smaller
+    // chunks, so that there are at least ~6 waves.  GLB_SPMV_MAX_GROUPS=<1..8> overrides.
+    uint32_t max_groups = GLB_MAX_GROUPS;
+    {
+        const uint64_t want_chunks = 6ull * 5920ull;
+        while (max_groups > 1 && nnz / (uint64_t(GLB_GROUP) * max_groups) < want_chunks) max_groups >>= 1;
+        if (const char *v = getenv("GLB_SPMV_MAX_GROUPS")) {
+            const unsigned long g = strtoul(v, nullptr, 10);
+            if (g >= 1 && g <= GLB_MAX_GROUPS) max_groups = uint32_t(g);
+        }
+    }
+    L.max_groups = max_groups;
+    const uint64_t kChunkMax = uint64_t(GLB_GROUP) * max_groups;
     std::vector<uint64_t> cs;  // chunk start positions (shard-local), plus the end sentinel
     {
         uint64_t cur = 0;
@@ -797,7 +812,7 @@ int glb_csr_format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *in
     std::vector<glb_fixup_t> fix(L.fix_short);
     fix.insert(fix.end(), L.fix_long.begin(), L.fix_long.end());
     out->group = GLB_GROUP;
-    out->max_groups = GLB_MAX_GROUPS;
+    out->max_groups = L.max_groups;
     out->row_cap = GLB_ROW_CAP;
     out->nnz = L.nnz;
     out->n_chunks = L.n_chunks;
@@ -952,7 +967,7 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
                       const float *mask, const glb_spmv_epilogue_t *ep) {
-    return glb_spmv_exchange_iterate(ctx, m, op, zero, mask_type, xc, src_vec, dst_vec, mask, ep, 1);
+    return glb_spmv_exchange_iterate(ctx, m, op, zero, mask_type, xc, src_vec, dst_vec, mask, ep, 1, nullptr);
 }
 
 // n_steps row-sharded iterations x -> y -> x ... over two exchange vectors.  Per step: the SpMV
@@ -966,10 +981,12 @@ int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_t
 // Only the last step is followed by an acquire of its own (so that whatever comes next on the
 // stream sees the complete vector).  All launches are graph-recordable.
 int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
-                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps) {
+                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps, const int *vec_plan) {
     GLB_REQUIRE(xc && xc->connected, "exchange is not connected");
     GLB_REQUIRE(src_vec >= 0 && src_vec < xc->n_vectors && dst_vec >= 0 && dst_vec < xc->n_vectors && src_vec != dst_vec,
                 "bad vector index");
+    for (int k = 0; vec_plan && k < 2 * n_steps; ++k)
+        GLB_REQUIRE(vec_plan[k] >= 0 && vec_plan[k] < xc->n_vectors, "bad vector index in the plan");
     GLB_REQUIRE(m && m->num_rows <= xc->n && m->num_cols <= xc->n, "matrix larger than the exchange vectors");
     GLB_REQUIRE(n_steps >= 0, "negative step count");
     static const int forced = [] {
@@ -980,7 +997,8 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
     const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
     for (int k = 0; k < n_steps; ++k) {
-        const int sv = (k & 1) ? dst_vec : src_vec, dv = (k & 1) ? src_vec : dst_vec;
+        const int sv = vec_plan ? vec_plan[2 * k] : (k & 1) ? dst_vec : src_vec;
+        const int dv = vec_plan ? vec_plan[2 * k + 1] : (k & 1) ? src_vec : dst_vec;
         const float *x = xc->local + size_t(sv) * xc->n;
         float *y = xc->local + size_t(dv) * xc->n;
         const glb_spmv_epilogue_t *ep = eps ? eps + k : nullptr;

@@ -308,9 +308,11 @@ int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_t
  * reads vector src_vec (k even) / dst_vec (k odd) and writes the other one on every rank; eps (NULL or
  * n_steps entries) = the fused epilogue of each step.  Between steps the acquire of the exchange rides
  * in the head of the next SpMV's first kernel instead of a launch of its own; the call ends with the
- * acquire of the last step.  Graph-recordable (glb_graph_begin). */
+ * acquire of the last step.  Graph-recordable (glb_graph_begin).  vec_plan (NULL, or 2 * n_steps vector
+ * indices {read, written} per step) replaces the ping-pong, e.g. a stream of independent input vectors. */
 int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec,
-                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps);
+                              int dst_vec, const float *mask, const glb_spmv_epilogue_t *eps, int n_steps,
+                              const int *vec_plan);
 /* glb_spmv_host_batch for a row-sharded run: called by every rank with the same full-length host
  * vectors; each rank uploads only its 1/nranks slice of x over PCIe, the slices meet over NVLink
  * (exchange vectors 0 and 1 are the two pipeline slots), and y_hosts[k] receives the rank's rows. */

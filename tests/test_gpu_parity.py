@@ -292,6 +292,28 @@ def test_spmspv_empty_frontier_and_rectangular(ctx, oracle):
     check_vec(gpu_spmspv(ctx, csc, 2, 255.0, 0, idx, val, None), oracle.port.spmspv(csc, 2, 255.0, 0, idx, val, None), 2)
 
 
+def test_chunk_sizes_small_shards(ctx, oracle, monkeypatch):
+    # chunks of 1 / 2 / 4 / 8 groups and the automatic choice (small shards get small chunks so that the
+    # launch has enough warps): three semirings, masked and not, against the oracle
+    rng = np.random.default_rng(70)
+    m = datasets.powerlaw_csr(6000, 6000, 150000, seed=23, max_degree=3000)
+    x = rng.integers(0, 3, m.num_cols).astype(np.float32)
+    mask = rng.integers(0, 2, m.num_rows).astype(np.float32)
+    for groups in ("1", "2", "4", "8", None):
+        if groups is None:
+            monkeypatch.delenv("GLB_SPMV_MAX_GROUPS", raising=False)
+        else:
+            monkeypatch.setenv("GLB_SPMV_MAX_GROUPS", groups)
+        A = capi.CsrMatrix(ctx, m)
+        if groups is not None:
+            assert A.info()["chunks"] >= m.nnz // (128 * int(groups))
+        A.close()
+        for op, zero in SEMIRINGS:
+            for mt in (0, 1, 2):
+                got = gpu_spmv(ctx, m, op, zero, mt, x, mask if mt else None)
+                check_vec(got, oracle.port.spmv(m, op, zero, mt, x, mask if mt else None), op)
+
+
 # ----------------------------------------------------------------------------- apply
 def test_apply_golden_fixture(ctx):
     z = golden()

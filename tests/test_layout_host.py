@@ -58,6 +58,23 @@ def test_powerlaw_and_shards(oracle):
     check(oracle, m, 1500, 1500)   # empty shard
 
 
+@pytest.mark.parametrize("groups", ["1", "2", "4", None])
+def test_chunk_sizes(oracle, monkeypatch, groups):
+    # small shards get smaller chunks (more warps per launch); every size the formatter can pick, and its
+    # own choice, through the same sequential model
+    if groups is None:
+        monkeypatch.delenv("GLB_SPMV_MAX_GROUPS", raising=False)
+    else:
+        monkeypatch.setenv("GLB_SPMV_MAX_GROUPS", groups)
+    rng = np.random.default_rng(2)
+    m = datasets.powerlaw_csr(3000, 3000, 60000, seed=7, max_degree=5000)
+    m.data = rng.random(m.nnz).astype(np.float32)
+    L = check(oracle, m, tile_k=64)
+    assert L["max_groups"] == (int(groups) if groups else 1)      # 60 000 non-zeros: the smallest chunks
+    assert L["n_chunks"] >= m.nnz // (128 * L["max_groups"])
+    check(oracle, m, 700, 2100, tile_k=0)
+
+
 def test_boundary_cases(oracle):
     # rows that are exactly one chunk, span several, end on a boundary, or are empty
     rng = np.random.default_rng(2)
