@@ -119,6 +119,8 @@ struct glb_csr_s {
     bool all_nonzero = false;      // no stored value is 0.0f (or-and skips the value stream)
     int smem_carveout_pct = 20;
     uint32_t tile_threads = 0;     // > 0: persistent shared-memory-tile kernel with that many threads per CTA
+    // progressive push of a row-sharded run over a multicast exchange (spmv.cu: push_block_when_complete)
+    uint32_t *push_bits = nullptr, *push_lo = nullptr, *push_count = nullptr;
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
     float *dx2 = nullptr, *dmask2 = nullptr, *dy2 = nullptr;  // second slot of glb_spmv_host_batch
@@ -182,9 +184,19 @@ void glb_ctx_retain(glb_ctx_t ctx);
 void glb_ctx_release(glb_ctx_t ctx);  // child destroyed; frees the context if it was destroyed meanwhile
 
 // launchers (defined in the .cu files)
+// Multicast destination of a row-sharded launch: y_mc = multicast mapping of y.  progressive: finished
+// blocks of rows are pushed from inside the main kernel, the fix-up kernel sends its rows and publishes
+// the epoch (*published tells whether it did -- it is not launched when it has no rows); otherwise every
+// row is stored to y_mc by the write-back that produces it and the caller publishes.
+struct GlbSpmvMc {
+    float *y_mc;
+    bool progressive;
+    uint32_t *pub_flags_mc, *pub_state;
+    int rank;
+};
 // `wait`: acquire of the previous step's exchange, folded into the head of the launch's first kernel (or NULL)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc,
-                    const GlbXchgWait *wait);
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
+                    const GlbXchgWait *wait, bool *published);
 
 #endif  // GLB_INTERNAL_H_

@@ -74,6 +74,19 @@ struct SpmvParams {
     float *y_peer[GLB_MAX_PEERS];  // the same vector on the other GPUs of a row-sharded run (peer-mapped memory)
     int n_peers;
     float *y_mc;  // or its multicast mapping: one store lands on every GPU (NVSwitch multicast)
+    int mc_rows_in_main;  // 1: the main kernel's write-back stores every row to y_mc itself (GLB_XCHG_MC=fused)
+    // Progressive push (multicast exchange, default): the CTA that completes a block of kPushCtas
+    // consecutive CTAs copies the block's finished rows to y_mc in 16-byte multimem.st stores while
+    // later blocks still compute; rows the fix-up kernel finishes are sent by that kernel, whose last
+    // CTA then publishes the epoch.
+    const uint32_t *push_bits;  // bit (row - push_row_base) = the main kernel writes this row
+    const uint32_t *push_lo;    // row boundaries of the push blocks (n_push_blocks + 1)
+    uint32_t *push_count;       // CTAs finished per push block (self-resetting)
+    uint32_t push_row_base;
+    uint32_t n_ctas;
+    uint32_t *pub_flags_mc;     // fix-up kernel: multicast mapping of the flag words (NULL: do not publish)
+    uint32_t *pub_state;        // exchange state: [0] epoch, [1] CTA ticket
+    int pub_rank;
     float *head_carry;
     float *tail_carry;
     uint32_t n_chunks;
@@ -116,7 +129,7 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
 
 // Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
 // spmv_module.h:513-532), then the optional fused eWiseAdd and dense assign.
-template <int OP>
+template <int OP, bool IN_MAIN = true>
 __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, float total) {
     float v = Semi<OP>::with_zero(P.zero, total);
     if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
@@ -128,7 +141,7 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
     P.y[row] = v;
     // fused exchange: the row also goes straight into every peer's copy over NVLink, so the
     // allgather of the next iteration's x rides inside the SpMV write-back
-    if (P.y_mc) {
+    if (P.y_mc && (!IN_MAIN || P.mc_rows_in_main)) {
         asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.y_mc + row), "f"(v) : "memory");
     } else {
 #pragma unroll
@@ -296,6 +309,48 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
     }
 }
 
+constexpr uint32_t kPushCtas = 64;  // CTAs per push block: 512 chunks, ~64 KB of y on a 32-nnz/row matrix
+
+// Tail of the main kernels in a row-sharded run over a multicast exchange: count this CTA as done;
+// the CTA that completes its push block sends the block's rows (those the main kernel writes: the
+// push_bits filter leaves chunk-crossing and empty rows to the fix-up kernel) to every rank.
+__device__ __forceinline__ void push_block_when_complete(const SpmvParams &P) {
+    __shared__ uint32_t s_last;
+    const uint32_t blk = blockIdx.x / kPushCtas;
+    __syncthreads();  // every warp of the CTA has written its rows
+    if (threadIdx.x == 0) {
+        const uint32_t first = blk * kPushCtas;
+        const uint32_t in_block = P.n_ctas - first < kPushCtas ? P.n_ctas - first : kPushCtas;
+        __threadfence();
+        s_last = atomicAdd(P.push_count + blk, 1u) == in_block - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();  // the other CTAs' rows (counted above) are visible from here on
+    const uint32_t lo = P.push_lo[blk], hi = P.push_lo[blk + 1];
+    for (uint32_t r0 = (lo & ~3u) + 4u * threadIdx.x; r0 < hi; r0 += 4u * kThreads) {
+        const uint32_t rel = r0 - P.push_row_base;
+        uint32_t bits = (__ldg(P.push_bits + (rel >> 5)) >> (rel & 31u)) & 0xfu;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r0 + i < lo || r0 + i >= hi) bits &= ~(1u << i);
+        if (bits == 0xfu) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(P.y + r0));
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.y_mc + r0), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w)
+                         : "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (bits & (1u << i)) {
+                    const float v = __ldcg(P.y + r0 + i);
+                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.y_mc + r0 + i), "f"(v) : "memory");
+                }
+        }
+    }
+    if (threadIdx.x == 0) P.push_count[blk] = 0;  // ready for the next launch
+}
+
 // Variant L1: one chunk per warp, hot x lines kept in L1 by the cache hints.
 template <int OP, bool MASKED>
 __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
@@ -303,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kerne
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk >= P.n_chunks) return;  // warp-uniform; no block-wide barrier below
-    process_chunk<OP, false, 0, MASKED>(P, chunk, lane, stage_all[wib], 0u);
+    if (chunk < P.n_chunks) process_chunk<OP, false, 0, MASKED>(P, chunk, lane, stage_all[wib], 0u);  // warp-uniform
+    if (P.push_bits) push_block_when_complete(P);
 }
 
 // Variant BITS (or-and): as above with x packed to a bitmap by pack_bits_kernel.
@@ -314,8 +369,8 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk >= P.n_chunks) return;
-    process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS, MASKED>(P, chunk, lane, stage_all[wib], 0u);
+    if (chunk < P.n_chunks) process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS, MASKED>(P, chunk, lane, stage_all[wib], 0u);
+    if (P.push_bits) push_block_when_complete(P);
 }
 
 // xbits: bit w = truth value of the x entry that stored column word w refers to.  Words below
@@ -414,45 +469,61 @@ __global__ void __launch_bounds__(kThreads) gather_hot_kernel(const float *x, co
     if (i < n) hot_x[i] = __ldcg(x + __ldg(hot_cols + i));
 }
 
-// Rows touching a chunk boundary: total = tail[c_begin .. c_last] (+) head[c_end].
+// Rows touching a chunk boundary: total = tail[c_begin .. c_last] (+) head[c_end].  In a row-sharded
+// run over a multicast exchange these rows (and the empty ones) go to every rank from here, and the
+// CTA that finishes last publishes the epoch of the step (the main kernel's pushes completed with
+// that kernel, before this one started).
 template <int OP>
 __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P, uint32_t nb_short, uint32_t nb_long) {
     const unsigned lane = threadIdx.x & 31u;
     if (blockIdx.x < nb_short) {
         const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-        if (i >= P.n_fix_short) return;
-        const glb_fixup_t e = P.fix_short[i];
-        const uint32_t c_end = e.c_end & ~GLB_FLAG;
-        const bool has_head = (e.c_end & GLB_FLAG) != 0;
-        const uint32_t c_stop = has_head ? c_end : c_end + 1;  // exclusive end of the tail range
-        float t = Semi<OP>::ident();
-        for (uint32_t c = e.c_begin; c < c_stop; ++c) t = Semi<OP>::add(t, P.tail_carry[c]);
-        if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
-        finish_row<OP>(P, e.row, t);
+        if (i < P.n_fix_short) {
+            const glb_fixup_t e = P.fix_short[i];
+            const uint32_t c_end = e.c_end & ~GLB_FLAG;
+            const bool has_head = (e.c_end & GLB_FLAG) != 0;
+            const uint32_t c_stop = has_head ? c_end : c_end + 1;  // exclusive end of the tail range
+            float t = Semi<OP>::ident();
+            for (uint32_t c = e.c_begin; c < c_stop; ++c) t = Semi<OP>::add(t, P.tail_carry[c]);
+            if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
+            finish_row<OP, false>(P, e.row, t);
+        }
     } else if (blockIdx.x < nb_short + nb_long) {
         const uint32_t i = (blockIdx.x - nb_short) * kWarpsPerBlock + (threadIdx.x >> 5);
-        if (i >= P.n_fix_long) return;
-        const glb_fixup_t e = P.fix_long[i];
-        const uint32_t c_end = e.c_end & ~GLB_FLAG;
-        const bool has_head = (e.c_end & GLB_FLAG) != 0;
-        const uint32_t c_stop = has_head ? c_end : c_end + 1;
-        float t = Semi<OP>::ident();
-        for (uint32_t c = e.c_begin + lane; c < c_stop; c += 32) t = Semi<OP>::add(t, P.tail_carry[c]);
+        if (i < P.n_fix_long) {  // warp-uniform
+            const glb_fixup_t e = P.fix_long[i];
+            const uint32_t c_end = e.c_end & ~GLB_FLAG;
+            const bool has_head = (e.c_end & GLB_FLAG) != 0;
+            const uint32_t c_stop = has_head ? c_end : c_end + 1;
+            float t = Semi<OP>::ident();
+            for (uint32_t c = e.c_begin + lane; c < c_stop; c += 32) t = Semi<OP>::add(t, P.tail_carry[c]);
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) t = Semi<OP>::add(t, __shfl_xor_sync(kFull, t, d));
-        if (lane == 0) {
-            if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
-            finish_row<OP>(P, e.row, t);
+            for (int d = 16; d >= 1; d >>= 1) t = Semi<OP>::add(t, __shfl_xor_sync(kFull, t, d));
+            if (lane == 0) {
+                if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
+                finish_row<OP, false>(P, e.row, t);
+            }
         }
     } else {
         const uint32_t i = (blockIdx.x - nb_short - nb_long) * kThreads + threadIdx.x;
-        if (i >= P.n_empty) return;
-        finish_row<OP>(P, P.empty_rows[i], Semi<OP>::ident());
+        if (i < P.n_empty) finish_row<OP, false>(P, P.empty_rows[i], Semi<OP>::ident());
+    }
+    if (P.pub_flags_mc) {  // uniform
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(P.pub_state + 1, 1u) == gridDim.x - 1) {
+            P.pub_state[1] = 0;
+            __threadfence_system();
+            const uint32_t epoch = P.pub_state[0] + 1;
+            P.pub_state[0] = epoch;
+            asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(P.pub_flags_mc + P.pub_rank), "r"(epoch) : "memory");
+        }
     }
 }
 
 template <int OP>
-int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
+int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
+    P.n_ctas = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (ctx->timing) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
@@ -503,8 +574,10 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, const SpmvParams &P) {
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
     const uint32_t nb_long = (P.n_fix_long + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const uint32_t nb_empty = (P.n_empty + kThreads - 1) / kThreads;
-    if (nb_short + nb_long + nb_empty)
+    if (nb_short + nb_long + nb_empty) {
         spmv_fixup_kernel<OP><<<nb_short + nb_long + nb_empty, kThreads, 0, ctx->stream>>>(P, nb_short, nb_long);
+        if (published) *published = P.pub_flags_mc != nullptr;
+    }
     if (ctx->timing) {
         GLB_CUDA(cudaEventRecord(ev[2], ctx->stream));
         for (auto e : ev) ctx->timing_events.push_back(e);
@@ -531,10 +604,24 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 }  // namespace
 
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
-                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, float *y_mc,
-                    const GlbXchgWait *wait) {
+                    float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
+                    const GlbXchgWait *wait, bool *published) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
+    if (published) *published = false;
+    float *y_mc = mc ? mc->y_mc : nullptr;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y_mc)) & 15u) == 0;
+    if (mc && mc->progressive && m->push_bits && m->n_chunks && !m->tile_threads && aligned16) {
+        P.push_bits = m->push_bits;
+        P.push_lo = m->push_lo;
+        P.push_count = m->push_count;
+        P.push_row_base = m->row_begin & ~31u;
+        P.pub_flags_mc = mc->pub_flags_mc;
+        P.pub_state = mc->pub_state;
+        P.pub_rank = mc->rank;
+    } else if (mc) {
+        P.mc_rows_in_main = 1;
+    }
     GlbXchgWait w;
     memset(&w, 0, sizeof(w));
     if (wait) w = *wait;
@@ -591,9 +678,9 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_empty = m->n_empty;
     P.n_nz_rows = m->n_nz_rows;
     switch (op) {
-        case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, m, P);
-        case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);
-        case GLB_OP_ADD_MIN: return launch_op<GLB_OP_ADD_MIN>(ctx, m, P);
+        case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, m, P, published);
+        case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, m, P, published);
+        case GLB_OP_ADD_MIN: return launch_op<GLB_OP_ADD_MIN>(ctx, m, P, published);
     }
     glb_set_error("glb_spmv: invalid semiring op %d", op);
     return GLB_EINVAL;
@@ -905,6 +992,26 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     //   GLB_SPMV_BITS=0              or-and SpMV gathers fp32 x like the other semirings (default 1: bitmap)
     if (!rc && env_u32("GLB_SPMV_BITS", 1) && L.n_chunks)
         rc = upload<uint32_t>(ctx, &m->xbits, nullptr, 0, (size_t(L.tile_k) + num_cols + 31) / 32 + 1, &bytes);
+    if (!rc && L.n_chunks) {
+        // progressive push of a row-sharded run (push_block_when_complete): which rows the main kernel
+        // writes, and the row boundaries of the blocks of kPushCtas consecutive CTAs
+        const uint32_t base = row_begin & ~31u;
+        std::vector<uint32_t> bits((size_t(row_end - base) + 31) / 32 + 1, 0u);
+        for (uint32_t r : L.nz_rows) bits[(r - base) >> 5] |= 1u << ((r - base) & 31u);
+        for (const auto &e : L.fix_short) bits[(e.row - base) >> 5] &= ~(1u << ((e.row - base) & 31u));
+        for (const auto &e : L.fix_long) bits[(e.row - base) >> 5] &= ~(1u << ((e.row - base) & 31u));
+        const uint32_t n_ctas = (L.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const uint32_t n_blocks = (n_ctas + kPushCtas - 1) / kPushCtas;
+        std::vector<uint32_t> lo(n_blocks + 1, row_end);
+        for (uint32_t j = 0; j < n_blocks; ++j) {
+            const uint32_t k = L.chunk_first[size_t(j) * kPushCtas * kWarpsPerBlock] & ~GLB_FLAG;
+            lo[j] = k < L.nz_rows.size() ? L.nz_rows[k] : row_end;
+        }
+        lo[0] = row_begin;
+        rc = upload(ctx, &m->push_bits, bits.data(), bits.size(), bits.size(), &bytes);
+        if (!rc) rc = upload(ctx, &m->push_lo, lo.data(), lo.size(), lo.size(), &bytes);
+        if (!rc) rc = upload<uint32_t>(ctx, &m->push_count, nullptr, 0, n_blocks, &bytes);
+    }
     if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -924,6 +1031,7 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaFree(m->stream); cudaFree(m->flags); cudaFree(m->chunk_goff); cudaFree(m->chunk_first); cudaFree(m->nz_rows);
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
     cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits);
+    cudaFree(m->push_bits); cudaFree(m->push_lo); cudaFree(m->push_count);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
     cudaFree(m->dx2); cudaFree(m->dmask2); cudaFree(m->dy2);
     glb_ctx_release(m->ctx);
@@ -962,7 +1070,7 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr, nullptr);
 }
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
@@ -993,7 +1101,6 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         const char *v = getenv("GLB_XCHG_MC");
         return !v ? 0 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : 0;
     }();
-    const bool mc_fused = xc->mc && forced == 2;
     const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
     for (int k = 0; k < n_steps; ++k) {
@@ -1005,17 +1112,28 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
         if (rc) return rc;
         const GlbXchgWait *w = k > 0 ? &wait : nullptr;
-        if (xc->mc && !mc_fused) {
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w);
+        if (xc->mc && xc->nranks > 1 && forced == 1) {
+            // separate push kernel after the SpMV kernels
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr);
             if (!rc) rc = glb_xchg_push(ctx, xc, dv, m->row_begin, size_t(m->row_end - m->row_begin));
-        } else if (xc->mc) {
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, xc->mc + size_t(dv) * xc->n, w);
-            if (!rc) rc = glb_xchg_signal(ctx, xc, false);
+        } else if (xc->mc && xc->nranks > 1) {
+            // default: completed blocks of rows are pushed from inside the main kernel while later blocks
+            // compute, the fix-up kernel sends its own rows and publishes (GLB_XCHG_MC=fused: every row is
+            // stored to the multicast address by the write-back that produces it)
+            GlbSpmvMc mc;
+            mc.y_mc = xc->mc + size_t(dv) * xc->n;
+            mc.progressive = forced != 2;
+            mc.pub_flags_mc = xc->mc_flags;
+            mc.pub_state = xc->d_state;
+            mc.rank = xc->rank;
+            bool published = false;
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, &published);
+            if (!rc && !published) rc = glb_xchg_signal(ctx, xc, false);
         } else {
             int n_peers = 0;
             for (int r = 0; r < xc->nranks; ++r)
                 if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w, nullptr);
             if (!rc) rc = glb_xchg_signal(ctx, xc, false);
         }
         if (rc) return rc;
