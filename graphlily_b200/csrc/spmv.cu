@@ -1099,7 +1099,7 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
     GLB_REQUIRE(n_steps >= 0, "negative step count");
     static const int forced = [] {
         const char *v = getenv("GLB_XCHG_MC");
-        return !v ? 0 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : 0;
+        return !v ? 1 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : !strcmp(v, "progressive") ? 3 : 1;
     }();
     const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
@@ -1113,16 +1113,20 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         if (rc) return rc;
         const GlbXchgWait *w = k > 0 ? &wait : nullptr;
         if (xc->mc && xc->nranks > 1 && forced == 1) {
-            // separate push kernel after the SpMV kernels
+            // default: one push kernel after the SpMV kernels (all SMs store the finished slice in 16-byte
+            // multimem.st; its last CTA publishes)
             rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr);
             if (!rc) rc = glb_xchg_push(ctx, xc, dv, m->row_begin, size_t(m->row_end - m->row_begin));
         } else if (xc->mc && xc->nranks > 1) {
-            // default: completed blocks of rows are pushed from inside the main kernel while later blocks
-            // compute, the fix-up kernel sends its own rows and publishes (GLB_XCHG_MC=fused: every row is
-            // stored to the multicast address by the write-back that produces it)
+            // GLB_XCHG_MC=progressive: completed blocks of rows are pushed from inside the main kernel while
+            // later blocks compute, the fix-up kernel sends its own rows and publishes; =fused: every row is
+            // stored to the multicast address by the write-back that produces it.  Both overlap the transfer
+            // with the kernel and both measured SLOWER than the separate push kernel (2 GPUs, C2: main kernel
+            // 242 us vs 185 us, fix-up 29 us vs 8 us): remote stores issued from an SM that also runs compute
+            // CTAs hold up that SM's L1 miss path, which is what bounds the SpMV.
             GlbSpmvMc mc;
             mc.y_mc = xc->mc + size_t(dv) * xc->n;
-            mc.progressive = forced != 2;
+            mc.progressive = forced == 3;
             mc.pub_flags_mc = xc->mc_flags;
             mc.pub_state = xc->d_state;
             mc.rank = xc->rank;
