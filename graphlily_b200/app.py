@@ -19,7 +19,7 @@ import copy
 import numpy as np
 
 from . import capi, io
-from .capi import Epilogue
+from .capi import Epilogue, SpmspvEpilogue, SpmspvNext
 from .module import (AssignVectorDenseModule, AssignVectorSparseModule, SpMSpVModule, SpMVModule, eWiseAddModule)
 
 ArithmeticSemiring = (capi.OP_MUL_ADD, 1.0, 0.0)
@@ -166,6 +166,38 @@ class ModuleCollection:
         capi.dense_to_sparse(self.ctx, dense, n, zero, list_buf)
         self.SpMV_.vector_buf, self.SpMV_.results_buf = dense, self.SpMV_.vector_buf
 
+    # -- push direction on one GPU: a level is ONE launch (glb_spmspv_fused) -----------------------
+    def _home_lists(self):
+        """Canonical roles of the two sparse-list buffers at the start of a run (lower address = vector),
+        so that the recorded sequence of an earlier run with the same arguments is found again."""
+        m = self.SpMSpV_
+        if m.vector_buf.ptr > m.results_buf.ptr:
+            m.vector_buf, m.results_buf = m.results_buf, m.vector_buf
+
+    def _dense_pair(self, fill):
+        """The two dense vectors the pull levels ping-pong through (the SpMV module's vector / results),
+        in canonical order, filled with ``fill``: the push level that stops pushing builds the input of
+        the first pull level in one of them."""
+        n, sp = self.matrix_num_rows_, self.SpMV_
+        for name in ("vector_buf", "results_buf"):
+            b = getattr(sp, name)
+            if b is None or not b.ptr or b.nbytes != 4 * n:
+                setattr(sp, name, self.ctx.alloc(4 * n))
+        sp.home_buffers()
+        for b in (sp.vector_buf, sp.results_buf):
+            capi.check(capi.lib.glb_buffer_fill_f32(self.ctx.handle, b.ptr, float(fill), n))
+        return [sp.vector_buf, sp.results_buf]
+
+    @property
+    def push_iterations_(self):
+        """Levels the last pull_push run spent pushing.  With the decision taken on the device it is read
+        back on demand (a blocking 16-byte copy), not on the critical path of the run."""
+        v = self.__dict__.get("push_iterations_host_")
+        if v is not None:
+            return v
+        levels = self.SpMSpV_.matrix.push_state()[1]
+        return levels if self.__dict__.get("last_num_iterations_", 2) >= 2 else 1
+
     # -- launch replay: the iteration loop of an app is a fixed launch sequence ------------------
     use_graphs_ = True
     _GRAPH_CACHE = 8
@@ -287,6 +319,7 @@ class BFS(ModuleCollection):
     def _push_setup(self, source):
         self._begin_run()
         self._push_begin()
+        self._home_lists()
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [1.0]))
         self.SpMSpV_.set_mask_constant(0.0, source, 1.0)      # distance, bfs.h:138-141
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
@@ -300,15 +333,42 @@ class BFS(ModuleCollection):
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.vector_buf)
         self.SparseAssign_.run(float(it + 1))
 
-    def push(self, source, num_iterations):
+    def _push_level_fused(self, lists, level, nxt=None):
+        """One push level in one launch: SpMSpV on lists[(level - 1) & 1] -> lists[level & 1] with the
+        sparse assign distance[row] = level + 1 (bfs.h:147-151) fused into the kernel."""
+        dist = self.SpMSpV_.mask_buf
+        ep = SpmspvEpilogue(capi.SPMSPV_EP_ASSIGN, dist.ptr, float(level + 1), None)
+        self.SpMSpV_.run_with(lists[(level - 1) & 1], lists[level & 1], ep, nxt)
+
+    def push(self, source, num_iterations, fused=True):
         """bfs.h:129-157"""
         self._push_setup(source)
-        for it in range(1, num_iterations + 1):
-            self._push_step(it)
+        if not fused or self.world_ > 1:
+            for it in range(1, num_iterations + 1):
+                self._push_step(it)
+            return self.SpMSpV_.send_mask_device_to_host()
+        lists = [self.SpMSpV_.vector_buf, self.SpMSpV_.results_buf]
+
+        def launches():
+            for level in range(1, num_iterations + 1):
+                self._push_level_fused(lists, level)
+
+        self._replay(("bfs_push", num_iterations, lists[0].ptr, lists[1].ptr, self.SpMSpV_.mask_buf.ptr), launches)
+        self.SpMSpV_.vector_buf, self.SpMSpV_.results_buf = lists[num_iterations & 1], lists[(num_iterations + 1) & 1]
         return self.SpMSpV_.send_mask_device_to_host()
 
     def pull_push(self, source, num_iterations, threshold=0.05, fused=True):
-        """bfs.h:160-219: push while the frontier is sparse, then pull."""
+        """bfs.h:160-219: push while the frontier is sparse, then pull.
+
+        On one GPU (fused, launch replay on) the whole run is ONE recorded sequence with no host
+        synchronisation between the start vectors and the read-back of the result: every push level is
+        one launch that also takes the reference's decision (bfs.h:186-190) on the device and feeds it
+        to the IF / ELSE node of the next level; the level that stops pushing scatters its frontier
+        into the dense input of the first pull level.  Otherwise (row-sharded, unfused, replay off)
+        the host reads the frontier size after every push level like the reference does."""
+        self.last_num_iterations_ = num_iterations
+        if fused and self.world_ == 1 and self.use_graphs_ and num_iterations >= 2:
+            return self._pull_push_device(source, num_iterations, threshold)
         n = self.matrix_num_rows_
         self._push_setup(source)
         it = 1
@@ -318,7 +378,7 @@ class BFS(ModuleCollection):
             it += 1
             if not (it < num_iterations and float(vector_nnz) / n < threshold):
                 break
-        self.push_iterations_ = it - 1
+        self.push_iterations_host_ = it - 1
         # switch: the last frontier becomes the dense SpMV input, on the device
         self.SpMV_.bind_mask_buf(self.SpMSpV_.mask_buf)
         if self.world_ == 1:   # (sharded: the frontier already sits in vector_buf, it travelled as a dense vector)
@@ -328,6 +388,38 @@ class BFS(ModuleCollection):
             capi.sparse_to_dense(self.ctx, self.SpMSpV_.vector_buf, self.SpMV_.vector_buf, n, LogicalSemiring[2])
         self._pull_loop(it, num_iterations, fused)
         self._gather(self.SpMSpV_.mask_buf, n)    # the pull levels updated the distance shard by shard
+        return self.SpMSpV_.send_mask_device_to_host()
+
+    def _pull_push_device(self, source, num_iterations, threshold):
+        n, ctx = self.matrix_num_rows_, self.ctx
+        self.push_iterations_host_ = None
+        self._push_setup(source)
+        dist = self.SpMSpV_.mask_buf
+        self.SpMV_.bind_mask_buf(dist)
+        dense = self._dense_pair(LogicalSemiring[2])
+        lists = [self.SpMSpV_.vector_buf, self.SpMSpV_.results_buf]
+        self.SpMSpV_.matrix.reset_levels()
+
+        def launches():
+            conds = {level: ctx.cond_create() for level in range(2, num_iterations + 1)}
+
+            def push_level(level):
+                nxt = None
+                if level < num_iterations:   # a level follows: this launch decides its direction
+                    nxt = SpmspvNext(int(level + 1 >= num_iterations), float(threshold), n, conds[level + 1],
+                                     capi.SPMSPV_DENSE_SCATTER, dense[(level + 1) & 1].ptr, None, n)
+                self._push_level_fused(lists, level, nxt)
+
+            def pull_level(level):
+                ep = Epilogue(0, 0.0, dist.ptr, float(level + 1), capi.MASK_WRITE_TO_ONE)
+                self.SpMV_.run_with(dense[level & 1], dist, dense[(level + 1) & 1], ep)
+
+            push_level(1)
+            for level in range(2, num_iterations + 1):
+                ctx.branch(conds[level], lambda lv=level: push_level(lv), lambda lv=level: pull_level(lv))
+
+        self._replay(("bfs_pull_push", num_iterations, float(threshold), lists[0].ptr, lists[1].ptr, dist.ptr,
+                      dense[0].ptr, dense[1].ptr), launches)
         return self.SpMSpV_.send_mask_device_to_host()
 
 
@@ -473,23 +565,54 @@ class SSSP(ModuleCollection):
     def _push_setup(self, source):
         self._begin_run()
         self._push_begin()
+        self._home_lists()
         self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [0.0]))
         self.SpMSpV_.set_mask_constant(self.semiring_[2], source, 0.0)   # distance, sssp.h:172-176
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.results_buf)
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
         self.SparseAssign_.bind_new_frontier_buf(self.SpMSpV_.vector_buf)
 
-    def push(self, source, num_iterations):
+    def _frontier_lists(self):
+        """The two lists the frontier alternates between in the fused push levels (the kernel reads the
+        old frontier while it appends the new one, so they cannot be one buffer as in sssp.h:185-187)."""
+        cap = self.SpMSpV_.get_num_cols() + 1
+        extra = self.__dict__.get("frontier2_buf_")
+        if extra is None or not extra.ptr or extra.nbytes != 8 * cap:
+            extra = self.frontier2_buf_ = self.ctx.alloc(8 * cap)
+        return [self.SpMSpV_.vector_buf, extra]
+
+    def _push_level_fused(self, lists, level, nxt=None):
+        """One push level in one launch: SpMSpV on lists[(level - 1) & 1] -> results, with the relax of
+        the distance vector and the new frontier -> lists[level & 1] (sssp.h:178-190) fused into the kernel."""
+        ep = SpmspvEpilogue(capi.SPMSPV_EP_RELAX, self.SpMSpV_.mask_buf.ptr, 0.0, lists[level & 1].ptr)
+        self.SpMSpV_.run_with(lists[(level - 1) & 1], self.SpMSpV_.results_buf, ep, nxt)
+
+    def push(self, source, num_iterations, fused=True):
         """sssp.h:169-194"""
         self._push_setup(source)
-        for _ in range(num_iterations):
-            self.SpMSpV_.run()
-            self._exchange_frontier(self.SpMSpV_.results_buf, self.semiring_[2])
-            self.SparseAssign_.run()
+        if not fused or self.world_ > 1:
+            for _ in range(num_iterations):
+                self.SpMSpV_.run()
+                self._exchange_frontier(self.SpMSpV_.results_buf, self.semiring_[2])
+                self.SparseAssign_.run()
+            return self.SpMSpV_.send_mask_device_to_host()
+        lists = self._frontier_lists()
+
+        def launches():
+            for level in range(1, num_iterations + 1):
+                self._push_level_fused(lists, level)
+
+        self._replay(("sssp_push", num_iterations, lists[0].ptr, lists[1].ptr, self.SpMSpV_.results_buf.ptr,
+                      self.SpMSpV_.mask_buf.ptr), launches)
         return self.SpMSpV_.send_mask_device_to_host()
 
     def pull_push(self, source, num_iterations, threshold=0.05, fused=True):
-        """sssp.h:197-243"""
+        """sssp.h:197-243.  On one GPU the run is one recorded sequence with the direction decided on the
+        device (see BFS.pull_push); the level that stops pushing copies the distance vector into the
+        input of the first pull level (sssp.h:219-222)."""
+        self.last_num_iterations_ = num_iterations
+        if fused and self.world_ == 1 and self.use_graphs_ and num_iterations >= 2:
+            return self._pull_push_device(source, num_iterations, threshold)
         n = self.matrix_num_rows_
         self._push_setup(source)
         it = 1
@@ -501,11 +624,45 @@ class SSSP(ModuleCollection):
             it += 1
             if not (it < num_iterations and float(vector_nnz) / n < threshold):
                 break
-        self.push_iterations_ = it - 1
+        self.push_iterations_host_ = it - 1
         # switch: the distance vector becomes the SpMV input (device copy, no host round trip)
         self.SpMV_.home_buffers()
         if self.SpMV_.vector_buf is None or self.SpMV_.vector_buf.nbytes < 4 * n:
             self.SpMV_.vector_buf = self.ctx.zeros_f32(n)
         capi.d2d(self.ctx, self.SpMV_.vector_buf, self.SpMSpV_.mask_buf, 4 * n)
         self._pull_loop(it, num_iterations, fused)
+        return self.SpMV_.send_vector_device_to_host()
+
+    def _pull_push_device(self, source, num_iterations, threshold):
+        n, ctx = self.matrix_num_rows_, self.ctx
+        self.push_iterations_host_ = None
+        self._push_setup(source)
+        dist = self.SpMSpV_.mask_buf
+        dense = self._dense_pair(self.semiring_[2])
+        lists = self._frontier_lists()
+        self.SpMSpV_.matrix.reset_levels()
+
+        def launches():
+            conds = {level: ctx.cond_create() for level in range(2, num_iterations + 1)}
+
+            def push_level(level):
+                nxt = None
+                if level < num_iterations:
+                    nxt = SpmspvNext(int(level + 1 >= num_iterations), float(threshold), n, conds[level + 1],
+                                     capi.SPMSPV_DENSE_COPY, dense[(level + 1) & 1].ptr, dist.ptr, n)
+                self._push_level_fused(lists, level, nxt)
+
+            def pull_level(level):
+                self.SpMV_.run_with(dense[level & 1], None, dense[(level + 1) & 1])
+
+            push_level(1)
+            for level in range(2, num_iterations + 1):
+                ctx.branch(conds[level], lambda lv=level: push_level(lv), lambda lv=level: pull_level(lv))
+
+        self._replay(("sssp_pull_push", num_iterations, float(threshold), lists[0].ptr, lists[1].ptr,
+                      self.SpMSpV_.results_buf.ptr, dist.ptr, dense[0].ptr, dense[1].ptr), launches)
+        # the last level is always a pull level (sssp.h:214: iter < num_iterations): its output is the result
+        last = dense[(num_iterations + 1) & 1]
+        other = dense[num_iterations & 1]
+        self.SpMV_.vector_buf, self.SpMV_.results_buf = last, other
         return self.SpMV_.send_vector_device_to_host()

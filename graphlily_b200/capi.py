@@ -32,6 +32,21 @@ class Epilogue(C.Structure):
                 ("assign_val", C.c_float), ("assign_mask_type", C.c_int)]
 
 
+class SpmspvEpilogue(C.Structure):
+    """glb_spmspv_epilogue_t"""
+    _fields_ = [("mode", C.c_int), ("inout", _vp), ("val", C.c_float), ("new_frontier", _vp)]
+
+
+class SpmspvNext(C.Structure):
+    """glb_spmspv_next_t"""
+    _fields_ = [("force_stop", C.c_int), ("threshold", C.c_float), ("num_vertices", C.c_uint32), ("cond_next", C.c_uint64),
+                ("dense_mode", C.c_int), ("dense", _vp), ("dense_src", _vp), ("dense_len", C.c_uint32)]
+
+
+SPMSPV_EP_NONE, SPMSPV_EP_ASSIGN, SPMSPV_EP_RELAX = 0, 1, 2
+SPMSPV_DENSE_NONE, SPMSPV_DENSE_SCATTER, SPMSPV_DENSE_COPY = 0, 1, 2
+
+
 class HostLayout(C.Structure):
     """glb_host_layout_t"""
     _fields_ = [("group", C.c_uint32), ("max_groups", C.c_uint32), ("row_cap", C.c_uint32), ("nnz", C.c_uint64),
@@ -77,6 +92,10 @@ SIGNATURES = {
     "glb_spmv_host": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "glb_spmv_host_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glb_spmspv": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "glb_spmspv_fused": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.POINTER(SpmspvEpilogue),
+                                   C.POINTER(SpmspvNext)]),
+    "glb_spmspv_push_state": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "glb_spmspv_reset_levels": (C.c_int, [_vp, _vp]),
     "glb_sparse_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
     "glb_sparse_to_dense_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float]),
     "glb_dense_to_sparse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, _vp]),
@@ -92,6 +111,10 @@ SIGNATURES = {
     "glb_allgather_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
     "glb_graph_begin": (C.c_int, [_vp]),
     "glb_graph_end": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "glb_graph_cond_create": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "glb_graph_branch_begin": (C.c_int, [_vp, C.c_uint64]),
+    "glb_graph_branch_else": (C.c_int, [_vp]),
+    "glb_graph_branch_end": (C.c_int, [_vp]),
     "glb_graph_launch": (C.c_int, [_vp, _vp]),
     "glb_graph_destroy": (C.c_int, [_vp]),
     "glb_xchg_create": (C.c_int, [_vp, C.c_uint32, C.c_int, C.POINTER(_vp)]),
@@ -204,6 +227,22 @@ class Context:
         h = _vp()
         check(lib.glb_graph_end(self.handle, C.byref(h)))
         return Graph(self, h)
+
+    def cond_create(self):
+        """A device-side condition of the sequence being recorded (glb_graph_cond_create)."""
+        c = C.c_uint64(0)
+        check(lib.glb_graph_cond_create(self.handle, C.byref(c)))
+        return c.value
+
+    def branch(self, cond, if_arm, else_arm):
+        """Record ``if_arm()`` / ``else_arm()`` as the two arms of an IF / ELSE node on ``cond``."""
+        check(lib.glb_graph_branch_begin(self.handle, cond))
+        try:
+            if_arm()
+            check(lib.glb_graph_branch_else(self.handle))
+            else_arm()
+        finally:
+            check(lib.glb_graph_branch_end(self.handle))
 
     # ---- buffers ------------------------------------------------------------------
     def alloc(self, nbytes):
@@ -493,8 +532,20 @@ class CscMatrix:
         self.ctx, self.handle = ctx, h
         self.num_rows, self.num_cols = int(m.num_rows), int(m.num_cols)
 
-    def spmspv(self, op, zero, mask_type, x, mask, y):
-        check(lib.glb_spmspv(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x), _ptr(mask), _ptr(y)))
+    def spmspv(self, op, zero, mask_type, x, mask, y, epilogue=None, nxt=None):
+        """glb_spmspv_fused: ``epilogue`` = SpmspvEpilogue or None, ``nxt`` = SpmspvNext or None."""
+        check(lib.glb_spmspv_fused(self.ctx.handle, self.handle, op, zero, mask_type, _ptr(x), _ptr(mask), _ptr(y),
+                                   C.byref(epilogue) if epilogue is not None else None,
+                                   C.byref(nxt) if nxt is not None else None))
+
+    def push_state(self):
+        """(keep_pushing, push_levels) of the device-side direction decision; blocking."""
+        k, n = C.c_uint32(0), C.c_uint32(0)
+        check(lib.glb_spmspv_push_state(self.ctx.handle, self.handle, C.byref(k), C.byref(n)))
+        return bool(k.value), int(n.value)
+
+    def reset_levels(self):
+        check(lib.glb_spmspv_reset_levels(self.ctx.handle, self.handle))
 
     def close(self):
         if self.handle:

@@ -105,6 +105,7 @@ static void ctx_free(glb_ctx_t ctx) {
         for (cudaEvent_t e : row) if (e) cudaEventDestroy(e);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->branch_stream) cudaStreamDestroy(ctx->branch_stream);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -378,6 +379,7 @@ int glb_graph_begin(glb_ctx_t ctx) {
 int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out) {
     GLB_REQUIRE(ctx && out, "NULL argument");
     *out = nullptr;
+    if (ctx->in_branch) glb_graph_branch_end(ctx);  // a failed recording is being abandoned
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess || !graph) {
@@ -398,6 +400,91 @@ int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out) {
         return GLB_ECUDA;
     }
     *out = g;
+    return GLB_OK;
+}
+
+// ---- branches inside a recorded sequence -------------------------------------------------------
+// The direction-optimising apps decide per level, from the size of the frontier, whether the next level
+// pushes or pulls (bfs.h:186-190).  The reference reads the count on the host; here the decision stays
+// on the device: the kernel that ends a push level writes it into a conditional handle of the recorded
+// graph (cudaGraphSetConditional) and an IF / ELSE node (CUDA 12.8 conditional nodes, two body graphs)
+// runs the push arm or the pull arm of the next level.  While a body is being recorded the context's
+// stream is a side stream capturing INTO that body graph, so every glb_* launch lands there unchanged.
+static int capture_info(glb_ctx_t ctx, cudaStream_t st, cudaGraph_t *graph, const cudaGraphNode_t **deps, size_t *n_deps) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    GLB_CUDA(cudaStreamGetCaptureInfo(st, &status, &id, graph, deps, n_deps));
+    if (status != cudaStreamCaptureStatusActive) {
+        glb_set_error("no launch sequence is being recorded (glb_graph_begin)");
+        return GLB_EINVAL;
+    }
+    return GLB_OK;
+}
+
+int glb_graph_cond_create(glb_ctx_t ctx, uint64_t *cond) {
+    GLB_REQUIRE(ctx && cond, "NULL argument");
+    GLB_REQUIRE(!ctx->in_branch, "conditions are created outside branch bodies");
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n_deps = 0;
+    int rc = capture_info(ctx, ctx->stream, &graph, &deps, &n_deps);
+    if (rc) return rc;
+    cudaGraphConditionalHandle h;
+    GLB_CUDA(cudaGraphConditionalHandleCreate(&h, graph, 0, cudaGraphCondAssignDefault));  // 0 at every replay: the ELSE arm
+    static_assert(sizeof(h) == sizeof(uint64_t), "conditional handle size");
+    *cond = uint64_t(h);
+    return GLB_OK;
+}
+
+int glb_graph_branch_begin(glb_ctx_t ctx, uint64_t cond) {
+    GLB_REQUIRE(ctx && cond, "bad argument");
+    GLB_REQUIRE(!ctx->in_branch, "branches do not nest");
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n_deps = 0;
+    int rc = capture_info(ctx, ctx->stream, &graph, &deps, &n_deps);
+    if (rc) return rc;
+    cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};  // (the union makes the default constructor unusable)
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = cudaGraphConditionalHandle(cond);
+    p.conditional.type = cudaGraphCondTypeIf;
+    p.conditional.size = 2;
+    cudaGraphNode_t node = nullptr;
+    GLB_CUDA(cudaGraphAddNode(&node, graph, deps, n_deps, &p));
+    ctx->branch_body[0] = p.conditional.phGraph_out[0];
+    ctx->branch_body[1] = p.conditional.phGraph_out[1];
+    // what follows the branch in the outer sequence depends on the node
+    GLB_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    if (!ctx->branch_stream) GLB_CUDA(cudaStreamCreateWithFlags(&ctx->branch_stream, cudaStreamNonBlocking));
+    GLB_CUDA(cudaStreamBeginCaptureToGraph(ctx->branch_stream, ctx->branch_body[0], nullptr, nullptr, 0,
+                                           cudaStreamCaptureModeThreadLocal));
+    ctx->outer_stream = ctx->stream;
+    ctx->stream = ctx->branch_stream;
+    ctx->in_branch = 1;
+    return GLB_OK;
+}
+
+int glb_graph_branch_else(glb_ctx_t ctx) {
+    GLB_REQUIRE(ctx && ctx->in_branch == 1, "no IF body is being recorded");
+    cudaGraph_t g = nullptr;
+    GLB_CUDA(cudaStreamEndCapture(ctx->branch_stream, &g));
+    GLB_CUDA(cudaStreamBeginCaptureToGraph(ctx->branch_stream, ctx->branch_body[1], nullptr, nullptr, 0,
+                                           cudaStreamCaptureModeThreadLocal));
+    ctx->in_branch = 2;
+    return GLB_OK;
+}
+
+int glb_graph_branch_end(glb_ctx_t ctx) {
+    GLB_REQUIRE(ctx && ctx->in_branch, "no branch is being recorded");
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->branch_stream, &g);
+    ctx->stream = ctx->outer_stream;
+    ctx->in_branch = 0;
+    if (e != cudaSuccess) {
+        glb_set_error("glb_graph_branch_end: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return GLB_ECUDA;
+    }
     return GLB_OK;
 }
 

@@ -54,6 +54,11 @@ struct glb_ctx_s {
     int carveout_set[3] = {-1, -1, -1};
     int bits_carveout_set = -1;
     size_t tile_smem_set[3] = {0, 0, 0};
+    // recording the two arms of a branch (glb_graph_branch_*): launches go to a side stream that
+    // captures into the body graph of the IF / ELSE node
+    cudaStream_t branch_stream = nullptr, outer_stream = nullptr;
+    cudaGraph_t branch_body[2] = {nullptr, nullptr};
+    int in_branch = 0;  // 1: IF body, 2: ELSE body
     // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]
@@ -138,7 +143,9 @@ struct glb_csc_s {
     float *vals = nullptr;
     float *acc = nullptr;         // dense accumulator of plus-times / or-and, num_rows, at rest 0.0f between runs
     float *acc_inf = nullptr;     // dense accumulator of min-plus, at rest +inf
-    uint32_t *counter = nullptr;  // output cursor
+    uint32_t *bitmap = nullptr;   // plus-times: rows already in the touched list
+    uint32_t *touched = nullptr;  // rows touched by the running launch
+    void *state = nullptr;        // SpmspvState (spmspv.cu): counters, direction decision, push levels
 };
 
 // ---------------------------------------------------------------- peer exchange (multi-GPU)

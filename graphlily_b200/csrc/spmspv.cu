@@ -6,17 +6,26 @@
 // write-back rule (kernel_spmspv_impl.h:200-229,263-281,551-555): only entries != zero that
 // pass the mask are listed, the head slot is {count, zero}, order is unspecified.
 //
-// Three stream-ordered launches, none sized by device data (persistent grids read the
-// frontier length from x[0].index):
-//   1. scatter (column heads): one warp per active column combines the first kSeg non-zeros of
-//      the column, a (x) v, into a dense accumulator that rests at the (+)-identity
-//      (atomicAdd / benign store of 1.0f / ordered-int atomicMin) and queues the rest of a
-//      longer column as segments of kSeg non-zeros;
-//   2. scatter (queued segments): one warp per segment, so the 10^5-long columns of a power-law
-//      graph are spread over the whole grid instead of serialising one warp (or one grid-wide
-//      pass per column, as the first version did: 29 us for ~80 long columns on C3);
-//   3. compact: scan the accumulator, fold `zero`, apply the mask, reset touched entries,
-//      emit with warp-aggregated atomics on y[0].index.
+// ONE persistent launch (2 CTAs per SM, all co-resident) with a grid-wide barrier between its two
+// phases; nothing is sized by host-side knowledge of the frontier (its length is read from
+// x[0].index), so the launch can be recorded and replayed:
+//   phase 1  scatter: CTAs fetch batches of 8 frontier entries from a shared cursor; the batch's
+//            columns are cut into segments of kSeg non-zeros which the 8 warps of the CTA take round
+//            robin (a 10^4-long hub column is spread over the CTA instead of serialising one warp).
+//            a (x) v is combined into a dense accumulator that rests at the (+)-identity
+//            (atomicAdd / exchange of 1.0f / ordered-int atomicMin).  The FIRST thread to touch a row
+//            appends it to a touched-row list: for or-and and min-plus the atomic's return value
+//            tells (the accumulator leaves its identity exactly once), for plus-times a bitmap
+//            (atomicOr) does, read-tested first so that hub rows cost one cached load per touch;
+//   phase 2  compact: over the TOUCHED rows only (not the whole accumulator): fold `zero`, apply the
+//            mask, reset accumulator and bitmap, emit with warp-aggregated appends -- and apply the
+//            fused epilogue on the emitted entries: the sparse assign of a BFS push level
+//            (inout[row] = val, bfs.h:147-151) or the relax + new-frontier of an SSSP push level
+//            (assign_vector_sparse_module.h:318-335, sssp.h:178-190), so a push level is one launch.
+// Direction switch on the device (bfs.h:160-219, sssp.h:197-243): the last CTA out of phase 2
+// evaluates the reference's "keep pushing" test on the result count, writes it where the recorded
+// IF / ELSE node of the next level reads it (cudaGraphSetConditional), and when pushing stops every
+// CTA helps to turn the frontier into the dense input of the first pull level.
 #include <math.h>
 #include <string.h>
 
@@ -28,9 +37,11 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kSeg = 512;             // non-zeros per unit of work (one warp: 16 strides of 32)
 constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
+constexpr uint32_t kInfBits = 0x7f800000u;
 
 template <int OP>
 __device__ __forceinline__ float spmspv_mul(float a, float v) {
@@ -42,116 +53,197 @@ __device__ __forceinline__ float spmspv_mul(float a, float v) {
     return Semi<OP>::mul(a, v);
 }
 
-template <int OP>
-__device__ __forceinline__ void combine(float *acc, float p) {
-    if (OP == GLB_OP_MUL_ADD) {
-        atomicAdd(acc, p);
-    } else if (OP == GLB_OP_LOGICAL_AND_OR) {
-        if (p != 0.0f) *acc = 1.0f;  // idempotent: racing writers store the same word
-    } else {
-        // float min through integer atomics: non-negative floats order like ints,
-        // negative floats order inversely as unsigned
-        if (p >= 0.0f) atomicMin(reinterpret_cast<int *>(acc), __float_as_int(p));
-        else atomicMax(reinterpret_cast<unsigned *>(acc), __float_as_uint(p));
-    }
-}
+// device-resident state of one CSC matrix: two sets of counters used alternately, so that a launch
+// resets the set of the NEXT launch while nobody reads it (no host-side reset, replayable)
+struct SpmspvCounters {
+    uint32_t n_touched, cursor, bar[3], done;
+    uint32_t pad[2];
+};
+struct SpmspvState {
+    uint32_t parity;
+    uint32_t keep_pushing;  // decision of the last launch that carried a `next` block (1 = push again)
+    uint32_t push_levels;   // launches with a `next` block since glb_spmspv_reset_levels (push_iterations_ of the apps)
+    uint32_t pad;
+    SpmspvCounters c[2];
+};
 
 struct SpmspvParams {
     const uint32_t *__restrict__ indptr;
     const uint32_t *__restrict__ indices;
     const float *__restrict__ vals;
-    const glb_idx_val_t *__restrict__ x;
-    const float *__restrict__ mask;
+    const glb_idx_val_t *x;
+    const float *mask;
     glb_idx_val_t *y;
     float *acc;
-    uint32_t *heavy;  // [0] = number of queued segments, [2 + 2i], [3 + 2i] = {frontier slot k, segment number}
-    uint32_t row_begin, row_end;  // output rows of this shard: the compaction scans only these
-    uint32_t heavy_cap;  // segments the queue holds (nnz / kSeg + 1: enough unless x repeats columns)
+    uint32_t *bitmap;   // plus-times: bit r = row r is in the touched list
+    uint32_t *touched;  // rows touched by this launch (capacity: rows of the shard)
+    SpmspvState *state;
+    uint32_t row_begin, row_end;
     uint32_t num_rows, num_cols;
     float zero;
     int mask_type;
+    // fused epilogue on the emitted entries
+    int ep_mode;        // GLB_SPMSPV_EP_NONE / _ASSIGN / _RELAX
+    float *ep_inout;
+    float ep_val;
+    glb_idx_val_t *ep_new_frontier;
+    // direction decision after this push level (glb_spmspv_next_t)
+    int has_next;
+    int force_stop;
+    float threshold;
+    float n_vertices;
+    unsigned long long cond_next;  // cudaGraphConditionalHandle of the next level's IF / ELSE node (0: none)
+    int dense_mode;                // on stop: GLB_SPMSPV_DENSE_NONE / _SCATTER (y list -> dense) / _COPY (dense_src -> dense)
+    float *dense;
+    const float *dense_src;
+    uint32_t dense_len;
 };
+
+// all CTAs of the launch are co-resident (2 per SM): a counter barrier
+__device__ __forceinline__ void grid_barrier(uint32_t *counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        uint32_t seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < gridDim.x);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void append_touched(const SpmspvParams &P, SpmspvCounters *C, bool first, uint32_t row, unsigned lane) {
+    const unsigned b = __ballot_sync(__activemask(), first);
+    if (!first) return;
+    const int leader = __ffs(int(b)) - 1;
+    uint32_t base = 0;
+    if (int(lane) == leader) base = atomicAdd(&C->n_touched, uint32_t(__popc(b)));
+    base = __shfl_sync(b, base, leader);
+    P.touched[base + __popc(b & ((1u << lane) - 1u))] = row;
+}
 
 // one warp, non-zeros [s, t) of one column, t - s <= kSeg
 template <int OP>
-__device__ __forceinline__ void scatter_span(const SpmspvParams &P, uint32_t s, uint32_t t, float v, unsigned lane) {
-#pragma unroll 4
-    for (uint32_t i = s + lane; i < t; i += 32)
-        combine<OP>(P.acc + __ldg(P.indices + i), spmspv_mul<OP>(__ldg(P.vals + i), v));
+__device__ __forceinline__ void scatter_span(const SpmspvParams &P, SpmspvCounters *C, uint32_t s, uint32_t t, float v,
+                                             unsigned lane) {
+    for (uint32_t i0 = s; i0 < t; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool first = false;
+        uint32_t row = 0;
+        if (i < t) {
+            row = __ldg(P.indices + i);
+            const float p = spmspv_mul<OP>(__ldg(P.vals + i), v);
+            float *a = P.acc + row;
+            if (OP == GLB_OP_MUL_ADD) {
+                atomicAdd(a, p);
+                const uint32_t w = row >> 5, bit = 1u << (row & 31u);
+                if (!(P.bitmap[w] & bit)) first = !(atomicOr(P.bitmap + w, bit) & bit);  // (a stale cached 0 only costs a retry)
+            } else if (OP == GLB_OP_LOGICAL_AND_OR) {
+                // idempotent: the first writer flips 0.0f -> 1.0f and owns the row
+                if (p != 0.0f && *a == 0.0f) first = atomicExch(reinterpret_cast<uint32_t *>(a), 0x3f800000u) == 0u;
+            } else {
+                // float min through integer atomics: non-negative floats order like ints, negative ones
+                // inversely as unsigned; the accumulator rests at +inf and leaves it exactly once
+                if (p >= 0.0f) first = uint32_t(atomicMin(reinterpret_cast<int *>(a), __float_as_int(p))) == kInfBits;
+                else first = atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(p)) == kInfBits;
+            }
+        }
+        append_touched(P, C, first, row, lane);
+    }
 }
 
 template <int OP>
-__global__ void __launch_bounds__(kThreads) spmspv_scatter_light(const SpmspvParams P) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
+__global__ void __launch_bounds__(kThreads, 2) spmspv_kernel(const SpmspvParams P) {
+    __shared__ uint32_t s_batch;
+    __shared__ uint32_t s_seg_end[kWarps + 1];  // prefix of the batch's segment counts
+    __shared__ uint32_t s_col_s[kWarps], s_col_t[kWarps];
+    __shared__ float s_col_v[kWarps];
+    __shared__ uint32_t s_last;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    SpmspvState *S = P.state;
+    const uint32_t par = S->parity;  // flipped by CTA 0 after the first barrier: every CTA has read it by then
+    SpmspvCounters *C = &S->c[par];
     const uint32_t nnz_x = P.x[0].index;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.y[0].index = 0;
         P.y[0].val = P.zero;
+        if (P.ep_mode == GLB_SPMSPV_EP_RELAX) {
+            P.ep_new_frontier[0].index = 0;
+            P.ep_new_frontier[0].val = 0.0f;
+        }
+        SpmspvCounters *N = &S->c[par ^ 1u];  // the next launch's counters
+        N->n_touched = 0; N->cursor = 0; N->bar[0] = 0; N->bar[1] = 0; N->bar[2] = 0; N->done = 0;
     }
-    for (uint32_t k = warp; k < nnz_x; k += n_warps) {
-        const glb_idx_val_t e = P.x[k + 1];
-        if (e.index >= P.num_cols) continue;  // not a column of this matrix: ignored (warp-uniform)
-        const uint32_t s = __ldg(P.indptr + e.index), t = __ldg(P.indptr + e.index + 1);
-        const uint32_t len = t - s;
-        bool queued = false;
-        if (len > kSeg) {  // queue segments 1 .. n_extra of this column: {frontier slot, segment}
-            const uint32_t n_extra = (len - 1) / kSeg;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(P.heavy, n_extra);
-            base = __shfl_sync(kFull, base, 0);
-            // a frontier that lists columns more than once can outgrow the queue: then this warp walks
-            // the whole column itself and voids what it reserved
-            queued = base + n_extra <= P.heavy_cap;
-            for (uint32_t j = lane; j < n_extra && base + j < P.heavy_cap; j += 32) {
-                P.heavy[2 + 2 * (base + j)] = k;
-                P.heavy[3 + 2 * (base + j)] = queued ? j + 1 : 0xffffffffu;
+
+    // ---- phase 1: scatter ---------------------------------------------------------------------
+    const uint32_t n_batches = (nnz_x + kWarps - 1) / kWarps;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_batch = atomicAdd(&C->cursor, 1u);
+        __syncthreads();
+        const uint32_t batch = s_batch;
+        if (batch >= n_batches) break;
+        if (lane == 0) {
+            const uint32_t k = batch * kWarps + warp;
+            uint32_t s = 0, t = 0;
+            float v = 0.0f;
+            if (k < nnz_x) {
+                const glb_idx_val_t e = P.x[k + 1];
+                if (e.index < P.num_cols) {  // not a column of this matrix: ignored
+                    s = __ldg(P.indptr + e.index);
+                    t = __ldg(P.indptr + e.index + 1);
+                    v = e.val;
+                }
             }
+            s_col_s[warp] = s; s_col_t[warp] = t; s_col_v[warp] = v;
         }
-        if (queued) {
-            scatter_span<OP>(P, s, s + kSeg, e.val, lane);
-        } else {
-            for (uint32_t b = s; b < t; b += kSeg) scatter_span<OP>(P, b, t - b > kSeg ? b + kSeg : t, e.val, lane);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int w = 0; w < kWarps; ++w) {
+                s_seg_end[w] = run;
+                run += (s_col_t[w] - s_col_s[w] + kSeg - 1) / kSeg;
+            }
+            s_seg_end[kWarps] = run;
+        }
+        __syncthreads();
+        const uint32_t n_seg = s_seg_end[kWarps];
+        for (uint32_t g = warp; g < n_seg; g += kWarps) {
+            int w = 0;
+#pragma unroll
+            for (int q = 1; q < kWarps; ++q) w += (s_seg_end[q] <= g);
+            const uint32_t s = s_col_s[w] + (g - s_seg_end[w]) * kSeg;
+            const uint32_t t = s_col_t[w] - s > kSeg ? s + kSeg : s_col_t[w];
+            scatter_span<OP>(P, C, s, t, s_col_v[w], lane);
         }
     }
-}
+    grid_barrier(&C->bar[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) S->parity = par ^ 1u;
 
-template <int OP>
-__global__ void __launch_bounds__(kThreads) spmspv_scatter_heavy(const SpmspvParams P) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
-    const uint32_t n_seg = P.heavy[0] < P.heavy_cap ? P.heavy[0] : P.heavy_cap;
-    for (uint32_t h = warp; h < n_seg; h += n_warps) {
-        const glb_idx_val_t e = P.x[P.heavy[2 + 2 * h] + 1];
-        const uint32_t seg = P.heavy[3 + 2 * h];
-        if (seg == 0xffffffffu) continue;  // voided reservation
-        const uint32_t t = __ldg(P.indptr + e.index + 1);
-        const uint32_t s = __ldg(P.indptr + e.index) + seg * kSeg;
-        scatter_span<OP>(P, s, (t - s > kSeg) ? s + kSeg : t, e.val, lane);
-    }
-}
-
-template <int OP>
-__global__ void __launch_bounds__(kThreads) spmspv_compact(const SpmspvParams P) {
-    const unsigned lane = threadIdx.x & 31u;
+    // ---- phase 2: compact the touched rows ---------------------------------------------------------
+    uint32_t n_touched;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(n_touched) : "l"(&C->n_touched) : "memory");
+    const uint32_t n_round = (n_touched + 31u) & ~31u;  // keep warps converged for the ballots
     const uint32_t n_threads = gridDim.x * kThreads;
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.heavy[0] = 0;  // ready for the next run
-    const uint32_t n_round = (P.row_end - P.row_begin + 31u) & ~31u;  // keep warps converged for the ballots
     for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n_round; q += n_threads) {
-        const uint32_t r = P.row_begin + q;
-        bool emit = false;
+        bool emit = false, improved = false;
         float val = 0.0f;
-        if (r < P.row_end) {
-            const float a = P.acc[r];
-            if (a != Semi<OP>::ident()) {
-                P.acc[r] = Semi<OP>::ident();
-                val = Semi<OP>::with_zero(P.zero, a);
-                bool off = false;
-                if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (P.mask[r] == P.zero);
-                else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (P.mask[r] != P.zero);
-                emit = !off && (val != P.zero);
+        uint32_t r = 0;
+        if (q < n_touched) {
+            r = __ldcg(P.touched + q);
+            const float a = __ldcg(P.acc + r);
+            P.acc[r] = Semi<OP>::ident();
+            if (OP == GLB_OP_MUL_ADD) P.bitmap[r >> 5] = 0u;  // every set bit of the word belongs to a row of this list
+            val = Semi<OP>::with_zero(P.zero, a);
+            bool off = false;
+            if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (P.mask[r] == P.zero);
+            else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (P.mask[r] != P.zero);
+            emit = !off && (val != P.zero);
+            if (emit && P.ep_mode == GLB_SPMSPV_EP_ASSIGN) P.ep_inout[r] = P.ep_val;
+            if (emit && P.ep_mode == GLB_SPMSPV_EP_RELAX && P.ep_inout[r] > val) {
+                P.ep_inout[r] = val;  // rows are unique in the list: no other thread touches this element
+                improved = true;
             }
         }
         const unsigned b = __ballot_sync(kFull, emit);
@@ -167,6 +259,53 @@ __global__ void __launch_bounds__(kThreads) spmspv_compact(const SpmspvParams P)
                 P.y[1 + base + __popc(b & ((1u << lane) - 1u))] = o;
             }
         }
+        const unsigned bi = __ballot_sync(kFull, improved);
+        if (bi) {
+            uint32_t base = 0;
+            const int leader = __ffs(int(bi)) - 1;
+            if (int(lane) == leader) base = atomicAdd(&P.ep_new_frontier[0].index, uint32_t(__popc(bi)));
+            base = __shfl_sync(kFull, base, leader);
+            if (improved) {
+                glb_idx_val_t o;
+                o.index = r;
+                o.val = val;
+                P.ep_new_frontier[1 + base + __popc(bi & ((1u << lane) - 1u))] = o;
+            }
+        }
+    }
+    if (!P.has_next) return;
+
+    // ---- direction decision: the last CTA out of phase 2 sees the final count ------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&C->done, 1u) == gridDim.x - 1;
+        if (s_last) {
+            __threadfence();
+            uint32_t count;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(count) : "l"(&P.y[0].index) : "memory");
+            // bfs.h:190 / sssp.h:214: keep pushing while iter < num_iterations (force_stop, from the host) and
+            // float(nnz) / num_vertices < threshold
+            const uint32_t keep = (!P.force_stop && (float(count) / P.n_vertices < P.threshold)) ? 1u : 0u;
+            S->keep_pushing = keep;
+            S->push_levels += 1;
+            if (P.cond_next) cudaGraphSetConditional(cudaGraphConditionalHandle(P.cond_next), keep);
+        }
+    }
+    if (P.dense_mode == GLB_SPMSPV_DENSE_NONE) return;
+    grid_barrier(&C->bar[1]);  // every CTA learns the decision
+    uint32_t keep;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(keep) : "l"(&S->keep_pushing) : "memory");
+    if (keep) return;
+    // pushing stops here: build the dense input of the first pull level, all CTAs together
+    if (P.dense_mode == GLB_SPMSPV_DENSE_SCATTER) {  // `dense` was filled with the semiring zero when the run was set up
+        const uint32_t count = P.y[0].index;
+        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < count; i += n_threads) {
+            const glb_idx_val_t e = P.y[i + 1];
+            if (e.index < P.dense_len) P.dense[e.index] = e.val;
+        }
+    } else {
+        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.dense_len; i += n_threads) P.dense[i] = P.dense_src[i];
     }
 }
 
@@ -223,10 +362,7 @@ __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
 
 template <int OP>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
-    const int grid = ctx->num_sms * 8;
-    spmspv_scatter_light<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
-    spmspv_scatter_heavy<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
-    spmspv_compact<OP><<<grid, kThreads, 0, ctx->stream>>>(P);
+    spmspv_kernel<OP><<<ctx->num_sms * 2, kThreads, 0, ctx->stream>>>(P);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
@@ -312,14 +448,17 @@ int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, con
     alloc(reinterpret_cast<void **>(&m->vals), sizeof(float) * nnz);
     alloc(reinterpret_cast<void **>(&m->acc), sizeof(float) * num_rows);
     alloc(reinterpret_cast<void **>(&m->acc_inf), sizeof(float) * num_rows);
-    alloc(reinterpret_cast<void **>(&m->counter), sizeof(uint32_t) * (2 * (size_t(nnz) / kSeg + 1) + 4));  // segment queue
+    alloc(reinterpret_cast<void **>(&m->bitmap), sizeof(uint32_t) * ((size_t(num_rows) + 31) / 32 + 1));
+    alloc(reinterpret_cast<void **>(&m->touched), sizeof(uint32_t) * (size_t(row_end - row_begin) + 32));
+    alloc(reinterpret_cast<void **>(&m->state), sizeof(SpmspvState));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->indptr, indptr, sizeof(uint32_t) * (size_t(num_cols) + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz)
         e = cudaMemcpyAsync(m->indices, indices, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz)
         e = cudaMemcpyAsync(m->vals, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(m->counter, 0, sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->bitmap, 0, sizeof(uint32_t) * ((size_t(num_rows) + 31) / 32 + 1), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->state, 0, sizeof(SpmspvState), ctx->stream);
     if (e == cudaSuccess && num_rows) {
         fill_f32_kernel<<<ctx->num_sms * 8, kThreads, 0, ctx->stream>>>(m->acc, 0.0f, num_rows);
         fill_f32_kernel<<<ctx->num_sms * 8, kThreads, 0, ctx->stream>>>(m->acc_inf, HUGE_VALF, num_rows);
@@ -339,20 +478,22 @@ int glb_csc_destroy(glb_csc_t m) {
     if (!m) return GLB_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf); cudaFree(m->counter);
+    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf);
+    cudaFree(m->bitmap); cudaFree(m->touched); cudaFree(m->state);
     glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
 }
 
-int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
-               glb_idx_val_t *y) {
+int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
+                     glb_idx_val_t *y, const glb_spmspv_epilogue_t *ep, const glb_spmspv_next_t *next) {
     GLB_REQUIRE(ctx && m && x && y, "NULL argument");
     GLB_REQUIRE(m->ctx == ctx, "matrix belongs to another context");
     GLB_REQUIRE(mask_type >= GLB_MASK_NONE && mask_type <= GLB_MASK_WRITE_TO_ONE, "invalid mask type");
     GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask, "mask is NULL but mask_type != kNoMask");
     GLB_REQUIRE(static_cast<const void *>(x) != static_cast<const void *>(y), "y must not alias x");
     SpmspvParams P;
+    memset(&P, 0, sizeof(P));
     P.indptr = m->indptr;
     P.indices = m->indices;
     P.vals = m->vals;
@@ -362,14 +503,42 @@ int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, co
     // one accumulator per (+)-identity, both filled when the matrix was created and left at rest by
     // every run: no launch depends on host-side state (launch sequences can be recorded at any time)
     P.acc = (op == GLB_OP_ADD_MIN) ? m->acc_inf : m->acc;
-    P.heavy = m->counter;
-    P.heavy_cap = uint32_t(m->nnz / kSeg + 1);
+    P.bitmap = m->bitmap;
+    P.touched = m->touched;
+    P.state = static_cast<SpmspvState *>(m->state);
     P.row_begin = m->row_begin;
     P.row_end = m->row_end;
     P.num_rows = m->num_rows;
     P.num_cols = m->num_cols;
     P.zero = zero;
     P.mask_type = mask_type;
+    if (ep && ep->mode != GLB_SPMSPV_EP_NONE) {
+        GLB_REQUIRE(ep->mode == GLB_SPMSPV_EP_ASSIGN || ep->mode == GLB_SPMSPV_EP_RELAX, "invalid epilogue mode");
+        GLB_REQUIRE(ep->inout, "epilogue needs an inout vector");
+        GLB_REQUIRE(ep->mode != GLB_SPMSPV_EP_RELAX || ep->new_frontier, "relax epilogue needs a new-frontier list");
+        GLB_REQUIRE(static_cast<const void *>(ep->new_frontier) != static_cast<const void *>(x) &&
+                        static_cast<const void *>(ep->new_frontier) != static_cast<const void *>(y),
+                    "new_frontier must not alias x or y");
+        P.ep_mode = ep->mode;
+        P.ep_inout = ep->inout;
+        P.ep_val = ep->val;
+        P.ep_new_frontier = ep->new_frontier;
+    }
+    if (next) {
+        GLB_REQUIRE(next->num_vertices > 0, "num_vertices must be positive");
+        GLB_REQUIRE(next->dense_mode >= GLB_SPMSPV_DENSE_NONE && next->dense_mode <= GLB_SPMSPV_DENSE_COPY, "invalid dense mode");
+        GLB_REQUIRE(next->dense_mode == GLB_SPMSPV_DENSE_NONE || next->dense, "dense vector is NULL");
+        GLB_REQUIRE(next->dense_mode != GLB_SPMSPV_DENSE_COPY || next->dense_src, "dense_src is NULL");
+        P.has_next = 1;
+        P.force_stop = next->force_stop;
+        P.threshold = next->threshold;
+        P.n_vertices = float(next->num_vertices);
+        P.cond_next = next->cond_next;
+        P.dense_mode = next->dense_mode;
+        P.dense = next->dense;
+        P.dense_src = next->dense_src;
+        P.dense_len = next->dense_len;
+    }
     switch (op) {
         case GLB_OP_MUL_ADD: return run_spmspv<GLB_OP_MUL_ADD>(ctx, m, P);
         case GLB_OP_LOGICAL_AND_OR: return run_spmspv<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);
@@ -377,6 +546,28 @@ int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, co
     }
     glb_set_error("glb_spmspv: invalid semiring op %d", op);
     return GLB_EINVAL;
+}
+
+int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
+               glb_idx_val_t *y) {
+    return glb_spmspv_fused(ctx, m, op, zero, mask_type, x, mask, y, nullptr, nullptr);
+}
+
+int glb_spmspv_push_state(glb_ctx_t ctx, glb_csc_t m, uint32_t *keep_pushing, uint32_t *push_levels) {
+    GLB_REQUIRE(ctx && m && m->ctx == ctx, "bad argument");
+    SpmspvState h;
+    GLB_CUDA(cudaMemcpyAsync(&h, m->state, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (keep_pushing) *keep_pushing = h.keep_pushing;
+    if (push_levels) *push_levels = h.push_levels;
+    return GLB_OK;
+}
+
+int glb_spmspv_reset_levels(glb_ctx_t ctx, glb_csc_t m) {
+    GLB_REQUIRE(ctx && m && m->ctx == ctx, "bad argument");
+    // keep_pushing, push_levels (parity and the counter sets are left alone)
+    GLB_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(m->state) + sizeof(uint32_t), 0, 2 * sizeof(uint32_t), ctx->stream));
+    return GLB_OK;
 }
 
 int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count) {

@@ -221,9 +221,14 @@ class SpMSpVModule(BaseModule):
 
     def run(self):
         """spmspv_module.h:437-441"""
+        self.run_with(self.vector_buf, self.results_buf)
+
+    def run_with(self, vector_buf, results_buf, epilogue=None, nxt=None):
+        """run() on explicit list buffers, optionally with the fused sparse assign of a push level and the
+        device-side direction decision (glb_spmspv_fused)."""
         op, _one, zero = self.semiring_
-        self.matrix.spmspv(op, zero, self.mask_type_, self.vector_buf,
-                           self.mask_buf if self.mask_type_ != capi.MASK_NONE else None, self.results_buf)
+        self.matrix.spmspv(op, zero, self.mask_type_, vector_buf,
+                           self.mask_buf if self.mask_type_ != capi.MASK_NONE else None, results_buf, epilogue, nxt)
 
     def send_vector_device_to_host(self):
         n = capi.sparse_count(self.ctx, self.vector_buf)

@@ -218,6 +218,48 @@ int glb_spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask
  * 263-281,551-555).  x: device list, capacity >= nnz+1; y: capacity num_rows+1. */
 int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x,
                const float *mask, glb_idx_val_t *y);
+/* A whole push level in one launch: glb_spmspv, then on the listed entries the sparse assign of the
+ * apps, fused into the kernel's compaction phase:
+ *   GLB_SPMSPV_EP_ASSIGN  inout[row] = val                          AssignVectorSparse (no new frontier), bfs.h:147-151
+ *   GLB_SPMSPV_EP_RELAX   if inout[row] > v { inout[row] = v; append {row, v} to new_frontier }
+ *                         AssignVectorSparse (new frontier), sssp.h:178-190; new_frontier[0] = {count, 0}
+ * `inout` may alias `mask` (BFS: both are the distance vector).
+ * `next` (optional) = the direction decision of pull_push, taken ON THE DEVICE after this level
+ * (bfs.h:186-190, sssp.h:210-214): keep pushing iff !force_stop && float(count(y)) / num_vertices < threshold.
+ * The decision goes to the IF / ELSE node `cond_next` of a recorded sequence (glb_graph_cond_create; 0: none)
+ * and can be read back with glb_spmspv_push_state.  When pushing stops the same launch prepares the dense
+ * input of the first pull level: GLB_SPMSPV_DENSE_SCATTER scatters y into `dense` (which the caller
+ * filled with the semiring zero beforehand), GLB_SPMSPV_DENSE_COPY copies dense_src (the distance
+ * vector, sssp.h:219-222) into it. */
+#define GLB_SPMSPV_EP_NONE 0
+#define GLB_SPMSPV_EP_ASSIGN 1
+#define GLB_SPMSPV_EP_RELAX 2
+#define GLB_SPMSPV_DENSE_NONE 0
+#define GLB_SPMSPV_DENSE_SCATTER 1
+#define GLB_SPMSPV_DENSE_COPY 2
+typedef struct glb_spmspv_epilogue {
+    int mode;
+    float *inout;
+    float val;
+    glb_idx_val_t *new_frontier;
+} glb_spmspv_epilogue_t;
+typedef struct glb_spmspv_next {
+    int force_stop;
+    float threshold;
+    uint32_t num_vertices;
+    uint64_t cond_next;
+    int dense_mode;
+    float *dense;
+    const float *dense_src;
+    uint32_t dense_len;
+} glb_spmspv_next_t;
+int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x,
+                     const float *mask, glb_idx_val_t *y, const glb_spmspv_epilogue_t *ep,
+                     const glb_spmspv_next_t *next);
+/* Blocking read of the last decision (1 = keep pushing) and of the number of levels that carried a
+ * `next` block since glb_spmspv_reset_levels (stream-ordered) -- push_iterations of a pull_push run. */
+int glb_spmspv_push_state(glb_ctx_t ctx, glb_csc_t m, uint32_t *keep_pushing, uint32_t *push_levels);
+int glb_spmspv_reset_levels(glb_ctx_t ctx, glb_csc_t m);
 /* SpMSpVModule::get_results_nnz (spmspv_module.h:239-242): blocking read of list[0].index. */
 int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count);
 /* convert_sparse_vec_to_dense_vec (global.h:153-164) done on the device (the reference does it
@@ -333,6 +375,17 @@ int glb_spmv_host_batch_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero,
  *   glb_graph_launch  enqueues the whole sequence on the context's stream */
 typedef struct glb_graph_s *glb_graph_t;
 int glb_graph_begin(glb_ctx_t ctx);
+/* A branch inside the recorded sequence, decided on the device at replay time (the push / pull choice of
+ * pull_push, bfs.h:186-190, without the host reading the frontier size):
+ *   glb_graph_cond_create   a condition (0 at the start of every replay); pass it to the launch that
+ *                           decides -- glb_spmspv_fused's next->cond_next -- recorded BEFORE the branch
+ *   glb_graph_branch_begin  launches that follow are recorded into the IF arm (condition != 0) ...
+ *   glb_graph_branch_else   ... from here on into the ELSE arm (condition == 0) ...
+ *   glb_graph_branch_end    ... and from here on after the branch again.  Branches do not nest. */
+int glb_graph_cond_create(glb_ctx_t ctx, uint64_t *cond);
+int glb_graph_branch_begin(glb_ctx_t ctx, uint64_t cond);
+int glb_graph_branch_else(glb_ctx_t ctx);
+int glb_graph_branch_end(glb_ctx_t ctx);
 int glb_graph_end(glb_ctx_t ctx, glb_graph_t *out);
 int glb_graph_launch(glb_ctx_t ctx, glb_graph_t g);
 int glb_graph_destroy(glb_graph_t g);

@@ -314,6 +314,94 @@ def test_chunk_sizes_small_shards(ctx, oracle, monkeypatch):
                 check_vec(got, oracle.port.spmv(m, op, zero, mt, x, mask if mt else None), op)
 
 
+def test_spmspv_fused_push_levels(ctx, oracle):
+    # glb_spmspv_fused: the sparse assign of a push level inside the SpMSpV launch, against the
+    # reference's two-module sequence (SpMSpV.run(); SparseAssign.run(), bfs.h:147-151 / sssp.h:178-190)
+    # evaluated with the oracle; repeated launches on one matrix (the accumulator, bitmap and counters
+    # must come back to rest), frontiers from empty to dense
+    rng = np.random.default_rng(71)
+    g = datasets.social_graph(3000, 60000, 400, seed=12, diagonal=True)
+    csc = io.csr2csc(g)
+    n = g.num_rows
+    A = capi.CscMatrix(ctx, csc)
+    dy = ctx.to_device(np.zeros(n + 1, capi.IDX_VAL))
+    dnf = ctx.to_device(np.zeros(n + 1, capi.IDX_VAL))
+    for density in (0.0, 0.001, 0.05, 0.6, 0.0005):
+        idx = np.nonzero(rng.random(n) < density)[0].astype(np.uint32)
+        dx = ctx.to_device(capi.sparse_to_numpy(idx, np.ones(len(idx), np.float32), n + 1))
+        # BFS level: or-and, mask = distance (write where 0), distance[row] = 7 on the listed rows
+        dist = np.where(rng.random(n) < 0.5, 0.0, rng.integers(1, 5, n)).astype(np.float32)
+        ddist = ctx.to_device(dist)
+        ep = capi.SpmspvEpilogue(capi.SPMSPV_EP_ASSIGN, ddist.ptr, 7.0, None)
+        A.spmspv(1, 0.0, capi.MASK_WRITE_TO_ZERO, dx, ddist, dy, ep)
+        y_ref = oracle.port.spmspv(csc, 1, 0.0, capi.MASK_WRITE_TO_ZERO, idx, np.ones(len(idx), np.float32), dist)
+        oi, ov = dy.read_sparse()
+        assert densify(oi, ov, n, 0.0).tobytes() == y_ref.tobytes()
+        assert ddist.read(np.float32, n).tobytes() == oracle.port.assign_sparse(np.nonzero(y_ref)[0], dist, 7.0).tobytes()
+        # SSSP level: min-plus, no mask, relax of the distance vector + new frontier
+        val = rng.integers(0, 6, len(idx)).astype(np.float32)
+        dx = ctx.to_device(capi.sparse_to_numpy(idx, val, n + 1))
+        dist = rng.integers(0, 9, n).astype(np.float32)
+        ddist = ctx.to_device(dist)
+        ep = capi.SpmspvEpilogue(capi.SPMSPV_EP_RELAX, ddist.ptr, 0.0, dnf.ptr)
+        A.spmspv(2, 255.0, capi.MASK_NONE, dx, None, dy, ep)
+        y_ref = oracle.port.spmspv(csc, 2, 255.0, capi.MASK_NONE, idx, val, None)
+        oi, ov = dy.read_sparse()
+        assert densify(oi, ov, n, 255.0).tobytes() == y_ref.tobytes()
+        listed = np.nonzero(y_ref != 255.0)[0].astype(np.uint32)
+        ref_inout, ref_fi, ref_fv = oracle.port.assign_sparse_relax(listed, y_ref[listed], dist)
+        assert ddist.read(np.float32, n).tobytes() == ref_inout.tobytes()
+        fi, fv = dnf.read_sparse()
+        o, ro = np.argsort(fi), np.argsort(ref_fi)
+        assert fi[o].tolist() == ref_fi[ro].tolist() and fv[o].tobytes() == ref_fv[ro].tobytes()
+        assert dnf.read(capi.IDX_VAL, 1)["val"][0] == 0.0
+        # plus-times through the same kernel (bitmap path), twice in a row
+        for _ in range(2):
+            A.spmspv(0, 0.0, capi.MASK_NONE, dx, None, dy)
+            oi, ov = dy.read_sparse()
+            check_vec(densify(oi, ov, n, 0.0), oracle.port.spmspv(csc, 0, 0.0, capi.MASK_NONE, idx, val, None), 0)
+    A.close()
+
+
+def test_spmspv_direction_decision_on_the_device(ctx, oracle):
+    # the `next` block of glb_spmspv_fused: keep pushing iff !force_stop && float(count) / n < threshold
+    # (bfs.h:186-190), read back with glb_spmspv_push_state; when pushing stops the launch builds the dense
+    # input of the first pull level (scatter of the result list, or a copy of the distance vector)
+    rng = np.random.default_rng(72)
+    g = datasets.social_graph(2048, 30000, 300, seed=13)
+    csc = io.csr2csc(g)
+    n = g.num_rows
+    A = capi.CscMatrix(ctx, csc)
+    dy = ctx.to_device(np.zeros(n + 1, capi.IDX_VAL))
+    idx = np.array([5], np.uint32)
+    dx = ctx.to_device(capi.sparse_to_numpy(idx, [1.0], n + 1))
+    y_ref = oracle.port.spmspv(csc, 1, 0.0, 0, idx, np.ones(1, np.float32), None)
+    count = int((y_ref != 0).sum())
+    assert count > 0
+    A.reset_levels()
+    cases = [(0, (count + 0.5) / n, True), (0, (count - 0.5) / n, False), (1, 1.0, False),
+             (0, float(np.float32(count) / np.float32(n)), False)]   # equality is not "less than"
+    for k, (force_stop, thr, keep_ref) in enumerate(cases):
+        dense = ctx.zeros_f32(n, 0.0)
+        src = ctx.to_device(rng.random(n).astype(np.float32))
+        for mode in (capi.SPMSPV_DENSE_SCATTER, capi.SPMSPV_DENSE_COPY, capi.SPMSPV_DENSE_NONE):
+            capi.check(capi.lib.glb_buffer_fill_f32(ctx.handle, dense.ptr, 0.0, n))
+            nxt = capi.SpmspvNext(force_stop, thr, n, 0, mode, dense.ptr if mode else None,
+                                  src.ptr if mode == capi.SPMSPV_DENSE_COPY else None, n)
+            A.spmspv(1, 0.0, 0, dx, None, dy, None, nxt)
+            keep, _levels = A.push_state()
+            assert keep == keep_ref, (k, mode)
+            got = dense.read(np.float32, n)
+            if keep or mode == capi.SPMSPV_DENSE_NONE:
+                assert not got.any()
+            elif mode == capi.SPMSPV_DENSE_SCATTER:
+                assert got.tobytes() == y_ref.tobytes()
+            else:
+                assert got.tobytes() == src.read(np.float32, n).tobytes()
+    assert A.push_state()[1] == 3 * len(cases)
+    A.close()
+
+
 # ----------------------------------------------------------------------------- apply
 def test_apply_golden_fixture(ctx):
     z = golden()
