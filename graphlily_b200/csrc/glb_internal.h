@@ -143,8 +143,9 @@ struct glb_csc_s {
     float *vals = nullptr;
     float *acc = nullptr;         // dense accumulator of plus-times / or-and, num_rows, at rest 0.0f between runs
     float *acc_inf = nullptr;     // dense accumulator of min-plus, at rest +inf
-    uint32_t *bitmap = nullptr;   // plus-times: rows already in the touched list
-    uint32_t *touched = nullptr;  // rows touched by the running launch
+    uint32_t *bitmap = nullptr;   // rows touched by the running launch (small frontiers), all zero at rest
+    unsigned long long *queue = nullptr;  // segment queue of the long columns (spmspv.cu), all ones at rest
+    uint32_t queue_cap = 0;
     void *state = nullptr;        // SpmspvState (spmspv.cu): counters, direction decision, push levels
 };
 

@@ -6,19 +6,19 @@
 // write-back rule (kernel_spmspv_impl.h:200-229,263-281,551-555): only entries != zero that
 // pass the mask are listed, the head slot is {count, zero}, order is unspecified.
 //
-// ONE persistent launch (2 CTAs per SM, all co-resident) with a grid-wide barrier between its two
+// ONE persistent launch (4 CTAs per SM, all co-resident) with a grid-wide barrier between its two
 // phases; nothing is sized by host-side knowledge of the frontier (its length is read from
 // x[0].index), so the launch can be recorded and replayed:
-//   phase 1  scatter: CTAs fetch batches of 8 frontier entries from a shared cursor; the batch's
-//            columns are cut into segments of kSeg non-zeros which the 8 warps of the CTA take round
-//            robin (a 10^4-long hub column is spread over the CTA instead of serialising one warp).
-//            a (x) v is combined into a dense accumulator that rests at the (+)-identity
-//            (atomicAdd / exchange of 1.0f / ordered-int atomicMin).  The FIRST thread to touch a row
-//            appends it to a touched-row list: for or-and and min-plus the atomic's return value
-//            tells (the accumulator leaves its identity exactly once), for plus-times a bitmap
-//            (atomicOr) does, read-tested first so that hub rows cost one cached load per touch;
-//   phase 2  compact: over the TOUCHED rows only (not the whole accumulator): fold `zero`, apply the
-//            mask, reset accumulator and bitmap, emit with warp-aggregated appends -- and apply the
+//   phase 1  scatter: a warp takes every (number of warps)-th frontier entry; columns longer than kSeg
+//            non-zeros are queued in the CTA's shared memory and cut into segments its 8 warps share
+//            (a 10^4-long hub column is spread over the CTA instead of serialising one warp).
+//            a (x) v is combined into a dense accumulator that rests at the (+)-identity with
+//            fire-and-forget operations (reduction atomics, an idempotent store for or-and: nothing
+//            waits for a result).  A SMALL frontier also marks the rows it touches in a bitmap
+//            (one more reduction atomic per non-zero, 1/32 of the accumulator's size);
+//   phase 2  compact: a small frontier walks the bitmap and visits only the touched rows, a large one
+//            scans the accumulator of the shard: fold `zero`, apply the mask, reset accumulator and
+//            bitmap, emit with warp-aggregated appends -- and apply the
 //            fused epilogue on the emitted entries: the sparse assign of a BFS push level
 //            (inout[row] = val, bfs.h:147-151) or the relax + new-frontier of an SSSP push level
 //            (assign_vector_sparse_module.h:318-335, sssp.h:178-190), so a push level is one launch.
@@ -29,6 +29,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "glb_internal.h"
@@ -41,7 +42,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kSeg = 512;             // non-zeros per unit of work (one warp: 16 strides of 32)
 constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
-constexpr uint32_t kInfBits = 0x7f800000u;
 
 template <int OP>
 __device__ __forceinline__ float spmspv_mul(float a, float v) {
@@ -56,8 +56,8 @@ __device__ __forceinline__ float spmspv_mul(float a, float v) {
 // device-resident state of one CSC matrix: two sets of counters used alternately, so that a launch
 // resets the set of the NEXT launch while nobody reads it (no host-side reset, replayable)
 struct SpmspvCounters {
-    uint32_t n_touched, cursor, bar[3], done;
-    uint32_t pad[2];
+    uint32_t q_tail, q_head, producers_done, bar[3], done;
+    uint32_t pad;
 };
 struct SpmspvState {
     uint32_t parity;
@@ -75,8 +75,9 @@ struct SpmspvParams {
     const float *mask;
     glb_idx_val_t *y;
     float *acc;
-    uint32_t *bitmap;   // plus-times: bit r = row r is in the touched list
-    uint32_t *touched;  // rows touched by this launch (capacity: rows of the shard)
+    uint32_t *bitmap;   // bit r = row r was touched by this launch (small frontiers only); at rest all zero
+    unsigned long long *queue;  // segments of long columns: {frontier slot, segment}
+    uint32_t queue_cap;
     SpmspvState *state;
     uint32_t row_begin, row_end;
     uint32_t num_rows, num_cols;
@@ -99,7 +100,7 @@ struct SpmspvParams {
     uint32_t dense_len;
 };
 
-// all CTAs of the launch are co-resident (2 per SM): a counter barrier
+// all CTAs of the launch are co-resident (4 per SM): a counter barrier
 __device__ __forceinline__ void grid_barrier(uint32_t *counter) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -113,58 +114,44 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void append_touched(const SpmspvParams &P, SpmspvCounters *C, bool first, uint32_t row, unsigned lane) {
-    const unsigned b = __ballot_sync(__activemask(), first);
-    if (!first) return;
-    const int leader = __ffs(int(b)) - 1;
-    uint32_t base = 0;
-    if (int(lane) == leader) base = atomicAdd(&C->n_touched, uint32_t(__popc(b)));
-    base = __shfl_sync(b, base, leader);
-    P.touched[base + __popc(b & ((1u << lane) - 1u))] = row;
-}
-
-// one warp, non-zeros [s, t) of one column, t - s <= kSeg
-template <int OP>
-__device__ __forceinline__ void scatter_span(const SpmspvParams &P, SpmspvCounters *C, uint32_t s, uint32_t t, float v,
-                                             unsigned lane) {
-    for (uint32_t i0 = s; i0 < t; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        bool first = false;
-        uint32_t row = 0;
-        if (i < t) {
-            row = __ldg(P.indices + i);
-            const float p = spmspv_mul<OP>(__ldg(P.vals + i), v);
-            float *a = P.acc + row;
-            if (OP == GLB_OP_MUL_ADD) {
-                atomicAdd(a, p);
-                const uint32_t w = row >> 5, bit = 1u << (row & 31u);
-                if (!(P.bitmap[w] & bit)) first = !(atomicOr(P.bitmap + w, bit) & bit);  // (a stale cached 0 only costs a retry)
-            } else if (OP == GLB_OP_LOGICAL_AND_OR) {
-                // idempotent: the first writer flips 0.0f -> 1.0f and owns the row
-                if (p != 0.0f && *a == 0.0f) first = atomicExch(reinterpret_cast<uint32_t *>(a), 0x3f800000u) == 0u;
-            } else {
-                // float min through integer atomics: non-negative floats order like ints, negative ones
-                // inversely as unsigned; the accumulator rests at +inf and leaves it exactly once
-                if (p >= 0.0f) first = uint32_t(atomicMin(reinterpret_cast<int *>(a), __float_as_int(p))) == kInfBits;
-                else first = atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(p)) == kInfBits;
-            }
+// Non-zeros [s, t) of one column by a group of STRIDE lanes (`sub` = lane inside the group): all combines
+// are fire-and-forget (reduction atomics / idempotent stores), so the index / value loads of a lane are in
+// flight together and nothing waits for an accumulator.  MARK: also set the row's bit in the touched bitmap.
+template <int OP, bool MARK, int STRIDE>
+__device__ __forceinline__ void scatter_span(const SpmspvParams &P, uint32_t s, uint32_t t, float v, unsigned sub) {
+#pragma unroll 8
+    for (uint32_t i = s + sub; i < t; i += STRIDE) {
+        const uint32_t row = __ldg(P.indices + i);
+        const float p = spmspv_mul<OP>(__ldg(P.vals + i), v);
+        float *a = P.acc + row;
+        if (OP == GLB_OP_MUL_ADD) {
+            atomicAdd(a, p);
+        } else if (OP == GLB_OP_LOGICAL_AND_OR) {
+            if (p != 0.0f) *a = 1.0f;  // idempotent: racing writers store the same word
+        } else {
+            // float min through integer atomics: non-negative floats order like ints, negative ones inversely as unsigned
+            if (p >= 0.0f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(p));
+            else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(p));
         }
-        append_touched(P, C, first, row, lane);
+        if (MARK) atomicOr(P.bitmap + (row >> 5), 1u << (row & 31u));
     }
 }
 
+constexpr int kSub = 8;                 // lanes per light column: a warp works on 32 / kSub columns at a time
+constexpr int kColsPerWarp = 32 / kSub;
+  // heavy columns a CTA can queue for its warps to share
+
 template <int OP>
-__global__ void __launch_bounds__(kThreads, 2) spmspv_kernel(const SpmspvParams P) {
-    __shared__ uint32_t s_batch;
-    __shared__ uint32_t s_seg_end[kWarps + 1];  // prefix of the batch's segment counts
-    __shared__ uint32_t s_col_s[kWarps], s_col_t[kWarps];
-    __shared__ float s_col_v[kWarps];
+__global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams P) {
     __shared__ uint32_t s_last;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     SpmspvState *S = P.state;
     const uint32_t par = S->parity;  // flipped by CTA 0 after the first barrier: every CTA has read it by then
     SpmspvCounters *C = &S->c[par];
     const uint32_t nnz_x = P.x[0].index;
+    // Small frontier: mark the touched rows in the bitmap, so that phase 2 visits only those instead of
+    // scanning the shard's accumulator; a large frontier touches most rows anyway and saves the marks.
+    const bool tracked = uint64_t(nnz_x) * 64u <= uint64_t(P.row_end - P.row_begin);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.y[0].index = 0;
         P.y[0].val = P.zero;
@@ -173,104 +160,137 @@ __global__ void __launch_bounds__(kThreads, 2) spmspv_kernel(const SpmspvParams 
             P.ep_new_frontier[0].val = 0.0f;
         }
         SpmspvCounters *N = &S->c[par ^ 1u];  // the next launch's counters
-        N->n_touched = 0; N->cursor = 0; N->bar[0] = 0; N->bar[1] = 0; N->bar[2] = 0; N->done = 0;
+        N->q_tail = 0; N->q_head = 0; N->producers_done = 0; N->bar[0] = 0; N->bar[1] = 0; N->bar[2] = 0; N->done = 0;
     }
 
-    // ---- phase 1: scatter ---------------------------------------------------------------------
-    const uint32_t n_batches = (nnz_x + kWarps - 1) / kWarps;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_batch = atomicAdd(&C->cursor, 1u);
-        __syncthreads();
-        const uint32_t batch = s_batch;
-        if (batch >= n_batches) break;
-        if (lane == 0) {
-            const uint32_t k = batch * kWarps + warp;
-            uint32_t s = 0, t = 0;
-            float v = 0.0f;
-            if (k < nnz_x) {
-                const glb_idx_val_t e = P.x[k + 1];
-                if (e.index < P.num_cols) {  // not a column of this matrix: ignored
-                    s = __ldg(P.indptr + e.index);
-                    t = __ldg(P.indptr + e.index + 1);
-                    v = e.val;
-                }
+    // ---- phase 1a: short columns, and the long ones cut into queued segments ------------------------
+    // What bounds this phase on short columns is the dependent chain frontier entry -> column bounds ->
+    // indices -> atomics, one chain per column: so a warp works on 4 columns at a time (8 lanes each).
+    // Consecutive frontier entries go to different CTAs (a 6-vertex frontier must not land on one SM).
+    // A column longer than kSeg non-zeros is cut into kSeg-long segments pushed to a device-wide queue
+    // that all warps of the grid work off in phase 1b, after a grid barrier: a 10^4-long hub column is
+    // spread over many SMs -- the reduction atomics of ONE SM retire at ~1 per clock, 27 000 of them
+    // would take 20 us.  A launch without long columns skips phase 1b and its barrier.
+    const unsigned sub = lane & (kSub - 1), grp = lane / kSub;
+    const unsigned grp_mask = ((1u << kSub) - 1u) << (grp * kSub);  // control flow is uniform per lane group
+    const uint32_t n_lane_groups = gridDim.x * kWarps * kColsPerWarp;
+    for (uint32_t k = (warp * kColsPerWarp + grp) * gridDim.x + blockIdx.x; k < nnz_x; k += n_lane_groups) {
+        const glb_idx_val_t e = P.x[k + 1];
+        if (e.index >= P.num_cols) continue;  // not a column of this matrix: ignored
+        const uint32_t s = __ldg(P.indptr + e.index), t = __ldg(P.indptr + e.index + 1);
+        if (t - s > kSeg) {
+            const uint32_t n_seg = (t - s + kSeg - 1) / kSeg;
+            uint32_t base = 0;
+            if (sub == 0) base = atomicAdd(&C->q_tail, n_seg);
+            base = __shfl_sync(grp_mask, base, int(grp * kSub));
+            const bool fits = base + n_seg <= P.queue_cap;  // (a frontier naming columns repeatedly can outgrow the queue)
+            for (uint32_t j = sub; j < n_seg && base + j < P.queue_cap; j += kSub) {
+                const unsigned long long item = fits ? ((unsigned long long)(k) << 32 | j) : ((unsigned long long)(k) << 32 | 0xfffffffeull);
+                P.queue[base + j] = item;
             }
-            s_col_s[warp] = s; s_col_t[warp] = t; s_col_v[warp] = v;
+            if (fits) continue;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (int w = 0; w < kWarps; ++w) {
-                s_seg_end[w] = run;
-                run += (s_col_t[w] - s_col_s[w] + kSeg - 1) / kSeg;
-            }
-            s_seg_end[kWarps] = run;
-        }
-        __syncthreads();
-        const uint32_t n_seg = s_seg_end[kWarps];
-        for (uint32_t g = warp; g < n_seg; g += kWarps) {
-            int w = 0;
-#pragma unroll
-            for (int q = 1; q < kWarps; ++q) w += (s_seg_end[q] <= g);
-            const uint32_t s = s_col_s[w] + (g - s_seg_end[w]) * kSeg;
-            const uint32_t t = s_col_t[w] - s > kSeg ? s + kSeg : s_col_t[w];
-            scatter_span<OP>(P, C, s, t, s_col_v[w], lane);
-        }
+        if (tracked) scatter_span<OP, true, kSub>(P, s, t, e.val, sub);
+        else scatter_span<OP, false, kSub>(P, s, t, e.val, sub);
     }
     grid_barrier(&C->bar[0]);
     if (blockIdx.x == 0 && threadIdx.x == 0) S->parity = par ^ 1u;
 
-    // ---- phase 2: compact the touched rows ---------------------------------------------------------
-    uint32_t n_touched;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(n_touched) : "l"(&C->n_touched) : "memory");
-    const uint32_t n_round = (n_touched + 31u) & ~31u;  // keep warps converged for the ballots
-    const uint32_t n_threads = gridDim.x * kThreads;
-    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n_round; q += n_threads) {
-        bool emit = false, improved = false;
-        float val = 0.0f;
-        uint32_t r = 0;
-        if (q < n_touched) {
-            r = __ldcg(P.touched + q);
-            const float a = __ldcg(P.acc + r);
+    // ---- phase 1b: the queued segments, one warp each (the queue is complete: every CTA passed the barrier) ----
+    uint32_t n_queued;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(n_queued) : "l"(&C->q_tail) : "memory");
+    if (n_queued > P.queue_cap) n_queued = P.queue_cap;
+    if (n_queued) {  // grid-uniform
+        const uint32_t n_warps = gridDim.x * kWarps;
+        for (uint32_t q = warp * gridDim.x + blockIdx.x; q < n_queued; q += n_warps) {  // consecutive segments on different SMs
+            const unsigned long long item = __ldcg(P.queue + q);
+            const uint32_t seg = uint32_t(item);
+            if (seg == 0xfffffffeu) continue;  // voided reservation (queue overflow): its producer walked the column itself
+            const glb_idx_val_t e = P.x[uint32_t(item >> 32) + 1];
+            const uint32_t t = __ldg(P.indptr + e.index + 1);
+            const uint32_t b = __ldg(P.indptr + e.index) + seg * kSeg;
+            const uint32_t b_end = t - b > kSeg ? b + kSeg : t;
+            if (tracked) scatter_span<OP, true, 32>(P, b, b_end, e.val, lane);
+            else scatter_span<OP, false, 32>(P, b, b_end, e.val, lane);
+        }
+        grid_barrier(&C->bar[2]);
+    }
+
+    // ---- phase 2: compact -----------------------------------------------------------------------------
+    // A warp step covers kBatch groups of 32 consecutive rows (lane = row inside the group: coalesced).
+    // Tracked: the step first reads the kBatch bitmap words and is skipped when all are zero.  All loads of
+    // a step (accumulator, mask, relax target) are issued together, the emitted entries are counted with
+    // shuffles and the output cursors are advanced once per step.
+    constexpr int kBatch = 8;
+    const uint32_t base_row = P.row_begin & ~31u;
+    const uint32_t n_groups = (P.row_end - base_row + 31u) >> 5;
+    const uint32_t n_warps_total = gridDim.x * kWarps, gwarp = blockIdx.x * kWarps + warp;
+    const bool relax = P.ep_mode == GLB_SPMSPV_EP_RELAX;
+    for (uint32_t g0 = gwarp * kBatch; g0 < n_groups; g0 += n_warps_total * kBatch) {
+        uint32_t my_word = 0xffffffffu;
+        if (tracked) {
+            my_word = (lane < kBatch && g0 + lane < n_groups) ? __ldcg(P.bitmap + (base_row >> 5) + g0 + lane) : 0u;
+            if (my_word) P.bitmap[(base_row >> 5) + g0 + lane] = 0u;  // back to rest
+            if (!__any_sync(kFull, my_word != 0u)) continue;
+        }
+        float a[kBatch], mk[kBatch], dv[kBatch];
+        uint32_t live = 0;  // bit j: row j of this lane is a candidate
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const uint32_t word = __shfl_sync(kFull, my_word, j);
+            const uint32_t r = base_row + ((g0 + j) << 5) + lane;
+            const bool ok = g0 + j < n_groups && r >= P.row_begin && r < P.row_end && ((word >> lane) & 1u);
+            a[j] = ok ? __ldcg(P.acc + r) : Semi<OP>::ident();
+            mk[j] = (ok && P.mask_type != GLB_MASK_NONE) ? P.mask[r] : 0.0f;
+            dv[j] = (ok && relax) ? P.ep_inout[r] : 0.0f;
+            if (ok) live |= 1u << j;
+        }
+        uint32_t emit = 0, improved = 0;
+        float val[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            val[j] = 0.0f;
+            if (!((live >> j) & 1u) || a[j] == Semi<OP>::ident()) continue;
+            const uint32_t r = base_row + ((g0 + j) << 5) + lane;
             P.acc[r] = Semi<OP>::ident();
-            if (OP == GLB_OP_MUL_ADD) P.bitmap[r >> 5] = 0u;  // every set bit of the word belongs to a row of this list
-            val = Semi<OP>::with_zero(P.zero, a);
+            val[j] = Semi<OP>::with_zero(P.zero, a[j]);
             bool off = false;
-            if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (P.mask[r] == P.zero);
-            else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (P.mask[r] != P.zero);
-            emit = !off && (val != P.zero);
-            if (emit && P.ep_mode == GLB_SPMSPV_EP_ASSIGN) P.ep_inout[r] = P.ep_val;
-            if (emit && P.ep_mode == GLB_SPMSPV_EP_RELAX && P.ep_inout[r] > val) {
-                P.ep_inout[r] = val;  // rows are unique in the list: no other thread touches this element
-                improved = true;
+            if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (mk[j] == P.zero);
+            else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (mk[j] != P.zero);
+            if (off || val[j] == P.zero) continue;
+            emit |= 1u << j;
+            if (P.ep_mode == GLB_SPMSPV_EP_ASSIGN) P.ep_inout[r] = P.ep_val;
+            if (relax && dv[j] > val[j]) {
+                P.ep_inout[r] = val[j];  // rows are unique: no other thread touches this element
+                improved |= 1u << j;
             }
         }
-        const unsigned b = __ballot_sync(kFull, emit);
-        if (b) {
-            uint32_t base = 0;
-            const int leader = __ffs(int(b)) - 1;
-            if (int(lane) == leader) base = atomicAdd(&P.y[0].index, uint32_t(__popc(b)));
-            base = __shfl_sync(kFull, base, leader);
-            if (emit) {
-                glb_idx_val_t o;
-                o.index = r;
-                o.val = val;
-                P.y[1 + base + __popc(b & ((1u << lane) - 1u))] = o;
+        // positions: exclusive prefix of the per-lane counts, one cursor update per list and step
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t bits = which ? improved : emit;
+            if (which && !relax) break;  // uniform
+            const uint32_t cnt = uint32_t(__popc(bits));
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t tq = __shfl_up_sync(kFull, incl, d);
+                if (int(lane) >= d) incl += tq;
             }
-        }
-        const unsigned bi = __ballot_sync(kFull, improved);
-        if (bi) {
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            if (total == 0) continue;  // uniform
+            glb_idx_val_t *list = which ? P.ep_new_frontier : P.y;
             uint32_t base = 0;
-            const int leader = __ffs(int(bi)) - 1;
-            if (int(lane) == leader) base = atomicAdd(&P.ep_new_frontier[0].index, uint32_t(__popc(bi)));
-            base = __shfl_sync(kFull, base, leader);
-            if (improved) {
-                glb_idx_val_t o;
-                o.index = r;
-                o.val = val;
-                P.ep_new_frontier[1 + base + __popc(bi & ((1u << lane) - 1u))] = o;
-            }
+            if (lane == 0) base = atomicAdd(&list[0].index, total);
+            base = __shfl_sync(kFull, base, 0) + (incl - cnt);
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j)
+                if ((bits >> j) & 1u) {
+                    glb_idx_val_t o;
+                    o.index = base_row + ((g0 + j) << 5) + lane;
+                    o.val = val[j];
+                    list[1 + base++] = o;
+                }
         }
     }
     if (!P.has_next) return;
@@ -298,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 2) spmspv_kernel(const SpmspvParams 
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(keep) : "l"(&S->keep_pushing) : "memory");
     if (keep) return;
     // pushing stops here: build the dense input of the first pull level, all CTAs together
+    const uint32_t n_threads = gridDim.x * kThreads;
     if (P.dense_mode == GLB_SPMSPV_DENSE_SCATTER) {  // `dense` was filled with the semiring zero when the run was set up
         const uint32_t count = P.y[0].index;
         for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < count; i += n_threads) {
@@ -362,7 +383,7 @@ __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
 
 template <int OP>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
-    spmspv_kernel<OP><<<ctx->num_sms * 2, kThreads, 0, ctx->stream>>>(P);
+    spmspv_kernel<OP><<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(P);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
@@ -449,8 +470,9 @@ int glb_csc_create_rows(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, con
     alloc(reinterpret_cast<void **>(&m->acc), sizeof(float) * num_rows);
     alloc(reinterpret_cast<void **>(&m->acc_inf), sizeof(float) * num_rows);
     alloc(reinterpret_cast<void **>(&m->bitmap), sizeof(uint32_t) * ((size_t(num_rows) + 31) / 32 + 1));
-    alloc(reinterpret_cast<void **>(&m->touched), sizeof(uint32_t) * (size_t(row_end - row_begin) + 32));
     alloc(reinterpret_cast<void **>(&m->state), sizeof(SpmspvState));
+    m->queue_cap = uint32_t(std::min<uint64_t>(nnz / kSeg + num_cols + 64, 0x7fffffffull));
+    alloc(reinterpret_cast<void **>(&m->queue), sizeof(unsigned long long) * m->queue_cap);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(m->indptr, indptr, sizeof(uint32_t) * (size_t(num_cols) + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz)
@@ -479,7 +501,7 @@ int glb_csc_destroy(glb_csc_t m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf);
-    cudaFree(m->bitmap); cudaFree(m->touched); cudaFree(m->state);
+    cudaFree(m->bitmap); cudaFree(m->state); cudaFree(m->queue);
     glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
@@ -504,7 +526,8 @@ int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_ty
     // every run: no launch depends on host-side state (launch sequences can be recorded at any time)
     P.acc = (op == GLB_OP_ADD_MIN) ? m->acc_inf : m->acc;
     P.bitmap = m->bitmap;
-    P.touched = m->touched;
+    P.queue = m->queue;
+    P.queue_cap = m->queue_cap;
     P.state = static_cast<SpmspvState *>(m->state);
     P.row_begin = m->row_begin;
     P.row_end = m->row_end;

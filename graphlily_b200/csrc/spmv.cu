@@ -52,6 +52,9 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef GLB_SPMV_WANT_CHUNKS
+#define GLB_SPMV_WANT_CHUNKS 2960ull  // half a wave of warps: only shards below ~3 M non-zeros get smaller chunks
+#endif
 #ifndef GLB_SPMV_PREFETCH
 #define GLB_SPMV_PREFETCH 2
 #endif
@@ -774,10 +777,13 @@ static int format_host(uint32_t num_rows, uint32_t num_cols, const uint32_t *ind
     // warp owns one chunk and a B200 holds 148 SMs x 5 CTAs x 8 warps = 5920 of them at a time: a shard
     // of a few million non-zeros (the BFS graph; 1/8 of C2 on 8 GPUs) would run 2-3 waves and lose up
     // to a third of the machine to the last, partly filled wave.  Small shards therefore get smaller
-    // chunks, so that there are at least ~6 waves.  GLB_SPMV_MAX_GROUPS=<1..8> overrides.
+    // chunks.  Measured on the BFS graph (13 M non-zeros): 256-nnz chunks (11 waves) ran a pull level in
+    // 45 us against 25 us with 1024-nnz chunks (2.2 waves) -- the per-chunk scan, flag words and
+    // fix-up rows cost more than the partly filled last wave -- so the threshold is low: only shards
+    // that would not even fill half the machine are cut finer.  GLB_SPMV_MAX_GROUPS=<1..8> overrides.
     uint32_t max_groups = GLB_MAX_GROUPS;
     {
-        const uint64_t want_chunks = 6ull * 5920ull;
+        const uint64_t want_chunks = GLB_SPMV_WANT_CHUNKS;
         while (max_groups > 1 && nnz / (uint64_t(GLB_GROUP) * max_groups) < want_chunks) max_groups >>= 1;
         if (const char *v = getenv("GLB_SPMV_MAX_GROUPS")) {
             const unsigned long g = strtoul(v, nullptr, 10);

@@ -124,7 +124,7 @@ def run_app(name, env, scale=1.0, reps=5, check=True, copy_results=False, hbm_pe
         ms, out, loop_ms = timed(fn)
         gteps = nnz / (ms / iters * 1e-3) / 1e9   # == nnz * iters / t for BFS / SSSP, nnz / t_iteration for PageRank
         modes[mode] = {"ms_total": ms, "ms_per_iteration": ms / iters, "iterations_per_sec": iters / ms * 1e3, "gteps": gteps}
-        if mode == "pull":
+        if loop_ev[2]:
             modes[mode].update(loop_only_ms_per_iteration=loop_ms / iters, loop_only_iterations_per_sec=iters / loop_ms * 1e3,
                                loop_only_gteps=nnz / (loop_ms / iters * 1e-3) / 1e9)
         if mode == "pull_push":
