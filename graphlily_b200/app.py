@@ -320,7 +320,7 @@ class BFS(ModuleCollection):
         self._begin_run()
         self._push_begin()
         self._home_lists()
-        self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [1.0]))
+        self.SpMSpV_.set_vector_single(source, 1.0)
         self.SpMSpV_.set_mask_constant(0.0, source, 1.0)      # distance, bfs.h:138-141
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)
 
@@ -566,7 +566,7 @@ class SSSP(ModuleCollection):
         self._begin_run()
         self._push_begin()
         self._home_lists()
-        self.SpMSpV_.send_vector_host_to_device(capi.sparse_to_numpy([source], [0.0]))
+        self.SpMSpV_.set_vector_single(source, 0.0)
         self.SpMSpV_.set_mask_constant(self.semiring_[2], source, 0.0)   # distance, sssp.h:172-176
         self.SparseAssign_.bind_mask_buf(self.SpMSpV_.results_buf)
         self.SparseAssign_.bind_inout_buf(self.SpMSpV_.mask_buf)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "glb_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
     "glb_ctx_destroy": (C.c_int, [_vp]),
     "glb_ctx_sync": (C.c_int, [_vp]),
+    "glb_device_sync": (C.c_int, [_vp]),
     "glb_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "glb_ctx_kernel_timing": (C.c_int, [_vp, C.c_int]),
     "glb_ctx_kernel_timing_read": (C.c_int, [_vp, C.POINTER(C.c_double)]),
@@ -96,6 +97,7 @@ SIGNATURES = {
                                    C.POINTER(SpmspvNext)]),
     "glb_spmspv_push_state": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "glb_spmspv_reset_levels": (C.c_int, [_vp, _vp]),
+    "glb_sparse_fill_one": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float]),
     "glb_sparse_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
     "glb_sparse_to_dense_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float]),
     "glb_dense_to_sparse": (C.c_int, [_vp, _vp, C.c_uint32, C.c_float, _vp]),

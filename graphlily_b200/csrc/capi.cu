@@ -119,6 +119,13 @@ int glb_ctx_sync(glb_ctx_t ctx) {
     return GLB_OK;
 }
 
+int glb_device_sync(glb_ctx_t ctx) {
+    GLB_REQUIRE(ctx, "ctx is NULL");
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    GLB_CUDA(cudaDeviceSynchronize());
+    return GLB_OK;
+}
+
 int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream) {
     GLB_REQUIRE(ctx && cuda_stream, "NULL argument");
     *cuda_stream = ctx->stream;

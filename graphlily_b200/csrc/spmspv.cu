@@ -376,6 +376,13 @@ __global__ void __launch_bounds__(kThreads) dense_to_sparse_kernel(const float *
     }
 }
 
+__global__ void sparse_one_kernel(glb_idx_val_t *list, uint32_t index, float val) {
+    list[0].index = 1;
+    list[0].val = 0.0f;
+    list[1].index = index;
+    list[1].val = val;
+}
+
 __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
     list[0].index = 0;
     list[0].val = zero;
@@ -590,6 +597,13 @@ int glb_spmspv_reset_levels(glb_ctx_t ctx, glb_csc_t m) {
     GLB_REQUIRE(ctx && m && m->ctx == ctx, "bad argument");
     // keep_pushing, push_levels (parity and the counter sets are left alone)
     GLB_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(m->state) + sizeof(uint32_t), 0, 2 * sizeof(uint32_t), ctx->stream));
+    return GLB_OK;
+}
+
+int glb_sparse_fill_one(glb_ctx_t ctx, glb_idx_val_t *list, uint32_t index, float val) {
+    GLB_REQUIRE(ctx && list, "NULL argument");
+    sparse_one_kernel<<<1, 1, 0, ctx->stream>>>(list, index, val);
+    GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
 

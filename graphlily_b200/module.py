@@ -210,6 +210,10 @@ class SpMSpVModule(BaseModule):
         """``vector``: idx_val_t array with the {nnz, -} head (spmspv_module.h:374-399)."""
         self.vector_buf.write(np.ascontiguousarray(vector, capi.IDX_VAL))
 
+    def set_vector_single(self, index, val):
+        """The one-entry start frontier, written on the device (no blocking upload)."""
+        capi.check(capi.lib.glb_sparse_fill_one(self.ctx.handle, self.vector_buf.ptr, int(index), float(val)))
+
     def send_mask_host_to_device(self, mask):
         self.mask_buf = self._dense_to_device(mask)          # spmspv_module.h:403-433
 

@@ -172,6 +172,10 @@ public:
         pull_loop(iter, num_iterations);
         return SpMSpV_->send_mask_device_to_host();  // the mask of SpMV on the host is not valid
     }
+
+    // compute_reference_results (reference: app/bfs.h:350-360): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    aligned_dense_float_vec_t compute_reference_results(uint32_t source, uint32_t num_iterations);
 };
 
 }  // namespace app

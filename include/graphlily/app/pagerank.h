@@ -88,6 +88,10 @@ public:
         }
         return SpMV_->send_vector_device_to_host();
     }
+
+    // compute_reference_results (reference: app/pagerank.h:150-159): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    aligned_dense_float_vec_t compute_reference_results(float damping, uint32_t num_iterations);
 };
 
 }  // namespace app

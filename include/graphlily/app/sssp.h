@@ -196,6 +196,10 @@ public:
         pull_loop(iter, num_iterations);
         return SpMV_->send_vector_device_to_host();
     }
+
+    // compute_reference_results (reference: app/sssp.h:245-253): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    aligned_dense_float_vec_t compute_reference_results(uint32_t source, uint32_t num_iterations);
 };
 
 }  // namespace app

@@ -67,6 +67,7 @@ using aligned_sparse_vec_t = std::vector<idx_val_t, aligned_allocator<idx_val_t>
 using aligned_dense_float_vec_t = std::vector<float, aligned_allocator<float>>;
 using aligned_sparse_float_vec_t = std::vector<idx_float_t, aligned_allocator<idx_float_t>>;
 
+const val_t UINT_INF = 0xffffffff;   // global.h:78 (the infinity of the unsigned val_t build)
 const val_t UFIXED_INF = 255;        // the shipped TropicalSemiring zero (global.h:79,99)
 const val_t FLOAT_INF = 999999999;   // global.h:80
 

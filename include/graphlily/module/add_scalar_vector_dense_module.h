@@ -42,6 +42,11 @@ public:
         download(out_, out_buf, out_buf.bytes() / sizeof(vector_data_t));
         return out_;
     }
+
+    // compute_reference_results (reference: add_scalar_vector_dense_module.h:195-204): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    graphlily::aligned_dense_float_vec_t compute_reference_results(graphlily::aligned_dense_float_vec_t const &in, uint32_t len,
+                                                                   float val);
 };
 
 }  // namespace module

@@ -56,6 +56,12 @@ public:
         download(inout_, inout_buf, inout_buf.bytes() / sizeof(vector_data_t));
         return inout_;
     }
+
+    // compute_reference_results (reference: assign_vector_dense_module.h:223-246): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    void compute_reference_results(graphlily::aligned_dense_float_vec_t &mask, graphlily::aligned_dense_float_vec_t &inout,
+                                   uint32_t len, float val);
+    graphlily::MaskType mask_type() const { return mask_type_; }
 };
 
 }  // namespace module

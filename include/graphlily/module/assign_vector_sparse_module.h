@@ -86,6 +86,13 @@ public:
         download(new_frontier_, new_frontier_buf, size_t(count_of(new_frontier_buf)) + 1);
         return new_frontier_;
     }
+
+    // compute_reference_results (reference: assign_vector_sparse_module.h:306-335): declared for the reference's callers, defined only by
+    // the test adapter tests/cpp/ref_compat/reference_results.h (oracle/); the product has no CPU path.
+    void compute_reference_results(graphlily::aligned_sparse_float_vec_t &mask, graphlily::aligned_dense_float_vec_t &inout,
+                                   float val);
+    void compute_reference_results(graphlily::aligned_sparse_float_vec_t &mask, graphlily::aligned_dense_float_vec_t &inout,
+                                   graphlily::aligned_sparse_float_vec_t &new_frontier);
 };
 
 }  // namespace module

@@ -13,10 +13,10 @@
 #include "graphlily/io/data_loader.h"
 #include "graphlily/module/base_module.h"
 
+using graphlily::io::CSCMatrix;  // at file scope, as in the reference (spmspv_module.h:17)
+
 namespace graphlily {
 namespace module {
-
-using graphlily::io::CSCMatrix;
 
 template <typename matrix_data_t, typename vector_data_t, typename idx_val_t>
 class SpMSpVModule : public BaseModule {
@@ -105,7 +105,16 @@ public:
     uint32_t get_results_nnz() { return count_of(results_buf); }
     uint32_t get_vector_nnz() { return count_of(vector_buf); }
 
+    // compute_reference_results (reference: spmspv_module.h:446-520) is DECLARED here so that the reference's own callers
+    // compile, but the product does not contain a CPU implementation: the definition is test
+    // infrastructure (tests/cpp/ref_compat/reference_results.h, which links oracle/); without it the call
+    // fails at link time.
+    graphlily::aligned_dense_float_vec_t compute_reference_results(graphlily::aligned_sparse_float_vec_t &vector,
+                                                                   graphlily::aligned_dense_float_vec_t &mask);
+
     CSCMatrix<float> const &host_matrix() { return csc_matrix_float_; }
+    graphlily::SemiringType semiring() const { return semiring_; }
+    graphlily::MaskType mask_type() const { return mask_type_; }
 };
 
 }  // namespace module

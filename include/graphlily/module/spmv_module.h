@@ -6,8 +6,8 @@
 // formatting + 16-channel upload (:282-420) becomes glb_csr_create (lane-segment layout); run()
 // (:471-475: setArg + enqueueTask + finish) becomes glb_spmv on the runtime's stream -- it returns
 // without synchronising, every send_*_device_to_host synchronises.
-// compute_reference_results (:478-532) is not part of the product: the CPU restatement lives in
-// oracle/ and is linked by the tests only.
+// compute_reference_results (:478-532) is declared but not defined by the product: the CPU restatement
+// lives in oracle/ and is linked by the tests only (tests/cpp/ref_compat/reference_results.h).
 #ifndef GRAPHLILY_SPMV_MODULE_H_
 #define GRAPHLILY_SPMV_MODULE_H_
 
@@ -17,10 +17,10 @@
 #include "graphlily/io/data_loader.h"
 #include "graphlily/module/base_module.h"
 
+using graphlily::io::CSRMatrix;  // at file scope, as in the reference (spmv_module.h:17): its callers name it unqualified
+
 namespace graphlily {
 namespace module {
-
-using graphlily::io::CSRMatrix;
 
 template <typename matrix_data_t, typename vector_data_t>
 class SpMVModule : public BaseModule {
@@ -133,8 +133,18 @@ public:
         return results_;
     }
 
+    // compute_reference_results (reference: spmv_module.h:478-532) is DECLARED here so that the reference's own callers
+    // compile, but the product does not contain a CPU implementation: the definition is test
+    // infrastructure (tests/cpp/ref_compat/reference_results.h, which links oracle/); without it the call
+    // fails at link time.
+    graphlily::aligned_dense_float_vec_t compute_reference_results(graphlily::aligned_dense_float_vec_t &vector);
+    graphlily::aligned_dense_float_vec_t compute_reference_results(graphlily::aligned_dense_float_vec_t &vector,
+                                                                   graphlily::aligned_dense_float_vec_t &mask);
+
     glb_csr_t device_matrix() { return matrix_; }
     CSRMatrix<float> const &host_matrix() { return csr_matrix_float_; }
+    graphlily::SemiringType semiring() const { return semiring_; }
+    graphlily::MaskType mask_type() const { return mask_type_; }
 };
 
 }  // namespace module

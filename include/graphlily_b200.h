@@ -80,7 +80,10 @@ int glb_device_count(int *count);
  * caller's torch stream) or NULL to create a private non-blocking stream. */
 int glb_ctx_create(int device, void *cuda_stream, glb_ctx_t *out);
 int glb_ctx_destroy(glb_ctx_t ctx);
-int glb_ctx_sync(glb_ctx_t ctx); /* command_queue_.finish() */
+int glb_ctx_sync(glb_ctx_t ctx);
+/* Waits for ALL work on the context's device (every stream): what command_queue.finish() means to a
+ * caller that shares buffers between modules with runtimes of their own. */
+int glb_device_sync(glb_ctx_t ctx); /* command_queue_.finish() */
 int glb_ctx_stream(glb_ctx_t ctx, void **cuda_stream);
 /* Per-kernel device timing for roofline accounting (the queues of the reference are created
  * with CL_QUEUE_PROFILING_ENABLE, base_module.h:127).  While enabled, glb_spmv / glb_spmv_fused
@@ -260,6 +263,9 @@ int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_ty
  * `next` block since glb_spmspv_reset_levels (stream-ordered) -- push_iterations of a pull_push run. */
 int glb_spmspv_push_state(glb_ctx_t ctx, glb_csc_t m, uint32_t *keep_pushing, uint32_t *push_levels);
 int glb_spmspv_reset_levels(glb_ctx_t ctx, glb_csc_t m);
+/* list = {1, 0}, {index, val}: the one-entry start frontier of the push apps (bfs.h:131-135, sssp.h:169-171),
+ * built on the device (stream-ordered) instead of uploaded with a blocking copy. */
+int glb_sparse_fill_one(glb_ctx_t ctx, glb_idx_val_t *list, uint32_t index, float val);
 /* SpMSpVModule::get_results_nnz (spmspv_module.h:239-242): blocking read of list[0].index. */
 int glb_sparse_count(glb_ctx_t ctx, const glb_idx_val_t *list, uint32_t *count);
 /* convert_sparse_vec_to_dense_vec (global.h:153-164) done on the device (the reference does it

@@ -77,3 +77,26 @@ def test_cpp_npz_reader_on_scipy_files(tmp_path):
 def test_cpp_modules_and_apps_on_gpu(name):
     out = _run(name)
     assert "FAILED" not in out
+
+
+@pytest.mark.gpu
+def test_reference_own_test_files_unmodified(tmp_path):
+    """SURVEY.md 8b "Callers: same call sequences must compile and run": the reference's OWN gtest files
+    (/root/reference/tests/test_app.cpp, test_module_spmv_spmspv.cpp, test_module_apply.cpp), compiled
+    unmodified against include/graphlily (tests/cpp/Makefile: ref_* targets, built where /root/reference
+    exists), run here on the datasets they name -- seeded synthetic matrices of those shapes -- and pass:
+    every kernel result within their own 1e-4 of compute_reference_results."""
+    import sys
+    bins = [os.path.join(BIN, n) for n in ("ref_test_app", "ref_test_module_spmv_spmspv", "ref_test_module_apply")]
+    if not all(os.path.exists(b) for b in bins):
+        if not os.path.exists("/root/reference/tests/test_app.cpp"):
+            pytest.skip("the ref_* binaries are built from /root/reference in the build container")
+        _build()
+    data = tmp_path / "sparse_matrix_graph"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_ref_test_data.py"), str(data)],
+                          stdout=subprocess.DEVNULL)
+    for exe in bins:
+        env = dict(os.environ, GLB_DATASET_DIR=str(data))
+        p = subprocess.run([exe], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, f"{exe} failed:\n{p.stdout[-4000:]}\n{p.stderr[-2000:]}"
+        assert "0 test(s) failed" in p.stdout and "[  OK  ]" in p.stdout
