@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GLB_LIB_PATH") or os.path.join(_HERE, "lib", "libgraphlily_b200.so")   # env: tuning builds only
 
 OP_MUL_ADD, OP_LOGICAL_AND_OR, OP_ADD_MIN = 0, 1, 2
+VAL_F32, VAL_U32, VAL_UFIXED = 0, 1, 2
 MASK_NONE, MASK_WRITE_TO_ZERO, MASK_WRITE_TO_ONE = 0, 1, 2
 
 IDX_VAL = np.dtype([("index", np.uint32), ("val", np.float32)])
@@ -106,6 +107,12 @@ SIGNATURES = {
     "glb_assign_dense": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_float, C.c_int]),
     "glb_assign_sparse": (C.c_int, [_vp, _vp, _vp, C.c_float]),
     "glb_assign_sparse_relax": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "glb_spmv_vt": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp, C.POINTER(Epilogue)]),
+    "glb_spmspv_vt": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp]),
+    "glb_ewise_add_vt": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint32, C.c_uint32]),
+    "glb_assign_dense_vt": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "glb_assign_sparse_vt": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint32]),
+    "glb_assign_sparse_relax_vt": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "glb_nccl_available": (C.c_int, []),
     "glb_nccl_unique_id": (C.c_int, [_vp]),
     "glb_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),

@@ -10,13 +10,17 @@
 //
 // All four are pure HBM streams / scatters: 128-bit vector accesses where the layout allows,
 // grids sized as multiples of the SM count, list lengths read on the device from slot 0.
+#include <string.h>
+
 #include "glb_internal.h"
+#include "semiring.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
+template <int VT>
 __global__ void __launch_bounds__(kThreads) ewise_add_kernel(const float *in, float *out, uint32_t len, float val) {
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
@@ -28,17 +32,18 @@ __global__ void __launch_bounds__(kThreads) ewise_add_kernel(const float *in, fl
         float4 *out4 = reinterpret_cast<float4 *>(out);
         for (uint32_t i = tid; i < n4; i += stride) {
             float4 v = in4[i];
-            v.x = __fadd_rn(v.x, val);
-            v.y = __fadd_rn(v.y, val);
-            v.z = __fadd_rn(v.z, val);
-            v.w = __fadd_rn(v.w, val);
+            v.x = Val<VT>::plus(v.x, val);
+            v.y = Val<VT>::plus(v.y, val);
+            v.z = Val<VT>::plus(v.z, val);
+            v.w = Val<VT>::plus(v.w, val);
             out4[i] = v;
         }
         done = n4 << 2;
     }
-    for (uint32_t i = done + tid; i < len; i += stride) out[i] = __fadd_rn(in[i], val);
+    for (uint32_t i = done + tid; i < len; i += stride) out[i] = Val<VT>::plus(in[i], val);
 }
 
+template <int VT>
 __global__ void __launch_bounds__(kThreads) assign_dense_kernel(const float *mask, float *inout, uint32_t len, float val,
                                                               int write_to_one) {
     const uint32_t stride = gridDim.x * kThreads;
@@ -52,8 +57,8 @@ __global__ void __launch_bounds__(kThreads) assign_dense_kernel(const float *mas
         float4 *io4 = reinterpret_cast<float4 *>(inout);
         for (uint32_t i = tid; i < n4; i += stride) {
             const float4 m = m4[i];
-            const bool h0 = (m.x != 0.0f) == want, h1 = (m.y != 0.0f) == want, h2 = (m.z != 0.0f) == want,
-                       h3 = (m.w != 0.0f) == want;
+            const bool h0 = !Val<VT>::is_zero(m.x) == want, h1 = !Val<VT>::is_zero(m.y) == want,
+                       h2 = !Val<VT>::is_zero(m.z) == want, h3 = !Val<VT>::is_zero(m.w) == want;
             if (h0 & h1 & h2 & h3) {
                 io4[i] = make_float4(val, val, val, val);
             } else {
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) assign_dense_kernel(const float *mas
         done = n4 << 2;
     }
     for (uint32_t i = done + tid; i < len; i += stride) {
-        const bool nz = mask[i] != 0.0f;
+        const bool nz = !Val<VT>::is_zero(mask[i]);
         if (nz == want) inout[i] = val;
     }
 }
@@ -83,9 +88,10 @@ __global__ void __launch_bounds__(kThreads) assign_sparse_kernel(const glb_idx_v
 // (assign_vector_sparse_module.h:318-335); true when THIS entry lowered the value.  A compare-and-
 // swap loop instead of a plain compare-then-store so that lists naming an index more than once
 // end with the minimum whatever the interleaving (NaN never wins the comparison, as in the host loop).
+template <int VT>
 __device__ __forceinline__ bool relax_min(float *addr, float val) {
     float old = *addr;
-    while (old > val) {
+    while (Val<VT>::less(val, old)) {
         const int seen = atomicCAS(reinterpret_cast<int *>(addr), __float_as_int(old), __float_as_int(val));
         if (seen == __float_as_int(old)) return true;
         old = __int_as_float(seen);
@@ -99,6 +105,7 @@ __device__ __forceinline__ bool relax_min(float *addr, float val) {
 // frontier then holds every entry that lowered the value at the moment it was applied -- always
 // including the one carrying the final minimum -- where the reference lists the record lows in
 // list order.
+template <int VT>
 __global__ void __launch_bounds__(kThreads) assign_sparse_relax_kernel(const glb_idx_val_t *__restrict__ list,
                                                                      float *inout, glb_idx_val_t *new_frontier) {
     const unsigned lane = threadIdx.x & 31u;
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) assign_sparse_relax_kernel(const glb
         glb_idx_val_t e = {0u, 0.0f};
         if (i < n) {
             e = list[i + 1];
-            emit = relax_min(inout + e.index, e.val);
+            emit = relax_min<VT>(inout + e.index, e.val);
         }
         const unsigned b = __ballot_sync(kFull, emit);
         if (b) {
@@ -133,26 +140,55 @@ inline unsigned grid_for(glb_ctx_t ctx, uint64_t work_items, int per_sm) {
 
 }  // namespace
 
+static inline float from_bits(uint32_t bits) {
+    float f;
+    memcpy(&f, &bits, sizeof(f));
+    return f;
+}
+
+#define GLB_VT_DISPATCH(vt, CALL)                                      \
+    switch (vt) {                                                      \
+        case GLB_VAL_F32: { constexpr int VT = GLB_VAL_F32; CALL; break; }       \
+        case GLB_VAL_U32: { constexpr int VT = GLB_VAL_U32; CALL; break; }       \
+        case GLB_VAL_UFIXED: { constexpr int VT = GLB_VAL_UFIXED; CALL; break; } \
+        default: glb_set_error("%s: invalid value type %d", __func__, vt); return GLB_EINVAL; \
+    }
+
 extern "C" {
 
-int glb_ewise_add(glb_ctx_t ctx, const float *in, float *out, uint32_t len, float val) {
+int glb_ewise_add_vt(glb_ctx_t ctx, int val_type, const void *in, void *out, uint32_t len, uint32_t val_bits) {
     GLB_REQUIRE(ctx && (len == 0 || (in && out)), "NULL argument");
     if (len == 0) return GLB_OK;
-    ewise_add_kernel<<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(in, out, len, val);
+    GLB_VT_DISPATCH(val_type, (ewise_add_kernel<VT><<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(
+                                   static_cast<const float *>(in), static_cast<float *>(out), len, from_bits(val_bits))));
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
 
-int glb_assign_dense(glb_ctx_t ctx, const float *mask, float *inout, uint32_t len, float val, int mask_type) {
+int glb_ewise_add(glb_ctx_t ctx, const float *in, float *out, uint32_t len, float val) {
+    uint32_t bits;
+    memcpy(&bits, &val, sizeof(bits));
+    return glb_ewise_add_vt(ctx, GLB_VAL_F32, in, out, len, bits);
+}
+
+int glb_assign_dense_vt(glb_ctx_t ctx, int val_type, const void *mask, void *inout, uint32_t len, uint32_t val_bits,
+                        int mask_type) {
     GLB_REQUIRE(ctx && (len == 0 || (mask && inout)), "NULL argument");
     // the reference prints "Please set the mask type" and exits (assign_vector_dense_module.h:88-95)
     GLB_REQUIRE(mask_type == GLB_MASK_WRITE_TO_ZERO || mask_type == GLB_MASK_WRITE_TO_ONE,
                 "dense assign needs kMaskWriteToZero or kMaskWriteToOne");
     if (len == 0) return GLB_OK;
-    assign_dense_kernel<<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(mask, inout, len, val,
-                                                                             mask_type == GLB_MASK_WRITE_TO_ONE);
+    GLB_VT_DISPATCH(val_type, (assign_dense_kernel<VT><<<grid_for(ctx, (uint64_t(len) + 3) / 4, 8), kThreads, 0, ctx->stream>>>(
+                                   static_cast<const float *>(mask), static_cast<float *>(inout), len, from_bits(val_bits),
+                                   mask_type == GLB_MASK_WRITE_TO_ONE)));
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
+}
+
+int glb_assign_dense(glb_ctx_t ctx, const float *mask, float *inout, uint32_t len, float val, int mask_type) {
+    uint32_t bits;
+    memcpy(&bits, &val, sizeof(bits));
+    return glb_assign_dense_vt(ctx, GLB_VAL_F32, mask, inout, len, bits, mask_type);
 }
 
 int glb_assign_sparse(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, float val) {
@@ -162,14 +198,24 @@ int glb_assign_sparse(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, fl
     return GLB_OK;
 }
 
-int glb_assign_sparse_relax(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, glb_idx_val_t *new_frontier) {
+int glb_assign_sparse_vt(glb_ctx_t ctx, int val_type, const glb_idx_val_t *list, void *inout, uint32_t val_bits) {
+    GLB_REQUIRE(val_type >= GLB_VAL_F32 && val_type <= GLB_VAL_UFIXED, "invalid value type");
+    return glb_assign_sparse(ctx, list, static_cast<float *>(inout), from_bits(val_bits));  // a store of the word: the same for every type
+}
+
+int glb_assign_sparse_relax_vt(glb_ctx_t ctx, int val_type, const glb_idx_val_t *list, void *inout, glb_idx_val_t *new_frontier) {
     GLB_REQUIRE(ctx && list && inout && new_frontier, "NULL argument");
     GLB_REQUIRE(static_cast<const void *>(list) != static_cast<const void *>(new_frontier),
                 "new_frontier must not alias list");
-    GLB_CUDA(cudaMemsetAsync(new_frontier, 0, sizeof(glb_idx_val_t), ctx->stream));  // head = {0, 0.0f}
-    assign_sparse_relax_kernel<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(list, inout, new_frontier);
+    GLB_CUDA(cudaMemsetAsync(new_frontier, 0, sizeof(glb_idx_val_t), ctx->stream));  // head = {0, 0}
+    GLB_VT_DISPATCH(val_type, (assign_sparse_relax_kernel<VT><<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(
+                                   list, static_cast<float *>(inout), new_frontier)));
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
+}
+
+int glb_assign_sparse_relax(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, glb_idx_val_t *new_frontier) {
+    return glb_assign_sparse_relax_vt(ctx, GLB_VAL_F32, list, inout, new_frontier);
 }
 
 }  // extern "C"

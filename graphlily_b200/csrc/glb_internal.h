@@ -51,7 +51,7 @@ struct glb_ctx_s {
     size_t staging_bytes = 0;
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     // kernel attributes already applied on this device (cudaFuncSetAttribute is per device)
-    int carveout_set[3] = {-1, -1, -1};
+    int carveout_set[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // [value type][semiring]
     int bits_carveout_set = -1;
     size_t tile_smem_set[3] = {0, 0, 0};
     // recording the two arms of a branch (glb_graph_branch_*): launches go to a side stream that
@@ -143,6 +143,7 @@ struct glb_csc_s {
     float *vals = nullptr;
     float *acc = nullptr;         // dense accumulator of plus-times / or-and, num_rows, at rest 0.0f between runs
     float *acc_inf = nullptr;     // dense accumulator of min-plus, at rest +inf
+    float *acc_max = nullptr;     // ... of min-plus on the integer value types, at rest 0xffffffff (allocated on first use)
     uint32_t *bitmap = nullptr;   // rows touched by the running launch (small frontiers), all zero at rest
     unsigned long long *queue = nullptr;  // segment queue of the long columns (spmspv.cu), all ones at rest
     uint32_t queue_cap = 0;
@@ -205,6 +206,6 @@ struct GlbSpmvMc {
 // `wait`: acquire of the previous step's exchange, folded into the head of the launch's first kernel (or NULL)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
-                    const GlbXchgWait *wait, bool *published);
+                    const GlbXchgWait *wait, bool *published, int val_type);
 
 #endif  // GLB_INTERNAL_H_

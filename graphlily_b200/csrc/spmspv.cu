@@ -43,14 +43,17 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kSeg = 512;             // non-zeros per unit of work (one warp: 16 strides of 32)
 constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
 
-template <int OP>
+// (x) of the scatter.  fp32 min-plus clamps at FLOAT_INF like the reference's CPU path
+// (spmspv_module.h:482-491); the integer value types follow the processing element's ALU
+// (ufixed_pe_fwd.h:23-44): plain (wrapping / saturating) addition.
+template <int OP, int VT>
 __device__ __forceinline__ float spmspv_mul(float a, float v) {
-    if (OP == GLB_OP_ADD_MIN) {
+    if (OP == GLB_OP_ADD_MIN && VT == GLB_VAL_F32) {
         if (a > kFloatInf || v > kFloatInf) return kFloatInf;
         const float s = __fadd_rn(a, v);
         return s > kFloatInf ? kFloatInf : s;
     }
-    return Semi<OP>::mul(a, v);
+    return Semi<OP, VT>::mul(a, v);
 }
 
 // device-resident state of one CSC matrix: two sets of counters used alternately, so that a launch
@@ -117,21 +120,34 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter) {
 // Non-zeros [s, t) of one column by a group of STRIDE lanes (`sub` = lane inside the group): all combines
 // are fire-and-forget (reduction atomics / idempotent stores), so the index / value loads of a lane are in
 // flight together and nothing waits for an accumulator.  MARK: also set the row's bit in the touched bitmap.
-template <int OP, bool MARK, int STRIDE>
+template <int OP, bool MARK, int STRIDE, int VT>
 __device__ __forceinline__ void scatter_span(const SpmspvParams &P, uint32_t s, uint32_t t, float v, unsigned sub) {
 #pragma unroll 8
     for (uint32_t i = s + sub; i < t; i += STRIDE) {
         const uint32_t row = __ldg(P.indices + i);
-        const float p = spmspv_mul<OP>(__ldg(P.vals + i), v);
+        const float p = spmspv_mul<OP, VT>(__ldg(P.vals + i), v);
         float *a = P.acc + row;
         if (OP == GLB_OP_MUL_ADD) {
-            atomicAdd(a, p);
+            if (VT == GLB_VAL_F32) {
+                atomicAdd(a, p);
+            } else if (VT == GLB_VAL_U32) {
+                atomicAdd(reinterpret_cast<unsigned *>(a), __float_as_uint(p));  // modulo 2^32
+            } else {  // saturating sum: no such atomic, compare-and-swap (sums of non-negative words commute)
+                unsigned *w = reinterpret_cast<unsigned *>(a);
+                unsigned old = *w, seen;
+                do {
+                    seen = old;
+                    old = atomicCAS(w, seen, __float_as_uint(Val<VT>::plus(__uint_as_float(seen), p)));
+                } while (old != seen);
+            }
         } else if (OP == GLB_OP_LOGICAL_AND_OR) {
-            if (p != 0.0f) *a = 1.0f;  // idempotent: racing writers store the same word
-        } else {
+            if (!Val<VT>::is_zero(p)) *a = Val<VT>::one();  // idempotent: racing writers store the same word
+        } else if (VT == GLB_VAL_F32) {
             // float min through integer atomics: non-negative floats order like ints, negative ones inversely as unsigned
             if (p >= 0.0f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(p));
             else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(p));
+        } else {
+            atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(p));
         }
         if (MARK) atomicOr(P.bitmap + (row >> 5), 1u << (row & 31u));
     }
@@ -141,7 +157,7 @@ constexpr int kSub = 8;                 // lanes per light column: a warp works 
 constexpr int kColsPerWarp = 32 / kSub;
   // heavy columns a CTA can queue for its warps to share
 
-template <int OP>
+template <int OP, int VT>
 __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams P) {
     __shared__ uint32_t s_last;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -190,8 +206,8 @@ __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams 
             }
             if (fits) continue;
         }
-        if (tracked) scatter_span<OP, true, kSub>(P, s, t, e.val, sub);
-        else scatter_span<OP, false, kSub>(P, s, t, e.val, sub);
+        if (tracked) scatter_span<OP, true, kSub, VT>(P, s, t, e.val, sub);
+        else scatter_span<OP, false, kSub, VT>(P, s, t, e.val, sub);
     }
     grid_barrier(&C->bar[0]);
     if (blockIdx.x == 0 && threadIdx.x == 0) S->parity = par ^ 1u;
@@ -210,8 +226,8 @@ __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams 
             const uint32_t t = __ldg(P.indptr + e.index + 1);
             const uint32_t b = __ldg(P.indptr + e.index) + seg * kSeg;
             const uint32_t b_end = t - b > kSeg ? b + kSeg : t;
-            if (tracked) scatter_span<OP, true, 32>(P, b, b_end, e.val, lane);
-            else scatter_span<OP, false, 32>(P, b, b_end, e.val, lane);
+            if (tracked) scatter_span<OP, true, 32, VT>(P, b, b_end, e.val, lane);
+            else scatter_span<OP, false, 32, VT>(P, b, b_end, e.val, lane);
         }
         grid_barrier(&C->bar[2]);
     }
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams 
             const uint32_t word = __shfl_sync(kFull, my_word, j);
             const uint32_t r = base_row + ((g0 + j) << 5) + lane;
             const bool ok = g0 + j < n_groups && r >= P.row_begin && r < P.row_end && ((word >> lane) & 1u);
-            a[j] = ok ? __ldcg(P.acc + r) : Semi<OP>::ident();
+            a[j] = ok ? __ldcg(P.acc + r) : Semi<OP, VT>::ident();
             mk[j] = (ok && P.mask_type != GLB_MASK_NONE) ? P.mask[r] : 0.0f;
             dv[j] = (ok && relax) ? P.ep_inout[r] : 0.0f;
             if (ok) live |= 1u << j;
@@ -250,17 +266,17 @@ __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams 
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
             val[j] = 0.0f;
-            if (!((live >> j) & 1u) || a[j] == Semi<OP>::ident()) continue;
+            if (!((live >> j) & 1u) || Val<VT>::equal(a[j], Semi<OP, VT>::ident())) continue;
             const uint32_t r = base_row + ((g0 + j) << 5) + lane;
-            P.acc[r] = Semi<OP>::ident();
-            val[j] = Semi<OP>::with_zero(P.zero, a[j]);
+            P.acc[r] = Semi<OP, VT>::ident();
+            val[j] = Semi<OP, VT>::with_zero(P.zero, a[j]);
             bool off = false;
-            if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = (mk[j] == P.zero);
-            else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = (mk[j] != P.zero);
-            if (off || val[j] == P.zero) continue;
+            if (P.mask_type == GLB_MASK_WRITE_TO_ONE) off = Val<VT>::equal(mk[j], P.zero);
+            else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) off = !Val<VT>::equal(mk[j], P.zero);
+            if (off || Val<VT>::equal(val[j], P.zero)) continue;
             emit |= 1u << j;
             if (P.ep_mode == GLB_SPMSPV_EP_ASSIGN) P.ep_inout[r] = P.ep_val;
-            if (relax && dv[j] > val[j]) {
+            if (relax && Val<VT>::less(val[j], dv[j])) {
                 P.ep_inout[r] = val[j];  // rows are unique: no other thread touches this element
                 improved |= 1u << j;
             }
@@ -388,9 +404,9 @@ __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
     list[0].val = zero;
 }
 
-template <int OP>
+template <int OP, int VT>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
-    spmspv_kernel<OP><<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(P);
+    spmspv_kernel<OP, VT><<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(P);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }
@@ -507,16 +523,17 @@ int glb_csc_destroy(glb_csc_t m) {
     if (!m) return GLB_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf);
+    cudaFree(m->indptr); cudaFree(m->indices); cudaFree(m->vals); cudaFree(m->acc); cudaFree(m->acc_inf); cudaFree(m->acc_max);
     cudaFree(m->bitmap); cudaFree(m->state); cudaFree(m->queue);
     glb_ctx_release(m->ctx);
     delete m;
     return GLB_OK;
 }
 
-int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
-                     glb_idx_val_t *y, const glb_spmspv_epilogue_t *ep, const glb_spmspv_next_t *next) {
+static int spmspv_any(glb_ctx_t ctx, glb_csc_t m, int val_type, int op, float zero, int mask_type, const glb_idx_val_t *x,
+                      const float *mask, glb_idx_val_t *y, const glb_spmspv_epilogue_t *ep, const glb_spmspv_next_t *next) {
     GLB_REQUIRE(ctx && m && x && y, "NULL argument");
+    GLB_REQUIRE(val_type >= GLB_VAL_F32 && val_type <= GLB_VAL_UFIXED, "invalid value type");
     GLB_REQUIRE(m->ctx == ctx, "matrix belongs to another context");
     GLB_REQUIRE(mask_type >= GLB_MASK_NONE && mask_type <= GLB_MASK_WRITE_TO_ONE, "invalid mask type");
     GLB_REQUIRE(mask_type == GLB_MASK_NONE || mask, "mask is NULL but mask_type != kNoMask");
@@ -532,6 +549,13 @@ int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_ty
     // one accumulator per (+)-identity, both filled when the matrix was created and left at rest by
     // every run: no launch depends on host-side state (launch sequences can be recorded at any time)
     P.acc = (op == GLB_OP_ADD_MIN) ? m->acc_inf : m->acc;
+    if (op == GLB_OP_ADD_MIN && val_type != GLB_VAL_F32) {  // the integer infinity is all ones: a third accumulator, on first use
+        if (!m->acc_max) {
+            GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->acc_max), sizeof(float) * (m->num_rows ? m->num_rows : 1)));
+            GLB_CUDA(cudaMemsetAsync(m->acc_max, 0xff, sizeof(float) * m->num_rows, ctx->stream));
+        }
+        P.acc = m->acc_max;
+    }
     P.bitmap = m->bitmap;
     P.queue = m->queue;
     P.queue_cap = m->queue_cap;
@@ -569,13 +593,31 @@ int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_ty
         P.dense_src = next->dense_src;
         P.dense_len = next->dense_len;
     }
-    switch (op) {
-        case GLB_OP_MUL_ADD: return run_spmspv<GLB_OP_MUL_ADD>(ctx, m, P);
-        case GLB_OP_LOGICAL_AND_OR: return run_spmspv<GLB_OP_LOGICAL_AND_OR>(ctx, m, P);
-        case GLB_OP_ADD_MIN: return run_spmspv<GLB_OP_ADD_MIN>(ctx, m, P);
+    switch (op * 3 + val_type) {
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_F32: return run_spmspv<GLB_OP_MUL_ADD, GLB_VAL_F32>(ctx, m, P);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_F32: return run_spmspv<GLB_OP_LOGICAL_AND_OR, GLB_VAL_F32>(ctx, m, P);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_F32: return run_spmspv<GLB_OP_ADD_MIN, GLB_VAL_F32>(ctx, m, P);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_U32: return run_spmspv<GLB_OP_MUL_ADD, GLB_VAL_U32>(ctx, m, P);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_U32: return run_spmspv<GLB_OP_LOGICAL_AND_OR, GLB_VAL_U32>(ctx, m, P);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_U32: return run_spmspv<GLB_OP_ADD_MIN, GLB_VAL_U32>(ctx, m, P);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_UFIXED: return run_spmspv<GLB_OP_MUL_ADD, GLB_VAL_UFIXED>(ctx, m, P);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_UFIXED: return run_spmspv<GLB_OP_LOGICAL_AND_OR, GLB_VAL_UFIXED>(ctx, m, P);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_UFIXED: return run_spmspv<GLB_OP_ADD_MIN, GLB_VAL_UFIXED>(ctx, m, P);
     }
     glb_set_error("glb_spmspv: invalid semiring op %d", op);
     return GLB_EINVAL;
+}
+
+int glb_spmspv_fused(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,
+                     glb_idx_val_t *y, const glb_spmspv_epilogue_t *ep, const glb_spmspv_next_t *next) {
+    return spmspv_any(ctx, m, GLB_VAL_F32, op, zero, mask_type, x, mask, y, ep, next);
+}
+
+int glb_spmspv_vt(glb_ctx_t ctx, glb_csc_t m, int val_type, int op, uint32_t zero_bits, int mask_type, const glb_idx_val_t *x,
+                  const void *mask, glb_idx_val_t *y) {
+    float zero;
+    memcpy(&zero, &zero_bits, sizeof(zero));
+    return spmspv_any(ctx, m, val_type, op, zero, mask_type, x, static_cast<const float *>(mask), y, nullptr, nullptr);
 }
 
 int glb_spmspv(glb_ctx_t ctx, glb_csc_t m, int op, float zero, int mask_type, const glb_idx_val_t *x, const float *mask,

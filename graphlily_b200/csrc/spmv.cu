@@ -132,15 +132,15 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
 
 // Row write-back: fold `zero`, apply the mask (literal 0 compare / literal 0 write,
 // spmv_module.h:513-532), then the optional fused eWiseAdd and dense assign.
-template <int OP, bool IN_MAIN = true>
+template <int OP, bool IN_MAIN = true, int VT = GLB_VAL_F32>
 __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, float total) {
-    float v = Semi<OP>::with_zero(P.zero, total);
+    float v = Semi<OP, VT>::with_zero(P.zero, total);
     if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
-        if (ld_stream_f32(P.mask + row) != 0.0f) v = 0.0f;
+        if (!Val<VT>::is_zero(ld_stream_f32(P.mask + row))) v = Val<VT>::zero();
     } else if (P.mask_type == GLB_MASK_WRITE_TO_ONE) {
-        if (ld_stream_f32(P.mask + row) == 0.0f) v = 0.0f;
+        if (Val<VT>::is_zero(ld_stream_f32(P.mask + row))) v = Val<VT>::zero();
     }
-    if (P.add_enable) v = __fadd_rn(v, P.add_val);
+    if (P.add_enable) v = Val<VT>::plus(v, P.add_val);
     P.y[row] = v;
     // fused exchange: the row also goes straight into every peer's copy over NVLink, so the
     // allgather of the next iteration's x rides inside the SpMV write-back
@@ -152,7 +152,7 @@ __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, fl
             if (p < P.n_peers) P.y_peer[p][row] = v;
     }
     if (P.assign_inout) {
-        bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? (v != 0.0f) : (v == 0.0f);
+        bool hit = (P.assign_mask_type == GLB_MASK_WRITE_TO_ONE) ? !Val<VT>::is_zero(v) : Val<VT>::is_zero(v);
         if (hit) P.assign_inout[row] = P.assign_val;
     }
 }
@@ -199,7 +199,7 @@ __device__ __forceinline__ uint32_t gather_bit(const uint32_t *xbits, uint32_t c
 // BITS (or-and only): 0 = fp32 x gathers, 1 = bitmap gathers + value stream (a != 0 is tested),
 // 2 = bitmap gathers, pattern only (the formatter saw no stored zero: the value stream is not read).
 // MASKED: the launch has a mask (compile-time so that unmasked launches carry none of the skip logic).
-template <int OP, bool TILE, int BITS = 0, bool MASKED = true>
+template <int OP, bool TILE, int BITS = 0, bool MASKED = true, int VT = GLB_VAL_F32>
 __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
                                               float *const stage, const uint32_t tile_base) {
     const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
@@ -240,14 +240,14 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
             const uint32_t ord = ord_base + j;
             if (ord >= P.n_nz_rows) continue;  // the padding pseudo-row of the last chunk
             const float mv = ld_stream_f32(P.mask + ld_stream_u32(P.nz_rows + ord));
-            lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? (mv == 0.0f) : (mv != 0.0f);
+            lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? Val<VT>::is_zero(mv) : !Val<VT>::is_zero(mv);
         }
     }
     const bool chunk_live = !MASKED || __any_sync(kFull, lane_live);
 
     // the lane's run: serial reduction in registers; every flagged element closes the open row
     float *sp = stage + excl;
-    float acc = Semi<OP>::ident();
+    float acc = Semi<OP, VT>::ident();
 #pragma unroll
     for (int g = 0; g < GLB_MAX_GROUPS; ++g) {
         if (g < n) {
@@ -269,13 +269,13 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float prod = (BITS == 2) ? xv[e] : Semi<OP>::mul(__uint_as_float(a[e]), xv[e]);
-                if (MASKED && !lane_live) prod = Semi<OP>::ident();  // every row of this lane is masked out
+                float prod = (BITS == 2) ? xv[e] : Semi<OP, VT>::mul(__uint_as_float(a[e]), xv[e]);
+                if (MASKED && !lane_live) prod = Semi<OP, VT>::ident();  // every row of this lane is masked out
                 if (fw & (1u << (4 * g + e))) {
                     *sp++ = acc;
-                    acc = Semi<OP>::ident();
+                    acc = Semi<OP, VT>::ident();
                 }
-                acc = Semi<OP>::add(acc, prod);
+                acc = Semi<OP, VT>::add(acc, prod);
             }
         }
     }
@@ -291,11 +291,11 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const float tv = __shfl_up_sync(kFull, v, d);
-        if (int(lane) - d >= start) v = Semi<OP>::add(tv, v);
+        if (int(lane) - d >= start) v = Semi<OP, VT>::add(tv, v);
     }
     float carry_in = __shfl_up_sync(kFull, v, 1);
-    if (lane == 0) carry_in = Semi<OP>::ident();
-    if (hasf) stage[excl] = Semi<OP>::add(carry_in, stage[excl]);  // the lane's first row end began in lower lanes
+    if (lane == 0) carry_in = Semi<OP, VT>::ident();
+    if (hasf) stage[excl] = Semi<OP, VT>::add(carry_in, stage[excl]);  // the lane's first row end began in lower lanes
     if (lane == 31) P.tail_carry[chunk] = v;
     __syncwarp();
 
@@ -307,7 +307,7 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
         if (k == 0 && !fresh) {
             P.head_carry[chunk] = val;  // row began in an earlier chunk
         } else {
-            finish_row<OP>(P, ld_stream_u32(P.nz_rows + ord0 + k), val);
+            finish_row<OP, true, VT>(P, ld_stream_u32(P.nz_rows + ord0 + k), val);
         }
     }
 }
@@ -355,13 +355,13 @@ __device__ __forceinline__ void push_block_when_complete(const SpmvParams &P) {
 }
 
 // Variant L1: one chunk per warp, hot x lines kept in L1 by the cache hints.
-template <int OP, bool MASKED>
+template <int OP, bool MASKED, int VT = GLB_VAL_F32>
 __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kernel(const SpmvParams P) {
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk < P.n_chunks) process_chunk<OP, false, 0, MASKED>(P, chunk, lane, stage_all[wib], 0u);  // warp-uniform
+    if (chunk < P.n_chunks) process_chunk<OP, false, 0, MASKED, VT>(P, chunk, lane, stage_all[wib], 0u);  // warp-uniform
     if (P.push_bits) push_block_when_complete(P);
 }
 
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) gather_hot_kernel(const float *x, co
 // run over a multicast exchange these rows (and the empty ones) go to every rank from here, and the
 // CTA that finishes last publishes the epoch of the step (the main kernel's pushes completed with
 // that kernel, before this one started).
-template <int OP>
+template <int OP, int VT = GLB_VAL_F32>
 __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P, uint32_t nb_short, uint32_t nb_long) {
     const unsigned lane = threadIdx.x & 31u;
     if (blockIdx.x < nb_short) {
@@ -486,10 +486,10 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
             const uint32_t c_end = e.c_end & ~GLB_FLAG;
             const bool has_head = (e.c_end & GLB_FLAG) != 0;
             const uint32_t c_stop = has_head ? c_end : c_end + 1;  // exclusive end of the tail range
-            float t = Semi<OP>::ident();
-            for (uint32_t c = e.c_begin; c < c_stop; ++c) t = Semi<OP>::add(t, P.tail_carry[c]);
-            if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
-            finish_row<OP, false>(P, e.row, t);
+            float t = Semi<OP, VT>::ident();
+            for (uint32_t c = e.c_begin; c < c_stop; ++c) t = Semi<OP, VT>::add(t, P.tail_carry[c]);
+            if (has_head) t = Semi<OP, VT>::add(t, P.head_carry[c_end]);
+            finish_row<OP, false, VT>(P, e.row, t);
         }
     } else if (blockIdx.x < nb_short + nb_long) {
         const uint32_t i = (blockIdx.x - nb_short) * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -498,18 +498,18 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
             const uint32_t c_end = e.c_end & ~GLB_FLAG;
             const bool has_head = (e.c_end & GLB_FLAG) != 0;
             const uint32_t c_stop = has_head ? c_end : c_end + 1;
-            float t = Semi<OP>::ident();
-            for (uint32_t c = e.c_begin + lane; c < c_stop; c += 32) t = Semi<OP>::add(t, P.tail_carry[c]);
+            float t = Semi<OP, VT>::ident();
+            for (uint32_t c = e.c_begin + lane; c < c_stop; c += 32) t = Semi<OP, VT>::add(t, P.tail_carry[c]);
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) t = Semi<OP>::add(t, __shfl_xor_sync(kFull, t, d));
+            for (int d = 16; d >= 1; d >>= 1) t = Semi<OP, VT>::add(t, __shfl_xor_sync(kFull, t, d));
             if (lane == 0) {
-                if (has_head) t = Semi<OP>::add(t, P.head_carry[c_end]);
-                finish_row<OP, false>(P, e.row, t);
+                if (has_head) t = Semi<OP, VT>::add(t, P.head_carry[c_end]);
+                finish_row<OP, false, VT>(P, e.row, t);
             }
         }
     } else {
         const uint32_t i = (blockIdx.x - nb_short - nb_long) * kThreads + threadIdx.x;
-        if (i < P.n_empty) finish_row<OP, false>(P, P.empty_rows[i], Semi<OP>::ident());
+        if (i < P.n_empty) finish_row<OP, false, VT>(P, P.empty_rows[i], Semi<OP, VT>::ident());
     }
     if (P.pub_flags_mc) {  // uniform
         __threadfence_system();
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
     }
 }
 
-template <int OP>
+template <int OP, int VT = GLB_VAL_F32>
 int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
     P.n_ctas = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -532,7 +532,7 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
         GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
     }
-    if (P.n_chunks && m->tile_threads) {
+    if (VT == GLB_VAL_F32 && P.n_chunks && m->tile_threads) {
         const uint32_t n_warps = m->tile_threads / 32;
         const size_t smem = size_t((P.tile_k + 3u) & ~3u) * 4 + size_t(n_warps) * GLB_ROW_CAP * 4 + 16;
         size_t *attr_set = ctx->tile_smem_set;  // function attributes are per device: cached in the context
@@ -543,7 +543,7 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
         uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
         if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
         spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
-    } else if (P.n_chunks && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
+    } else if (VT == GLB_VAL_F32 && P.n_chunks && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
         int &bits_carveout_set = ctx->bits_carveout_set;
         if (bits_carveout_set != m->smem_carveout_pct) {
@@ -561,24 +561,24 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
         else spmv_lane_bits_kernel<1, false><<<grid, kThreads, 0, ctx->stream>>>(P);
     } else if (P.n_chunks) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
-        int *carveout_set = ctx->carveout_set;
+        int *carveout_set = ctx->carveout_set + 3 * VT;
         if (carveout_set[OP] != m->smem_carveout_pct) {
-            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, false, VT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           m->smem_carveout_pct));
-            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            GLB_CUDA(cudaFuncSetAttribute(spmv_lane_kernel<OP, true, VT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           m->smem_carveout_pct));
             carveout_set[OP] = m->smem_carveout_pct;
         }
         const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (P.mask_type != GLB_MASK_NONE) spmv_lane_kernel<OP, true><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else spmv_lane_kernel<OP, false><<<grid, kThreads, 0, ctx->stream>>>(P);
+        if (P.mask_type != GLB_MASK_NONE) spmv_lane_kernel<OP, true, VT><<<grid, kThreads, 0, ctx->stream>>>(P);
+        else spmv_lane_kernel<OP, false, VT><<<grid, kThreads, 0, ctx->stream>>>(P);
     }
     if (ctx->timing) GLB_CUDA(cudaEventRecord(ev[1], ctx->stream));
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
     const uint32_t nb_long = (P.n_fix_long + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const uint32_t nb_empty = (P.n_empty + kThreads - 1) / kThreads;
     if (nb_short + nb_long + nb_empty) {
-        spmv_fixup_kernel<OP><<<nb_short + nb_long + nb_empty, kThreads, 0, ctx->stream>>>(P, nb_short, nb_long);
+        spmv_fixup_kernel<OP, VT><<<nb_short + nb_long + nb_empty, kThreads, 0, ctx->stream>>>(P, nb_short, nb_long);
         if (published) *published = P.pub_flags_mc != nullptr;
     }
     if (ctx->timing) {
@@ -608,7 +608,7 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
-                    const GlbXchgWait *wait, bool *published) {
+                    const GlbXchgWait *wait, bool *published, int val_type) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
     if (published) *published = false;
@@ -628,7 +628,7 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     GlbXchgWait w;
     memset(&w, 0, sizeof(w));
     if (wait) w = *wait;
-    const bool head_is_pack = op == GLB_OP_LOGICAL_AND_OR && m->xbits && m->n_chunks && !m->tile_threads;
+    const bool head_is_pack = val_type == GLB_VAL_F32 && op == GLB_OP_LOGICAL_AND_OR && m->xbits && m->n_chunks && !m->tile_threads;
     const bool head_is_gather = !head_is_pack && m->n_hot && m->n_chunks;
     if (wait && !head_is_pack && !head_is_gather) {  // no kernel of this launch opens with the acquire: its own launch
         int rc = glb_xchg_wait_launch(ctx, w);
@@ -643,7 +643,7 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.chunk_first = m->chunk_first;
     P.nz_rows = m->nz_rows;
     P.tile_k = m->tile_k;
-    if (op == GLB_OP_LOGICAL_AND_OR && m->xbits && m->n_chunks && !m->tile_threads) {
+    if (head_is_pack) {
         // or-and: one bit per stored column word replaces the fp32 gathers
         const uint32_t n_words32 = (m->tile_k + m->num_cols + 31u) / 32u;
         const uint32_t threads = n_words32 * 32u;
@@ -680,10 +680,16 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
     P.n_nz_rows = m->n_nz_rows;
-    switch (op) {
-        case GLB_OP_MUL_ADD: return launch_op<GLB_OP_MUL_ADD>(ctx, m, P, published);
-        case GLB_OP_LOGICAL_AND_OR: return launch_op<GLB_OP_LOGICAL_AND_OR>(ctx, m, P, published);
-        case GLB_OP_ADD_MIN: return launch_op<GLB_OP_ADD_MIN>(ctx, m, P, published);
+    switch (op * 3 + val_type) {
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_F32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_F32>(ctx, m, P, published);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_F32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_F32>(ctx, m, P, published);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_F32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_F32>(ctx, m, P, published);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_U32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_U32>(ctx, m, P, published);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_U32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_U32>(ctx, m, P, published);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_U32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_U32>(ctx, m, P, published);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_UFIXED>(ctx, m, P, published);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_UFIXED>(ctx, m, P, published);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_UFIXED>(ctx, m, P, published);
     }
     glb_set_error("glb_spmv: invalid semiring op %d", op);
     return GLB_EINVAL;
@@ -1076,7 +1082,19 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr, nullptr);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr, nullptr, GLB_VAL_F32);
+}
+
+int glb_spmv_vt(glb_ctx_t ctx, glb_csr_t m, int val_type, int op, uint32_t zero_bits, int mask_type, const void *x, const void *mask,
+                void *y, const glb_spmv_epilogue_t *ep) {
+    GLB_REQUIRE(val_type >= GLB_VAL_F32 && val_type <= GLB_VAL_UFIXED, "invalid value type");
+    float zero;
+    memcpy(&zero, &zero_bits, sizeof(zero));
+    int rc = check_spmv_args(ctx, m, op, mask_type, static_cast<const float *>(x), static_cast<const float *>(mask),
+                             static_cast<float *>(y), ep);
+    if (rc) return rc;
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, static_cast<const float *>(x), static_cast<const float *>(mask),
+                           static_cast<float *>(y), ep, nullptr, 0, nullptr, nullptr, nullptr, val_type);
 }
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
@@ -1121,7 +1139,7 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         if (xc->mc && xc->nranks > 1 && forced == 1) {
             // default: one push kernel after the SpMV kernels (all SMs store the finished slice in 16-byte
             // multimem.st; its last CTA publishes)
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr, GLB_VAL_F32);
             if (!rc) rc = glb_xchg_push(ctx, xc, dv, m->row_begin, size_t(m->row_end - m->row_begin));
         } else if (xc->mc && xc->nranks > 1) {
             // GLB_XCHG_MC=progressive: completed blocks of rows are pushed from inside the main kernel while
@@ -1137,13 +1155,13 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
             mc.pub_state = xc->d_state;
             mc.rank = xc->rank;
             bool published = false;
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, &published);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, &published, GLB_VAL_F32);
             if (!rc && !published) rc = glb_xchg_signal(ctx, xc, false);
         } else {
             int n_peers = 0;
             for (int r = 0; r < xc->nranks; ++r)
                 if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w, nullptr);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w, nullptr, GLB_VAL_F32);
             if (!rc) rc = glb_xchg_signal(ctx, xc, false);
         }
         if (rc) return rc;

@@ -56,6 +56,12 @@ extern "C" {
 #define GLB_OP_ADD_MIN 2
 
 /* MaskType, global.h:103-107 */
+/* Value types (global.h:60-64 of the reference offers three; all are 32-bit words).  Every entry point
+ * without a _vt suffix computes in GLB_VAL_F32, the type of the reference's CPU path and the parity target. */
+#define GLB_VAL_F32 0     /* float */
+#define GLB_VAL_U32 1     /* unsigned, arithmetic modulo 2^32, UINT_INF = 0xffffffff */
+#define GLB_VAL_UFIXED 2  /* ap_ufixed<32, 8, AP_RND, AP_SAT>: Q8.24, rounded products, saturating sums */
+
 #define GLB_MASK_NONE 0
 #define GLB_MASK_WRITE_TO_ZERO 1 /* write where mask is zero     */
 #define GLB_MASK_WRITE_TO_ONE 2  /* write where mask is non-zero */
@@ -301,6 +307,28 @@ int glb_assign_sparse(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout, fl
  * reference's; order is unspecified. new_frontier must not alias list. */
 int glb_assign_sparse_relax(glb_ctx_t ctx, const glb_idx_val_t *list, float *inout,
                             glb_idx_val_t *new_frontier);
+
+/* ------------------------------------------------------------------ value-type variants
+ * The same operators on the other two `val_t` choices of the reference (global.h:60-64): GLB_VAL_U32 and
+ * GLB_VAL_UFIXED (the Q8.24 of the shipped bitstream), with the arithmetic of its processing elements
+ * (ufixed_pe_fwd.h:23-65; semiring.cuh).  Vectors, masks and matrix values are 32-bit WORDS of that type
+ * (glb_csr_create / glb_csc_create take them through their `data` pointer unchanged); scalars travel as
+ * words: zero_bits, val_bits, and the add_val / assign_val members of the epilogue hold the word's bits.
+ * Mask tests compare against the word 0 (SpMV, dense assign) or against `zero` (SpMSpV), as in the fp32
+ * entry points.  Exact integer arithmetic: results do not depend on the reduction order.
+ * The reference ships no artefact that pins its device numerics (no bitstream, no emulator), so parity of
+ * these variants is against a software model of the documented ap_ufixed semantics (oracle/valtype_model.h),
+ * not against reference output: "parity unpinned". */
+int glb_spmv_vt(glb_ctx_t ctx, glb_csr_t m, int val_type, int op, uint32_t zero_bits, int mask_type, const void *x,
+                const void *mask, void *y, const glb_spmv_epilogue_t *ep);
+int glb_spmspv_vt(glb_ctx_t ctx, glb_csc_t m, int val_type, int op, uint32_t zero_bits, int mask_type,
+                  const glb_idx_val_t *x, const void *mask, glb_idx_val_t *y);
+int glb_ewise_add_vt(glb_ctx_t ctx, int val_type, const void *in, void *out, uint32_t len, uint32_t val_bits);
+int glb_assign_dense_vt(glb_ctx_t ctx, int val_type, const void *mask, void *inout, uint32_t len, uint32_t val_bits,
+                        int mask_type);
+int glb_assign_sparse_vt(glb_ctx_t ctx, int val_type, const glb_idx_val_t *list, void *inout, uint32_t val_bits);
+int glb_assign_sparse_relax_vt(glb_ctx_t ctx, int val_type, const glb_idx_val_t *list, void *inout,
+                               glb_idx_val_t *new_frontier);
 
 /* ------------------------------------------------------------------ multi-GPU ------
  * Row-range sharding: one process per GPU, each holding glb_csr_create(..., row_begin, row_end)

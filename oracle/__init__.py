@@ -23,6 +23,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_PATH = os.path.join(_HERE, "liboracle.so")
 REF_PATH = os.path.join(_HERE, "_ref", "libgraphlily_ref.so")
+REF_UFIXED_PATH = os.path.join(_HERE, "_ref", "libgraphlily_ref_ufixed.so")
+VALMODEL_PATH = os.path.join(_HERE, "libvaltype_model.so")
 
 OP_MUL_ADD, OP_LOGICAL_AND_OR, OP_ADD_MIN = 0, 1, 2
 MASK_NONE, MASK_WRITE_TO_ZERO, MASK_WRITE_TO_ONE = 0, 1, 2
@@ -239,14 +241,77 @@ def _load_port():
     return _Backend(PORT_PATH, "oracle_", False)
 
 
-def _load_ref():
-    if not os.path.exists(REF_PATH):
+def _load_ref(path=REF_PATH):
+    if not os.path.exists(path):
         return None
     try:
-        return _Ref(REF_PATH)
+        return _Ref(path)
     except OSError:
         return None
 
 
+class _ValModel:
+    """Sequential model of the unsigned / Q8.24 value-type variants (oracle/valtype_model.cpp); words are uint32."""
+    U32, UFIXED = 1, 2
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.lib.vt_ufixed_from_double.restype = C.c_uint32
+        self.lib.vt_ufixed_from_double.argtypes = [C.c_double]
+        self.lib.vt_ufixed_to_double.restype = C.c_double
+        self.lib.vt_ufixed_to_double.argtypes = [C.c_uint32]
+        for n in ("vt_ufixed_mul", "vt_ufixed_add"):
+            getattr(self.lib, n).restype = C.c_uint32
+            getattr(self.lib, n).argtypes = [C.c_uint32, C.c_uint32]
+
+    def spmv(self, vt, m, op, zero, mask_type, x, mask=None):
+        ip, ix, d = _u32(m.indptr), _u32(m.indices), _u32(m.data)
+        x = _u32(x)
+        mask = None if mask is None else _u32(mask)
+        y = np.empty(int(m.num_rows), np.uint32)
+        rc = self.lib.vt_spmv(C.c_int(vt), C.c_uint32(int(m.num_rows)), C.c_uint32(int(m.num_cols)), _pu(ip), _pu(ix), _pu(d),
+                              C.c_int(op), C.c_uint32(int(zero)), C.c_int(mask_type), _pu(x), None if mask is None else _pu(mask), _pu(y))
+        assert rc == 0
+        return y
+
+    def spmspv(self, vt, m, op, zero, mask_type, x_idx, x_val, mask=None):
+        ip, ix, d = _u32(m.indptr), _u32(m.indices), _u32(m.data)
+        x_idx, x_val = _u32(x_idx), _u32(x_val)
+        mask = None if mask is None else _u32(mask)
+        y = np.empty(int(m.num_rows), np.uint32)
+        rc = self.lib.vt_spmspv(C.c_int(vt), C.c_uint32(int(m.num_rows)), C.c_uint32(int(m.num_cols)), _pu(ip), _pu(ix), _pu(d),
+                                C.c_int(op), C.c_uint32(int(zero)), C.c_int(mask_type), _pu(x_idx), _pu(x_val),
+                                C.c_uint32(len(x_idx)), None if mask is None else _pu(mask), _pu(y))
+        assert rc == 0
+        return y
+
+    def ewise_add(self, vt, vec, val):
+        vec = _u32(vec)
+        out = np.empty_like(vec)
+        self.lib.vt_ewise_add(C.c_int(vt), _pu(vec), _pu(out), C.c_uint32(len(vec)), C.c_uint32(int(val)))
+        return out
+
+    def assign_sparse_relax(self, vt, m_idx, m_val, inout):
+        m_idx, m_val, out = _u32(m_idx), _u32(m_val), _u32(inout).copy()
+        n = len(m_idx)
+        nf_i, nf_v = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.uint32)
+        cnt = self.lib.vt_assign_sparse_relax(C.c_int(vt), _pu(m_idx), _pu(m_val), C.c_uint32(n), _pu(out), _pu(nf_i), _pu(nf_v))
+        return out, nf_i[:cnt].copy(), nf_v[:cnt].copy()
+
+    def to_ufixed(self, x):
+        return np.array([self.lib.vt_ufixed_from_double(float(v)) for v in np.atleast_1d(x)], np.uint32)
+
+    def from_ufixed(self, w):
+        return np.array([self.lib.vt_ufixed_to_double(int(v)) for v in np.atleast_1d(w)], np.float64)
+
+
+def _load_valmodel():
+    if not os.path.exists(VALMODEL_PATH):
+        build()
+    return _ValModel(VALMODEL_PATH)
+
+
 port = _load_port()
-ref = _load_ref()
+ref = _load_ref()                      # the reference compiled with val_t = float: the fp32 parity target
+ref_ufixed = _load_ref(REF_UFIXED_PATH)   # ... with val_t = the software ap_ufixed<32, 8, AP_RND, AP_SAT>
+valmodel = _load_valmodel()
