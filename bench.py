@@ -381,9 +381,15 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
+    secondary = None
+    try:   # the unit that actually limits the kernel (committed ncu capture)
+        secondary = json.load(open(os.path.join(ROOT, "profiles", "spmv_l1_port.json")))
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": "spmv_lane_kernel<plus-times>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if world == 1 else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fixup}
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "fixup_kernel_ms": ms_fixup,
+                "secondary": secondary if world == 1 else None}
     ms_kernels_max = max_over_ranks(ms_kernel + ms_fixup)
     step_breakdown = {"main_plus_fixup_ms_max_over_ranks": ms_kernels_max,
                       "other_ms": ms_step - ms_kernels_max,
