@@ -30,6 +30,7 @@ int main(int argc, char *argv[]) {
     spmv.run();
     auto kernel_results = spmv.send_results_device_to_host();
 
+    // bench_spmv.cpp:96-112: 100 runs; run() returns when the kernel has (as the reference's does)
     const uint32_t num_runs = 100;
     auto t1 = std::chrono::high_resolution_clock::now();
     for (size_t i = 0; i < num_runs; i++) spmv.run();
@@ -37,5 +38,13 @@ int main(int argc, char *argv[]) {
     const double average_time_in_sec = seconds_since(t1) / num_runs;
     std::cout << "average_time: " << average_time_in_sec * 1000 << " ms" << std::endl;
     std::cout << "Compute THROUGHPUT = " << double(spmv.get_nnz()) / 1e9 / average_time_in_sec << " GTEPS" << std::endl;
+    // the same 100 launches enqueued back to back, one synchronisation at the end
+    spmv.set_async_run(true);
+    auto t2 = std::chrono::high_resolution_clock::now();
+    for (size_t i = 0; i < num_runs; i++) spmv.run();
+    spmv.get_runtime()->finish();
+    const double async_time_in_sec = seconds_since(t2) / num_runs;
+    std::cout << "back-to-back average_time: " << async_time_in_sec * 1000 << " ms, "
+              << double(spmv.get_nnz()) / 1e9 / async_time_in_sec << " GTEPS" << std::endl;
     return 0;
 }

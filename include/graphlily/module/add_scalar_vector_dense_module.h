@@ -36,7 +36,10 @@ public:
     void bind_in_buf(DeviceBuffer src_buf) { in_buf = src_buf; }
     void bind_out_buf(DeviceBuffer src_buf) { out_buf = src_buf; }
 
-    void run(uint32_t len, vector_data_t val) { GLB_CHECK(glb_ewise_add(ctx(), in_buf.f32(), out_buf.f32(), len, val)); }
+    void run(uint32_t len, vector_data_t val) {
+        GLB_CHECK(glb_ewise_add(ctx(), in_buf.f32(), out_buf.f32(), len, val));
+        end_run();
+    }
 
     aligned_dense_vec_t send_out_device_to_host() {
         download(out_, out_buf, out_buf.bytes() / sizeof(vector_data_t));

@@ -46,6 +46,7 @@ public:
 
     void run(uint32_t len, vector_data_t val) {
         GLB_CHECK(glb_assign_dense(ctx(), mask_buf.f32(), inout_buf.f32(), len, val, mask_type_));
+        end_run();
     }
 
     aligned_dense_vec_t send_mask_device_to_host() {

@@ -66,11 +66,13 @@ public:
     void run(vector_data_t val) {
         require_new_frontier(false);
         GLB_CHECK(glb_assign_sparse(ctx(), mask_buf.sparse(), inout_buf.f32(), val));
+        end_run();
     }
     // SSSP mode: relax and emit the new frontier
     void run() {
         require_new_frontier(true);
         GLB_CHECK(glb_assign_sparse_relax(ctx(), mask_buf.sparse(), inout_buf.f32(), new_frontier_buf.sparse()));
+        end_run();
     }
 
     aligned_sparse_vec_t send_mask_device_to_host() {

@@ -23,6 +23,14 @@ protected:
     std::string kernel_name_;
     std::string target_ = "hw";
     std::shared_ptr<Runtime> runtime_;
+    // The reference's run() is setArg + enqueueTask + finish (spmv_module.h:471-475): callers -- its
+    // benchmark drivers time `for (...) run();` with no synchronisation of their own -- rely on run()
+    // returning after the kernel has.  run() keeps that; set_async_run(true) makes it return after
+    // enqueueing (the apps' own loops do not go through run(): they record launch sequences).
+    bool async_run_ = false;
+    void end_run() {
+        if (!async_run_) runtime_->finish();
+    }
 
     glb_ctx_t ctx() const {
         if (!runtime_) {
@@ -63,6 +71,7 @@ public:
     // Share an existing runtime (what ModuleCollection does with its context and queues).
     void set_runtime(std::shared_ptr<Runtime> runtime) { runtime_ = runtime; }
     std::shared_ptr<Runtime> get_runtime() { return runtime_; }
+    void set_async_run(bool on) { async_run_ = on; }
 
     void set_target(std::string target) {
         assert(target == "sw_emu" || target == "hw_emu" || target == "hw");

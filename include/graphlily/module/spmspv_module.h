@@ -88,6 +88,7 @@ public:
     void run() {
         GLB_CHECK(glb_spmspv(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.sparse(),
                              mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.sparse()));
+        end_run();
     }
 
     aligned_sparse_vec_t send_vector_device_to_host() {

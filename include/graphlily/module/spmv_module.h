@@ -4,8 +4,9 @@
 // arguments, set_semiring / set_mask_type, load_and_format_matrix, send_*_host_to_device,
 // bind_mask_buf, run, send_*_device_to_host, public vector_buf / mask_buf / results_buf).  The CPSR
 // formatting + 16-channel upload (:282-420) becomes glb_csr_create (lane-segment layout); run()
-// (:471-475: setArg + enqueueTask + finish) becomes glb_spmv on the runtime's stream -- it returns
-// without synchronising, every send_*_device_to_host synchronises.
+// (:471-475: setArg + enqueueTask + finish) becomes glb_spmv on the runtime's stream followed by a
+// stream synchronisation, as in the reference (set_async_run(true) drops it); run_fused, which the apps'
+// loops use, only enqueues.
 // compute_reference_results (:478-532) is declared but not defined by the product: the CPU restatement
 // lives in oracle/ and is linked by the tests only (tests/cpp/ref_compat/reference_results.h).
 #ifndef GRAPHLILY_SPMV_MODULE_H_
@@ -105,7 +106,10 @@ public:
         mask_buf = constant_on_device(mask_buf, get_num_rows(), value, true, index, index_value);
     }
 
-    void run() { run_fused(nullptr); }
+    void run() {
+        run_fused(nullptr);
+        end_run();
+    }
 
     // One launch for SpMV + the eWiseAdd / dense assign the apps run right after it (glb_spmv_fused).
     void run_fused(const glb_spmv_epilogue_t *epilogue) {
