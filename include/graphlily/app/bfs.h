@@ -43,6 +43,7 @@ private:
     graphlily::SemiringType semiring_ = graphlily::LogicalSemiring;
     bool fused_ = true;
     uint32_t push_iterations_ = 0;
+    bool push_iterations_device_ = false;
 
     using aligned_dense_vec_t = graphlily::aligned_dense_vec_t;
     using aligned_sparse_vec_t = graphlily::aligned_sparse_vec_t;
@@ -74,12 +75,61 @@ private:
     }
 
     void push_setup(uint32_t source) {
-        aligned_sparse_vec_t spmspv_input(2);
-        spmspv_input[0] = {1, 0};  // one source vertex
-        spmspv_input[1] = {source, 1};
-        SpMSpV_->send_vector_host_to_device(spmspv_input);
+        SpMSpV_->home_lists();
+        SpMSpV_->set_vector_single(source, 1);     // one source vertex (bfs.h:131-135), built on the device
         SpMSpV_->set_mask_constant(0, source, 1);  // distance: 0 but distance[source] = 1, built on the device
         SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
+    }
+
+    // One push level in ONE launch: SpMSpV lists[(level - 1) & 1] -> lists[level & 1] with the sparse assign
+    // distance[row] = level + 1 (bfs.h:147-151) fused into the kernel.
+    void push_level_fused(const DeviceBuffer lists[2], uint32_t level, const glb_spmspv_next_t *next) {
+        glb_spmspv_epilogue_t ep = {GLB_SPMSPV_EP_ASSIGN, SpMSpV_->mask_buf.f32(), float(level + 1), nullptr};
+        SpMSpV_->run_fused(lists[(level - 1) & 1], lists[level & 1], &ep, next);
+    }
+
+    // The two dense vectors the pull levels ping-pong through, zero-filled: the push level that stops pushing
+    // scatters its frontier into one of them.
+    void dense_pair(DeviceBuffer dense[2]) {
+        const uint32_t n = matrix_num_rows_;
+        if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() != sizeof(graphlily::val_t) * size_t(n))
+            SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * size_t(n));
+        SpMV_->home_buffers();
+        dense[0] = SpMV_->vector_buf;
+        dense[1] = SpMV_->results_buf;
+        for (int i = 0; i < 2; i++) GLB_CHECK(glb_buffer_fill_f32(runtime_->ctx(), dense[i].f32(), semiring_.zero, n));
+    }
+
+    // pull_push as ONE recorded sequence with the direction decided on the device (bfs.h:186-190): every push
+    // level is one launch that also sets the IF / ELSE condition of the next level; no host synchronisation
+    // between the start vectors and the read-back of the result.
+    aligned_dense_vec_t pull_push_device(uint32_t source, uint32_t num_iterations, float threshold) {
+        const uint32_t n = matrix_num_rows_;
+        push_setup(source);
+        DeviceBuffer dist = SpMSpV_->mask_buf;
+        SpMV_->bind_mask_buf(dist);
+        DeviceBuffer dense[2], lists[2] = {SpMSpV_->vector_buf, SpMSpV_->results_buf};
+        dense_pair(dense);
+        SpMSpV_->reset_push_levels();
+        replay({4, key_of(SpMV_->device_matrix()), num_iterations, key_of(threshold), key_of(lists[0].ptr()), key_of(lists[1].ptr()),
+                key_of(dist.ptr()), key_of(dense[0].ptr()), key_of(dense[1].ptr())}, [&] {
+            std::vector<uint64_t> cond(num_iterations + 2, 0);
+            for (uint32_t level = 2; level <= num_iterations; level++) cond[level] = cond_create();
+            auto push_level = [&](uint32_t level) {
+                glb_spmspv_next_t next = {int(level + 1 >= num_iterations), threshold, n, cond[level + 1], GLB_SPMSPV_DENSE_SCATTER,
+                                          dense[(level + 1) & 1].f32(), nullptr, n};
+                push_level_fused(lists, level, level < num_iterations ? &next : nullptr);
+            };
+            auto pull_level = [&](uint32_t level) {
+                glb_spmv_epilogue_t ep = {0, 0.0f, dist.f32(), float(level + 1), GLB_MASK_WRITE_TO_ONE};
+                SpMV_->run_fused(dense[level & 1], dist, dense[(level + 1) & 1], &ep);
+            };
+            push_level(1);
+            for (uint32_t level = 2; level <= num_iterations; level++)
+                branch(cond[level], [&] { push_level(level); }, [&] { pull_level(level); });
+        });
+        push_iterations_device_ = true;
+        return SpMSpV_->send_mask_device_to_host();
     }
 
     void push_step(uint32_t iter) {
@@ -113,7 +163,8 @@ public:
     void set_fused(bool fused) { fused_ = fused; }
     uint32_t get_nnz() { return SpMV_->get_nnz(); }
     uint32_t get_num_rows() { return matrix_num_rows_; }
-    uint32_t get_push_iterations() { return push_iterations_; }
+    // levels the last pull_push spent pushing; with the decision on the device it is read back on demand
+    uint32_t get_push_iterations() { return push_iterations_device_ ? SpMSpV_->push_levels() : push_iterations_; }
 
     void load_and_format_matrix(CSRMatrix<float> csr_matrix, bool skip_empty_rows) {
         graphlily::io::util_round_csr_matrix_dim(csr_matrix, num_channels_ * graphlily::pack_size,
@@ -147,11 +198,23 @@ public:
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
         push_setup(source);
-        for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);
+        if (!fused_) {
+            for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);
+            return SpMSpV_->send_mask_device_to_host();
+        }
+        DeviceBuffer lists[2] = {SpMSpV_->vector_buf, SpMSpV_->results_buf};
+        replay({3, key_of(SpMV_->device_matrix()), num_iterations, key_of(lists[0].ptr()), key_of(lists[1].ptr()),
+                key_of(SpMSpV_->mask_buf.ptr())}, [&] {
+            for (uint32_t level = 1; level <= num_iterations; level++) push_level_fused(lists, level, nullptr);
+        });
+        SpMSpV_->vector_buf = lists[num_iterations & 1];
+        SpMSpV_->results_buf = lists[(num_iterations + 1) & 1];
         return SpMSpV_->send_mask_device_to_host();
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
+        if (fused_ && use_graphs_ && num_iterations >= 2) return pull_push_device(source, num_iterations, threshold);
+        push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);
         uint32_t iter = 1;

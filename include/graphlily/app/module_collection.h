@@ -56,6 +56,19 @@ protected:
         for (auto &kv : graphs_) glb_graph_destroy(kv.second);
         graphs_.clear();
     }
+    // A branch of the recorded sequence decided on the device (glb_graph_cond_create / glb_graph_branch_*)
+    uint64_t cond_create() {
+        uint64_t c = 0;
+        GLB_CHECK(glb_graph_cond_create(runtime_->ctx(), &c));
+        return c;
+    }
+    void branch(uint64_t cond, const std::function<void()> &if_arm, const std::function<void()> &else_arm) {
+        GLB_CHECK(glb_graph_branch_begin(runtime_->ctx(), cond));
+        if_arm();
+        GLB_CHECK(glb_graph_branch_else(runtime_->ctx()));
+        else_arm();
+        GLB_CHECK(glb_graph_branch_end(runtime_->ctx()));
+    }
     static uint64_t key_of(const void *p) { return uint64_t(reinterpret_cast<uintptr_t>(p)); }
     static uint64_t key_of(float v) { uint32_t b; memcpy(&b, &v, sizeof(b)); return b; }
 

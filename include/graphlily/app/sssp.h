@@ -81,6 +81,8 @@ private:
     graphlily::SemiringType semiring_ = graphlily::TropicalSemiring;
     bool fused_ = true;
     uint32_t push_iterations_ = 0;
+    bool push_iterations_device_ = false;
+    DeviceBuffer frontier2_buf_;   // second frontier list of the fused push levels
     using aligned_dense_vec_t = graphlily::aligned_dense_vec_t;
     using aligned_sparse_vec_t = graphlily::aligned_sparse_vec_t;
 
@@ -107,14 +109,61 @@ private:
     }
 
     void push_setup(uint32_t source) {
-        aligned_sparse_vec_t spmspv_input(2);
-        spmspv_input[0] = {1, 0};
-        spmspv_input[1] = {source, 0};
-        SpMSpV_->send_vector_host_to_device(spmspv_input);
+        SpMSpV_->home_lists();
+        SpMSpV_->set_vector_single(source, 0);                  // the source frontier (sssp.h:169-171), built on the device
         SpMSpV_->set_mask_constant(semiring_.zero, source, 0);  // distance (sssp.h:172-176), built on the device
         SparseAssign_->bind_mask_buf(SpMSpV_->results_buf);
         SparseAssign_->bind_inout_buf(SpMSpV_->mask_buf);
         SparseAssign_->bind_new_frontier_buf(SpMSpV_->vector_buf);
+    }
+
+    // The two lists the frontier alternates between in the fused push levels (the kernel reads the old
+    // frontier while it appends the new one, so they cannot be one buffer as in sssp.h:185-187).
+    void frontier_lists(DeviceBuffer lists[2]) {
+        const size_t bytes = sizeof(graphlily::idx_val_t) * (size_t(matrix_num_cols_) + 1);
+        if (!frontier2_buf_.valid() || frontier2_buf_.bytes() != bytes) frontier2_buf_ = DeviceBuffer(runtime_, bytes);
+        lists[0] = SpMSpV_->vector_buf;
+        lists[1] = frontier2_buf_;
+    }
+    // One push level in ONE launch: SpMSpV lists[(level - 1) & 1] -> results, with the relax of the distance
+    // vector and the new frontier -> lists[level & 1] (sssp.h:178-190) fused into the kernel.
+    void push_level_fused(const DeviceBuffer lists[2], uint32_t level, const glb_spmspv_next_t *next) {
+        glb_spmspv_epilogue_t ep = {GLB_SPMSPV_EP_RELAX, SpMSpV_->mask_buf.f32(), 0.0f, lists[level & 1].sparse()};
+        SpMSpV_->run_fused(lists[(level - 1) & 1], SpMSpV_->results_buf, &ep, next);
+    }
+
+    // pull_push as ONE recorded sequence with the direction decided on the device (sssp.h:210-214); the level
+    // that stops pushing copies the distance vector into the input of the first pull level (sssp.h:219-222).
+    aligned_dense_vec_t pull_push_device(uint32_t source, uint32_t num_iterations, float threshold) {
+        const uint32_t n = matrix_num_rows_;
+        push_setup(source);
+        DeviceBuffer dist = SpMSpV_->mask_buf, lists[2], dense[2];
+        frontier_lists(lists);
+        if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() != sizeof(graphlily::val_t) * size_t(n))
+            SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * size_t(n));
+        SpMV_->home_buffers();
+        dense[0] = SpMV_->vector_buf;
+        dense[1] = SpMV_->results_buf;
+        SpMSpV_->reset_push_levels();
+        replay({5, key_of(SpMV_->device_matrix()), num_iterations, key_of(threshold), key_of(lists[0].ptr()), key_of(lists[1].ptr()),
+                key_of(SpMSpV_->results_buf.ptr()), key_of(dist.ptr()), key_of(dense[0].ptr()), key_of(dense[1].ptr())}, [&] {
+            std::vector<uint64_t> cond(num_iterations + 2, 0);
+            for (uint32_t level = 2; level <= num_iterations; level++) cond[level] = cond_create();
+            auto push_level = [&](uint32_t level) {
+                glb_spmspv_next_t next = {int(level + 1 >= num_iterations), threshold, n, cond[level + 1], GLB_SPMSPV_DENSE_COPY,
+                                          dense[(level + 1) & 1].f32(), dist.f32(), n};
+                push_level_fused(lists, level, level < num_iterations ? &next : nullptr);
+            };
+            push_level(1);
+            for (uint32_t level = 2; level <= num_iterations; level++)
+                branch(cond[level], [&] { push_level(level); },
+                       [&] { SpMV_->run_fused(dense[level & 1], DeviceBuffer(), dense[(level + 1) & 1], nullptr); });
+        });
+        push_iterations_device_ = true;
+        // the last level is always a pull level (sssp.h:214: iter < num_iterations): its output is the result
+        SpMV_->vector_buf = dense[(num_iterations + 1) & 1];
+        SpMV_->results_buf = dense[num_iterations & 1];
+        return SpMV_->send_vector_device_to_host();
     }
 
 public:
@@ -138,7 +187,7 @@ public:
     void set_fused(bool fused) { fused_ = fused; }
     uint32_t get_nnz() { return SpMV_->get_nnz(); }
     uint32_t get_num_rows() { return matrix_num_rows_; }
-    uint32_t get_push_iterations() { return push_iterations_; }
+    uint32_t get_push_iterations() { return push_iterations_device_ ? SpMSpV_->push_levels() : push_iterations_; }
 
     void load_and_format_matrix(graphlily::io::CSRMatrix<float> csr_matrix, bool skip_empty_rows) {
         detail::sssp_preprocess(csr_matrix);
@@ -169,14 +218,25 @@ public:
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
         push_setup(source);
-        for (uint32_t iter = 1; iter <= num_iterations; iter++) {
-            SpMSpV_->run();
-            SparseAssign_->run();
+        if (!fused_) {
+            for (uint32_t iter = 1; iter <= num_iterations; iter++) {
+                SpMSpV_->run();
+                SparseAssign_->run();
+            }
+            return SpMSpV_->send_mask_device_to_host();
         }
+        DeviceBuffer lists[2];
+        frontier_lists(lists);
+        replay({4, key_of(SpMV_->device_matrix()), num_iterations, key_of(lists[0].ptr()), key_of(lists[1].ptr()),
+                key_of(SpMSpV_->results_buf.ptr()), key_of(SpMSpV_->mask_buf.ptr())}, [&] {
+            for (uint32_t level = 1; level <= num_iterations; level++) push_level_fused(lists, level, nullptr);
+        });
         return SpMSpV_->send_mask_device_to_host();
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
+        if (fused_ && use_graphs_ && num_iterations >= 2) return pull_push_device(source, num_iterations, threshold);
+        push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);
         uint32_t iter = 1;

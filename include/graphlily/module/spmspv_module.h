@@ -91,6 +91,30 @@ public:
         end_run();
     }
 
+    // A whole push level in one launch over explicit list buffers: SpMSpV + the sparse assign / relax of the
+    // apps + (next != nullptr) the push-or-pull decision of pull_push taken on the device (glb_spmspv_fused).
+    void run_fused(const DeviceBuffer &vector, const DeviceBuffer &results, const glb_spmspv_epilogue_t *epilogue,
+                   const glb_spmspv_next_t *next) {
+        GLB_CHECK(glb_spmspv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector.sparse(),
+                                   mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results.sparse(), epilogue, next));
+    }
+    // the one-entry start frontier, written on the device (no blocking upload)
+    void set_vector_single(uint32_t index, vector_data_t val) {
+        GLB_CHECK(glb_sparse_fill_one(ctx(), vector_buf.sparse(), index, val));
+    }
+    void home_lists() {  // canonical roles of the two list buffers at the start of a run: recorded sequences are found again
+        if (vector_buf.valid() && results_buf.valid() && vector_buf.bytes() == results_buf.bytes() &&
+            vector_buf.ptr() > results_buf.ptr())
+            std::swap(vector_buf, results_buf);
+    }
+    uint32_t push_levels() {  // levels of the last pull_push run that carried the decision (blocking, on demand)
+        uint32_t keep = 0, levels = 0;
+        GLB_CHECK(glb_spmspv_push_state(ctx(), matrix_, &keep, &levels));
+        return levels;
+    }
+    void reset_push_levels() { GLB_CHECK(glb_spmspv_reset_levels(ctx(), matrix_)); }
+    glb_csc_t device_matrix() { return matrix_; }
+
     aligned_sparse_vec_t send_vector_device_to_host() {
         download(vector_, vector_buf, size_t(count_of(vector_buf)) + 1);
         return vector_;

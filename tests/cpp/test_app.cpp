@@ -34,6 +34,15 @@ TEST(BFS, AllModesFusedAndUnfused) {
         verify(ref, bfs.pull_push(0, 10, 0.1f), true);
         EXPECT_TRUE(bfs.get_push_iterations() >= 1 && bfs.get_push_iterations() < 10);
         verify(ref, bfs.pull(0, 10), true);  // modules are reusable after a pull_push
+        // the direction decided on the device (fused) / by the host (unfused): every threshold, other sources
+        // and iteration counts, the recorded sequence replayed
+        for (float thr : {0.001f, 0.1f, 1.1f}) verify(ref, bfs.pull_push(0, 10, thr), true);
+        EXPECT_EQ(bfs.get_push_iterations(), 9u);   // threshold 1.1: push until the last level, which always pulls
+        for (uint32_t src : {5u, 123u, 5u}) {
+            dense_t r2 = ref_bfs(g, src, 4);
+            verify(r2, bfs.pull_push(src, 4, 0.01f), true);
+            verify(r2, bfs.push(src, 4), true);
+        }
     }
 }
 
@@ -86,6 +95,9 @@ TEST(SSSP, AllModes) {
         verify(ref, sssp.pull(0, 10), true);
         verify(ref, sssp.push(0, 10), true);
         verify(ref, sssp.pull_push(0, 10, 0.1f), true);
+        for (float thr : {0.001f, 0.1f, 1.1f}) verify(ref, sssp.pull_push(0, 10, thr), true);
+        verify(ref, sssp.push(0, 10), true);
+        verify(ref, sssp.pull(0, 10), true);
     }
 }
 
