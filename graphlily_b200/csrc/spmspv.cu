@@ -43,6 +43,15 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kSeg = 512;             // non-zeros per unit of work (one warp: 16 strides of 32)
 constexpr float kFloatInf = 999999999.0f;  // FLOAT_INF, global.h:80 (spmspv_module.h:482-491)
 
+// Order-preserving map float -> signed int (and back: it is an involution): negative floats, whose bit patterns
+// order inversely, get their magnitude bits flipped.  -0.0f sorts just below +0.0f; NaN keys are never produced
+// by min-plus on ordered inputs.
+__device__ __forceinline__ int f32_key(float v) {
+    const int b = __float_as_int(v);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float f32_unkey(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 // (x) of the scatter.  fp32 min-plus clamps at FLOAT_INF like the reference's CPU path
 // (spmspv_module.h:482-491); the integer value types follow the processing element's ALU
 // (ufixed_pe_fwd.h:23-44): plain (wrapping / saturating) addition.
@@ -143,9 +152,9 @@ __device__ __forceinline__ void scatter_span(const SpmspvParams &P, uint32_t s, 
         } else if (OP == GLB_OP_LOGICAL_AND_OR) {
             if (!Val<VT>::is_zero(p)) *a = Val<VT>::one();  // idempotent: racing writers store the same word
         } else if (VT == GLB_VAL_F32) {
-            // float min through integer atomics: non-negative floats order like ints, negative ones inversely as unsigned
-            if (p >= 0.0f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(p));
-            else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(p));
+            // float min as ONE integer reduction: the accumulator holds order-preserving keys (f32_key) of the
+            // floats, so signed-int min is float min for every sign; +inf is its own key, so the rest state is +inf
+            atomicMin(reinterpret_cast<int *>(a), f32_key(p));
         } else {
             atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(p));
         }
@@ -257,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 4) spmspv_kernel(const SpmspvParams 
             const uint32_t r = base_row + ((g0 + j) << 5) + lane;
             const bool ok = g0 + j < n_groups && r >= P.row_begin && r < P.row_end && ((word >> lane) & 1u);
             a[j] = ok ? __ldcg(P.acc + r) : Semi<OP, VT>::ident();
+            if (OP == GLB_OP_ADD_MIN && VT == GLB_VAL_F32) a[j] = f32_unkey(__float_as_int(a[j]));  // keys -> floats (+inf is its own key)
             mk[j] = (ok && P.mask_type != GLB_MASK_NONE) ? P.mask[r] : 0.0f;
             dv[j] = (ok && relax) ? P.ep_inout[r] : 0.0f;
             if (ok) live |= 1u << j;
