@@ -50,9 +50,16 @@ private:
 
     void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
         const uint32_t n = matrix_num_rows_;
-        if (fused_) {
+        if (fused_ || exchange_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf, mask = SpMV_->mask_buf;
             replay({1, key_of(SpMV_->device_matrix()), first_iter, num_iterations, key_of(vec.ptr()), key_of(res.ptr()), key_of(mask.ptr())}, [&] {
+                if (exchange_) {   // the whole loop in one call; the distance stays row-local until the end
+                    std::vector<glb_spmv_epilogue_t> eps;
+                    for (uint32_t iter = first_iter; iter <= num_iterations; iter++)
+                        eps.push_back({0, 0.0f, mask.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE});
+                    SpMV_->iterate_exchange(*exchange_, vec, mask, res, eps.data(), int(eps.size()));
+                    return;
+                }
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
                     glb_spmv_epilogue_t ep = {0, 0.0f, mask.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
@@ -183,20 +190,31 @@ public:
 
     void send_matrix_host_to_device() {
         drop_recorded_sequences();
-        SpMV_->send_matrix_host_to_device();
-        SpMSpV_->send_matrix_host_to_device();
+        if (world_ > 1) make_cuts(SpMV_->host_matrix().adj_indptr, matrix_num_rows_);
+        SpMV_->send_matrix_host_to_device(row_begin(), row_end(matrix_num_rows_));
+        if (exchange_) {   // vector / results / distance of the pull loop live in the exchange
+            assert(exchange_->size() == matrix_num_rows_ && exchange_->vectors() >= 3);
+            SpMV_->vector_buf = exchange_->buffer(0);
+            SpMV_->results_buf = exchange_->buffer(1);
+            SpMV_->mask_buf = exchange_->buffer(2);
+        }
+        if (world_ == 1) SpMSpV_->send_matrix_host_to_device();   // (the C++ mirror shards the pull direction only)
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
+        if (exchange_) exchange_->barrier();   // no rank overwrites vectors a peer still reads from the previous run
         // input = zero, input[source] = 1; distance = 0, distance[source] = 1 (bfs.h:108-112): built on
         // the device instead of uploaded
         SpMV_->set_vector_constant(semiring_.zero, source, 1);
         SpMV_->set_mask_constant(0, source, 1);
         pull_loop(1, num_iterations);
+        if (exchange_)   // the distance was updated shard by shard: complete it on every rank
+            exchange_->allgather(2, row_begin(), row_end(matrix_num_rows_) - row_begin());
         return SpMV_->send_mask_device_to_host();
     }
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
+        assert(world_ == 1 && "the C++ mirror shards the pull direction only");
         push_setup(source);
         if (!fused_) {
             for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);

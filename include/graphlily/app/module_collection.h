@@ -7,6 +7,7 @@
 #ifndef GRAPHLILY_MODULE_COLLECTION_H_
 #define GRAPHLILY_MODULE_COLLECTION_H_
 
+#include <algorithm>
 #include <cassert>
 #include <cstring>
 #include <functional>
@@ -30,6 +31,25 @@ protected:
     std::vector<std::string> kernel_names_;
     std::string target_ = "hw";
     std::shared_ptr<Runtime> runtime_;
+
+    // Row-range sharding over the ranks of one box (one process per GPU): this process owns the
+    // rows [cuts_[rank], cuts_[rank + 1]) of the CSR, cut where the nnz prefix crosses r / world (32-row
+    // aligned); the slices of every iteration's result meet over the exchange.  Pull direction.
+    int rank_ = 0, world_ = 1;
+    Exchange *exchange_ = nullptr;
+    std::vector<uint32_t> cuts_;
+    void make_cuts(const std::vector<uint32_t> &indptr, uint32_t n) {
+        cuts_.assign(size_t(world_) + 1, 0);
+        const uint64_t nnz = indptr[n];
+        for (int r = 1; r < world_; r++) {
+            const uint64_t want = nnz * uint64_t(r) / uint64_t(world_);
+            const uint32_t row = uint32_t(std::lower_bound(indptr.begin(), indptr.begin() + n + 1, uint32_t(want)) - indptr.begin());
+            cuts_[r] = std::max(cuts_[r - 1], std::min(n, row) / 32 * 32);
+        }
+        cuts_[world_] = n;
+    }
+    uint32_t row_begin() const { return cuts_.empty() ? 0 : cuts_[rank_]; }
+    uint32_t row_end(uint32_t n) const { return cuts_.empty() ? n : cuts_[rank_ + 1]; }
 
     // Launch replay.  The iteration loop of an app is a fixed launch sequence (same buffers, same
     // per-iteration scalars): it is recorded once per key as a CUDA graph (glb_graph_begin / _end)
@@ -81,6 +101,14 @@ public:
         for (size_t i = 0; i < num_modules_; i++) delete modules_[i];
     }
     void set_use_graphs(bool on) { use_graphs_ = on; }
+    // Call before send_matrix_host_to_device.  `exchange`: connected, >= 3 vectors of the padded dimension
+    // (0 / 1: the SpMV vector / results, 2: its mask); the collection does not own it.
+    void set_sharding(int rank, int world, Exchange *exchange) {
+        assert(rank >= 0 && rank < world && (world == 1 || exchange != nullptr));
+        rank_ = rank;
+        world_ = world;
+        exchange_ = exchange;
+    }
 
     void add_module(BaseModule *module) {
         modules_.push_back(module);

@@ -60,17 +60,29 @@ public:
 
     void send_matrix_host_to_device() {
         drop_recorded_sequences();
-        SpMV_->send_matrix_host_to_device();
+        if (world_ > 1) make_cuts(SpMV_->host_matrix().adj_indptr, matrix_num_rows_);
+        SpMV_->send_matrix_host_to_device(row_begin(), row_end(matrix_num_rows_));
+        if (exchange_) {   // the vectors of the loop live in the exchange: every rank sees every slice
+            assert(exchange_->size() == matrix_num_rows_ && exchange_->vectors() >= 2);
+            SpMV_->vector_buf = exchange_->buffer(0);
+            SpMV_->results_buf = exchange_->buffer(1);
+        }
     }
 
     aligned_dense_vec_t pull(float damping, uint32_t num_iterations) {
         const uint32_t n = matrix_num_rows_;
         const float teleport = (1 - damping) / n;
+        if (exchange_) exchange_->barrier();   // no rank overwrites vectors a peer still reads from the previous run
         SpMV_->set_vector_constant(float(1.0 / n));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
-        if (fused_) {
+        if (fused_ || exchange_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
             replay({2, key_of(SpMV_->device_matrix()), key_of(teleport), num_iterations, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
                 glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
+                if (exchange_) {
+                    std::vector<glb_spmv_epilogue_t> eps(num_iterations, ep);
+                    SpMV_->iterate_exchange(*exchange_, vec, DeviceBuffer(), res, eps.data(), int(num_iterations));
+                    return;
+                }
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t iter = 1; iter <= num_iterations; iter++) {
                     SpMV_->run_fused(v, DeviceBuffer(), r, &ep);

@@ -87,10 +87,14 @@ private:
     using aligned_sparse_vec_t = graphlily::aligned_sparse_vec_t;
 
     void pull_loop(uint32_t first_iter, uint32_t num_iterations) {
-        if (fused_) {
+        if (fused_ || exchange_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
             const uint32_t count = num_iterations >= first_iter ? num_iterations - first_iter + 1 : 0;
             replay({3, key_of(SpMV_->device_matrix()), count, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
+                if (exchange_) {
+                    SpMV_->iterate_exchange(*exchange_, vec, DeviceBuffer(), res, nullptr, int(count));
+                    return;
+                }
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t k = 0; k < count; k++) {
                     SpMV_->run_fused(v, DeviceBuffer(), r, nullptr);
@@ -206,17 +210,25 @@ public:
 
     void send_matrix_host_to_device() {
         drop_recorded_sequences();
-        SpMV_->send_matrix_host_to_device();
-        SpMSpV_->send_matrix_host_to_device();
+        if (world_ > 1) make_cuts(SpMV_->host_matrix().adj_indptr, matrix_num_rows_);
+        SpMV_->send_matrix_host_to_device(row_begin(), row_end(matrix_num_rows_));
+        if (exchange_) {
+            assert(exchange_->size() == matrix_num_rows_ && exchange_->vectors() >= 2);
+            SpMV_->vector_buf = exchange_->buffer(0);
+            SpMV_->results_buf = exchange_->buffer(1);
+        }
+        if (world_ == 1) SpMSpV_->send_matrix_host_to_device();   // (the C++ mirror shards the pull direction only)
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
+        if (exchange_) exchange_->barrier();
         SpMV_->set_vector_constant(semiring_.zero, source, 0);  // sssp.h:153-156
         pull_loop(1, num_iterations);
         return SpMV_->send_vector_device_to_host();
     }
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
+        assert(world_ == 1 && "the C++ mirror shards the pull direction only");
         push_setup(source);
         if (!fused_) {
             for (uint32_t iter = 1; iter <= num_iterations; iter++) {

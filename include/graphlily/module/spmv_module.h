@@ -124,6 +124,16 @@ public:
                                  mask_type_ == graphlily::kNoMask ? nullptr : mask.f32(), results.f32(), epilogue));
     }
 
+    // Row-sharded pull loop in one call (glb_spmv_exchange_iterate): vector -> results -> vector ... over two
+    // vectors of the exchange, eps = nullptr or one fused epilogue per step.
+    void iterate_exchange(Exchange &xc, const DeviceBuffer &vector, const DeviceBuffer &mask, const DeviceBuffer &results,
+                          const glb_spmv_epilogue_t *eps, int n_steps) {
+        assert(vector.exchange_vector() >= 0 && results.exchange_vector() >= 0);
+        GLB_CHECK(glb_spmv_exchange_iterate(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, xc.handle(),
+                                            vector.exchange_vector(), results.exchange_vector(),
+                                            mask_type_ == graphlily::kNoMask ? nullptr : mask.f32(), eps, n_steps, nullptr));
+    }
+
     aligned_dense_vec_t send_vector_device_to_host() {
         download(vector_, vector_buf, get_num_cols());
         return vector_;

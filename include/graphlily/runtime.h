@@ -47,6 +47,13 @@ class DeviceBuffer {
 public:
     DeviceBuffer() {}
     DeviceBuffer(const std::shared_ptr<Runtime> &rt, size_t bytes) : block_(std::make_shared<Block>(rt, bytes)) {}
+    // non-owning handle over device memory that belongs to something else (a vector of an Exchange)
+    static DeviceBuffer view(const std::shared_ptr<Runtime> &rt, void *ptr, size_t bytes, int exchange_vector = -1) {
+        DeviceBuffer b;
+        b.block_ = std::make_shared<Block>(rt, ptr, bytes, exchange_vector);
+        return b;
+    }
+    int exchange_vector() const { return block_ ? block_->exchange_vector : -1; }
     void *ptr() const { return block_ ? block_->ptr : nullptr; }
     float *f32() const { return static_cast<float *>(ptr()); }
     glb_idx_val_t *sparse() const { return static_cast<glb_idx_val_t *>(ptr()); }
@@ -58,10 +65,50 @@ private:
         std::shared_ptr<Runtime> rt;
         void *ptr = nullptr;
         size_t bytes = 0;
+        bool owned = true;
+        int exchange_vector = -1;
         Block(const std::shared_ptr<Runtime> &r, size_t b) : rt(r), bytes(b) { GLB_CHECK(glb_buffer_alloc(rt->ctx(), b, &ptr)); }
-        ~Block() { glb_buffer_free(rt->ctx(), ptr); }
+        Block(const std::shared_ptr<Runtime> &r, void *p, size_t b, int xv) : rt(r), ptr(p), bytes(b), owned(false), exchange_vector(xv) {}
+        ~Block() { if (owned) glb_buffer_free(rt->ctx(), ptr); }
     };
     std::shared_ptr<Block> block_;
+};
+
+// Vectors of a row-sharded run, mapped in every rank's process (one process per GPU): the C ABI's peer
+// exchange over CUDA IPC (glb_xchg_create / _export / _connect) -- no framework in the data path.  The
+// host exchanges the 64-byte handles of all ranks by any means it has (a pipe, MPI, a file).
+class Exchange {
+public:
+    Exchange(const std::shared_ptr<Runtime> &rt, uint32_t n_floats, int n_vectors) : rt_(rt), n_(n_floats), n_vectors_(n_vectors) {
+        GLB_CHECK(glb_xchg_create(rt_->ctx(), n_floats, n_vectors, &xc_));
+    }
+    ~Exchange() { glb_xchg_destroy(xc_); }
+    Exchange(const Exchange &) = delete;
+    Exchange &operator=(const Exchange &) = delete;
+    void export_handle(void *handle64) { GLB_CHECK(glb_xchg_export(xc_, handle64)); }
+    // handles: world x GLB_IPC_HANDLE_BYTES, in rank order
+    void connect(int rank, int world, const void *handles) {
+        GLB_CHECK(glb_xchg_connect(xc_, rank, world, handles));
+        rank_ = rank;
+        world_ = world;
+    }
+    DeviceBuffer buffer(int which) {
+        float *p = nullptr;
+        GLB_CHECK(glb_xchg_vector(xc_, which, &p));
+        return DeviceBuffer::view(rt_, p, sizeof(float) * size_t(n_), which);
+    }
+    void barrier() { GLB_CHECK(glb_xchg_barrier(rt_->ctx(), xc_)); }
+    void allgather(int which, size_t offset, size_t count) { GLB_CHECK(glb_xchg_allgather(rt_->ctx(), xc_, which, offset, count)); }
+    glb_xchg_t handle() const { return xc_; }
+    uint32_t size() const { return n_; }
+    int vectors() const { return n_vectors_; }
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+private:
+    std::shared_ptr<Runtime> rt_;
+    glb_xchg_t xc_ = nullptr;
+    uint32_t n_;
+    int n_vectors_, rank_ = 0, world_ = 1;
 };
 
 }  // namespace graphlily

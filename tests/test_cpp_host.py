@@ -80,6 +80,16 @@ def test_cpp_modules_and_apps_on_gpu(name):
 
 
 @pytest.mark.gpu
+def test_cpp_sharded_apps_two_processes():
+    """Row-sharded BFS / PageRank / SSSP from the C++ mirror: two processes, one GPU each, vectors in a
+    CUDA-IPC peer exchange (no torch anywhere).  The binary reports SKIPPED on a 1-GPU box."""
+    out = _run("test_sharded")
+    if "SKIPPED" in out:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    assert out.count("[  OK  ]") == 2
+
+
+@pytest.mark.gpu
 def test_reference_own_test_files_unmodified(tmp_path):
     """SURVEY.md 8b "Callers: same call sequences must compile and run": the reference's OWN gtest files
     (/root/reference/tests/test_app.cpp, test_module_spmv_spmspv.cpp, test_module_apply.cpp), compiled
