@@ -106,6 +106,12 @@ static void ctx_free(glb_ctx_t ctx) {
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->branch_stream) cudaStreamDestroy(ctx->branch_stream);
+    if (ctx->split_ev_head) cudaEventDestroy(ctx->split_ev_head);
+    for (int s = 0; s < GLB_MAX_SPLIT; ++s) {
+        if (ctx->split_stream[s]) cudaStreamDestroy(ctx->split_stream[s]);
+        if (ctx->split_ev_main[s]) cudaEventDestroy(ctx->split_ev_main[s]);
+        if (ctx->split_ev_done[s]) cudaEventDestroy(ctx->split_ev_done[s]);
+    }
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

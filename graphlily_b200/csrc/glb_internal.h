@@ -59,6 +59,10 @@ struct glb_ctx_s {
     cudaStream_t branch_stream = nullptr, outer_stream = nullptr;
     cudaGraph_t branch_body[2] = {nullptr, nullptr};
     int in_branch = 0;  // 1: IF body, 2: ELSE body
+    // split steps of a row-sharded run (spmv.cu: launch_split): one stream per sub-block of the shard
+#define GLB_MAX_SPLIT 8
+    cudaStream_t split_stream[GLB_MAX_SPLIT] = {};
+    cudaEvent_t split_ev_head = nullptr, split_ev_main[GLB_MAX_SPLIT] = {}, split_ev_done[GLB_MAX_SPLIT] = {};
     // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]
@@ -124,6 +128,9 @@ struct glb_csr_s {
     bool all_nonzero = false;      // no stored value is 0.0f (or-and skips the value stream)
     int smem_carveout_pct = 20;
     uint32_t tile_threads = 0;     // > 0: persistent shared-memory-tile kernel with that many threads per CTA
+    // sub-blocks of a split step (host side): chunk / row boundaries and the ranges of the fix-up and empty-row
+    // lists whose rows lie in each sub-block
+    std::vector<uint32_t> sub_chunk, sub_row, sub_fs, sub_fl, sub_em;
     // progressive push of a row-sharded run over a multicast exchange (spmv.cu: push_block_when_complete)
     uint32_t *push_bits = nullptr, *push_lo = nullptr, *push_count = nullptr;
     // scratch vectors for glb_spmv_host
@@ -203,9 +210,15 @@ struct GlbSpmvMc {
     uint32_t *pub_flags_mc, *pub_state;
     int rank;
 };
+// Split step: the finished rows of every sub-block go to these peer copies of y with copy-engine copies while
+// later sub-blocks still compute (launch_split); the caller publishes the epoch afterwards.
+struct GlbSpmvSplit {
+    float *y_peers[GLB_MAX_PEERS];
+    int n_peers;
+};
 // `wait`: acquire of the previous step's exchange, folded into the head of the launch's first kernel (or NULL)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
-                    const GlbXchgWait *wait, bool *published, int val_type);
+                    const GlbXchgWait *wait, bool *published, int val_type, const GlbSpmvSplit *split);
 
 #endif  // GLB_INTERNAL_H_

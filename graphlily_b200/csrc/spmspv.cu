@@ -416,7 +416,19 @@ __global__ void sparse_head_kernel(glb_idx_val_t *list, float zero) {
 
 template <int OP, int VT>
 int run_spmspv(glb_ctx_t ctx, glb_csc_t m, const SpmspvParams &P) {
-    spmspv_kernel<OP, VT><<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(P);
+    // The grid barriers need every CTA of the launch resident at once: ask the runtime how many CTAs of THIS
+    // instantiation fit on an SM (once per instantiation) instead of trusting the launch bounds.
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmspv_kernel<OP, VT>, kThreads, 0));
+        if (n < 1) {
+            glb_set_error("glb_spmspv: the kernel does not fit on an SM");
+            return GLB_ECUDA;
+        }
+        per_sm = n < 4 ? n : 4;
+    }
+    spmspv_kernel<OP, VT><<<ctx->num_sms * per_sm, kThreads, 0, ctx->stream>>>(P);
     GLB_CUDA(cudaGetLastError());
     return GLB_OK;
 }

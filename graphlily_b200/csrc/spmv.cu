@@ -93,6 +93,7 @@ struct SpmvParams {
     float *head_carry;
     float *tail_carry;
     uint32_t n_chunks;
+    uint32_t chunk_begin, chunk_end;  // the chunks THIS launch of the main kernel covers (all, or one sub-block of a split step)
     uint32_t tile_k;
     float zero;
     int mask_type;
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_kerne
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk < P.n_chunks) process_chunk<OP, false, 0, MASKED, VT>(P, chunk, lane, stage_all[wib], 0u);  // warp-uniform
+    const uint32_t chunk = P.chunk_begin + blockIdx.x * kWarpsPerBlock + wib;
+    if (chunk < P.chunk_end) process_chunk<OP, false, 0, MASKED, VT>(P, chunk, lane, stage_all[wib], 0u);  // warp-uniform
     if (P.push_bits) push_block_when_complete(P);
 }
 
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_
     __shared__ float stage_all[kWarpsPerBlock][GLB_ROW_CAP];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wib = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * kWarpsPerBlock + wib;
-    if (chunk < P.n_chunks) process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS, MASKED>(P, chunk, lane, stage_all[wib], 0u);
+    const uint32_t chunk = P.chunk_begin + blockIdx.x * kWarpsPerBlock + wib;
+    if (chunk < P.chunk_end) process_chunk<GLB_OP_LOGICAL_AND_OR, false, BITS, MASKED>(P, chunk, lane, stage_all[wib], 0u);
     if (P.push_bits) push_block_when_complete(P);
 }
 
@@ -524,15 +525,22 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
     }
 }
 
+constexpr int kLaunchMain = 1, kLaunchFixup = 2;
+
+// `st`: the stream of this launch (the context's, or a sub-block stream of a split step); `which`: main kernel,
+// fix-up kernel or both.  The main kernel covers chunks [P.chunk_begin, P.chunk_end).
 template <int OP, int VT = GLB_VAL_F32>
-int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
-    P.n_ctas = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published, cudaStream_t st, int which) {
+    const uint32_t n_window = P.chunk_end - P.chunk_begin;
+    P.n_ctas = (n_window + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const bool timing = ctx->timing && st == ctx->stream && which == (kLaunchMain | kLaunchFixup);
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    if (ctx->timing) {
+    if (timing) {
         for (auto &e : ev) GLB_CUDA(cudaEventCreate(&e));
-        GLB_CUDA(cudaEventRecord(ev[0], ctx->stream));
+        GLB_CUDA(cudaEventRecord(ev[0], st));
     }
-    if (VT == GLB_VAL_F32 && P.n_chunks && m->tile_threads) {
+    const bool do_main = (which & kLaunchMain) && n_window;
+    if (VT == GLB_VAL_F32 && do_main && m->tile_threads) {
         const uint32_t n_warps = m->tile_threads / 32;
         const size_t smem = size_t((P.tile_k + 3u) & ~3u) * 4 + size_t(n_warps) * GLB_ROW_CAP * 4 + 16;
         size_t *attr_set = ctx->tile_smem_set;  // function attributes are per device: cached in the context
@@ -540,11 +548,11 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
             GLB_CUDA(cudaFuncSetAttribute(spmv_lane_tile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             attr_set[OP] = smem;
         }
-        uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;
+        uint32_t grid = (P.n_chunks + n_warps - 1) / n_warps;  // (no split support: always the whole shard)
         if (grid > uint32_t(ctx->num_sms)) grid = uint32_t(ctx->num_sms);
-        spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, ctx->stream>>>(P);
-    } else if (VT == GLB_VAL_F32 && P.n_chunks && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
-        const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        spmv_lane_tile_kernel<OP><<<grid, m->tile_threads, smem, st>>>(P);
+    } else if (VT == GLB_VAL_F32 && do_main && OP == GLB_OP_LOGICAL_AND_OR && P.xbits) {
+        const uint32_t grid = P.n_ctas;
         int &bits_carveout_set = ctx->bits_carveout_set;
         if (bits_carveout_set != m->smem_carveout_pct) {
             const int pct = m->smem_carveout_pct;
@@ -555,11 +563,11 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
             bits_carveout_set = pct;
         }
         const bool masked = P.mask_type != GLB_MASK_NONE;
-        if (m->all_nonzero && masked) spmv_lane_bits_kernel<2, true><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else if (m->all_nonzero) spmv_lane_bits_kernel<2, false><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else if (masked) spmv_lane_bits_kernel<1, true><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else spmv_lane_bits_kernel<1, false><<<grid, kThreads, 0, ctx->stream>>>(P);
-    } else if (P.n_chunks) {
+        if (m->all_nonzero && masked) spmv_lane_bits_kernel<2, true><<<grid, kThreads, 0, st>>>(P);
+        else if (m->all_nonzero) spmv_lane_bits_kernel<2, false><<<grid, kThreads, 0, st>>>(P);
+        else if (masked) spmv_lane_bits_kernel<1, true><<<grid, kThreads, 0, st>>>(P);
+        else spmv_lane_bits_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
+    } else if (do_main) {
         // leave everything but the staging arrays to L1: that is where the hot x lines live
         int *carveout_set = ctx->carveout_set + 3 * VT;
         if (carveout_set[OP] != m->smem_carveout_pct) {
@@ -569,20 +577,20 @@ int launch_op(glb_ctx_t ctx, glb_csr_t m, SpmvParams P, bool *published) {
                                           m->smem_carveout_pct));
             carveout_set[OP] = m->smem_carveout_pct;
         }
-        const uint32_t grid = (P.n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (P.mask_type != GLB_MASK_NONE) spmv_lane_kernel<OP, true, VT><<<grid, kThreads, 0, ctx->stream>>>(P);
-        else spmv_lane_kernel<OP, false, VT><<<grid, kThreads, 0, ctx->stream>>>(P);
+        const uint32_t grid = P.n_ctas;
+        if (P.mask_type != GLB_MASK_NONE) spmv_lane_kernel<OP, true, VT><<<grid, kThreads, 0, st>>>(P);
+        else spmv_lane_kernel<OP, false, VT><<<grid, kThreads, 0, st>>>(P);
     }
-    if (ctx->timing) GLB_CUDA(cudaEventRecord(ev[1], ctx->stream));
+    if (timing) GLB_CUDA(cudaEventRecord(ev[1], st));
     const uint32_t nb_short = (P.n_fix_short + kThreads - 1) / kThreads;
     const uint32_t nb_long = (P.n_fix_long + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const uint32_t nb_empty = (P.n_empty + kThreads - 1) / kThreads;
-    if (nb_short + nb_long + nb_empty) {
-        spmv_fixup_kernel<OP, VT><<<nb_short + nb_long + nb_empty, kThreads, 0, ctx->stream>>>(P, nb_short, nb_long);
+    if ((which & kLaunchFixup) && nb_short + nb_long + nb_empty) {
+        spmv_fixup_kernel<OP, VT><<<nb_short + nb_long + nb_empty, kThreads, 0, st>>>(P, nb_short, nb_long);
         if (published) *published = P.pub_flags_mc != nullptr;
     }
-    if (ctx->timing) {
-        GLB_CUDA(cudaEventRecord(ev[2], ctx->stream));
+    if (timing) {
+        GLB_CUDA(cudaEventRecord(ev[2], st));
         for (auto e : ev) ctx->timing_events.push_back(e);
     }
     GLB_CUDA(cudaGetLastError());
@@ -606,9 +614,71 @@ int upload(glb_ctx_t ctx, T **dptr, const T *host, size_t n, size_t n_alloc, siz
 
 }  // namespace
 
+static int dispatch_op(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const SpmvParams &P, bool *published, cudaStream_t st,
+                       int which) {
+    switch (op * 3 + val_type) {
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_F32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_F32>(ctx, m, P, published, st, which);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_F32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_F32>(ctx, m, P, published, st, which);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_F32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_F32>(ctx, m, P, published, st, which);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_U32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_U32>(ctx, m, P, published, st, which);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_U32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_U32>(ctx, m, P, published, st, which);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_U32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_U32>(ctx, m, P, published, st, which);
+        case GLB_OP_MUL_ADD * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_UFIXED>(ctx, m, P, published, st, which);
+        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_UFIXED>(ctx, m, P, published, st, which);
+        case GLB_OP_ADD_MIN * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_UFIXED>(ctx, m, P, published, st, which);
+    }
+    glb_set_error("glb_spmv: invalid semiring op %d", op);
+    return GLB_EINVAL;
+}
+
+// Split step of a row-sharded run: the shard's chunks are cut into sub-blocks whose main kernels are launched
+// on streams of their own (they run concurrently, like one launch, but each signals its own completion); as
+// soon as a sub-block and its fix-up rows are done, its finished rows [sub_row[s], sub_row[s + 1]) go to every
+// peer with COPY-ENGINE peer copies, which overlap the sub-blocks still computing without touching the SMs'
+// request ports (SM-issued remote stores from inside the kernel measured slower).  The
+// caller publishes the epoch after the join.
+static int launch_split(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const SpmvParams &P0, const GlbSpmvSplit &sp) {
+    const int S = int(m->sub_chunk.size()) - 1;
+    if (!ctx->split_ev_head) {
+        GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_head, cudaEventDisableTiming));
+        for (int s = 0; s < GLB_MAX_SPLIT; ++s) {
+            GLB_CUDA(cudaStreamCreateWithFlags(&ctx->split_stream[s], cudaStreamNonBlocking));
+            GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_main[s], cudaEventDisableTiming));
+            GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_done[s], cudaEventDisableTiming));
+        }
+    }
+    GLB_CUDA(cudaEventRecord(ctx->split_ev_head, ctx->stream));  // after the head kernel (hot-column pack / bitmap, with the acquire)
+    for (int s = 0; s < S; ++s) {
+        cudaStream_t st = ctx->split_stream[s];
+        GLB_CUDA(cudaStreamWaitEvent(st, ctx->split_ev_head, 0));
+        SpmvParams P = P0;
+        P.chunk_begin = m->sub_chunk[s];
+        P.chunk_end = m->sub_chunk[s + 1];
+        int rc = dispatch_op(ctx, m, op, val_type, P, nullptr, st, kLaunchMain);
+        if (rc) return rc;
+        GLB_CUDA(cudaEventRecord(ctx->split_ev_main[s], st));
+        // rows of this sub-block that touch chunk boundaries (their spans may reach back into earlier sub-blocks) and its empty rows
+        for (int t = 0; t < s; ++t) GLB_CUDA(cudaStreamWaitEvent(st, ctx->split_ev_main[t], 0));
+        P.fix_short = m->fix_short + m->sub_fs[s];
+        P.n_fix_short = m->sub_fs[s + 1] - m->sub_fs[s];
+        P.fix_long = m->fix_long + m->sub_fl[s];
+        P.n_fix_long = m->sub_fl[s + 1] - m->sub_fl[s];
+        P.empty_rows = m->empty_rows + m->sub_em[s];
+        P.n_empty = m->sub_em[s + 1] - m->sub_em[s];
+        rc = dispatch_op(ctx, m, op, val_type, P, nullptr, st, kLaunchFixup);
+        if (rc) return rc;
+        const uint32_t r0 = m->sub_row[s], r1 = m->sub_row[s + 1];
+        for (int p = 0; p < sp.n_peers && r1 > r0; ++p)
+            GLB_CUDA(cudaMemcpyAsync(sp.y_peers[p] + r0, P0.y + r0, sizeof(float) * size_t(r1 - r0), cudaMemcpyDeviceToDevice, st));
+        GLB_CUDA(cudaEventRecord(ctx->split_ev_done[s], st));
+    }
+    for (int s = 0; s < S; ++s) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->split_ev_done[s], 0));
+    return GLB_OK;
+}
+
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
-                    const GlbXchgWait *wait, bool *published, int val_type) {
+                    const GlbXchgWait *wait, bool *published, int val_type, const GlbSpmvSplit *split) {
     SpmvParams P;
     memset(&P, 0, sizeof(P));
     if (published) *published = false;
@@ -664,6 +734,8 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.head_carry = m->head_carry;
     P.tail_carry = m->tail_carry;
     P.n_chunks = m->n_chunks;
+    P.chunk_begin = 0;
+    P.chunk_end = m->n_chunks;
     P.zero = zero;
     P.mask_type = mask_type;
     if (ep) {
@@ -680,19 +752,8 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
     P.n_nz_rows = m->n_nz_rows;
-    switch (op * 3 + val_type) {
-        case GLB_OP_MUL_ADD * 3 + GLB_VAL_F32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_F32>(ctx, m, P, published);
-        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_F32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_F32>(ctx, m, P, published);
-        case GLB_OP_ADD_MIN * 3 + GLB_VAL_F32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_F32>(ctx, m, P, published);
-        case GLB_OP_MUL_ADD * 3 + GLB_VAL_U32: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_U32>(ctx, m, P, published);
-        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_U32: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_U32>(ctx, m, P, published);
-        case GLB_OP_ADD_MIN * 3 + GLB_VAL_U32: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_U32>(ctx, m, P, published);
-        case GLB_OP_MUL_ADD * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_MUL_ADD, GLB_VAL_UFIXED>(ctx, m, P, published);
-        case GLB_OP_LOGICAL_AND_OR * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_LOGICAL_AND_OR, GLB_VAL_UFIXED>(ctx, m, P, published);
-        case GLB_OP_ADD_MIN * 3 + GLB_VAL_UFIXED: return launch_op<GLB_OP_ADD_MIN, GLB_VAL_UFIXED>(ctx, m, P, published);
-    }
-    glb_set_error("glb_spmv: invalid semiring op %d", op);
-    return GLB_EINVAL;
+    if (!split) return dispatch_op(ctx, m, op, val_type, P, published, ctx->stream, kLaunchMain | kLaunchFixup);
+    return launch_split(ctx, m, op, val_type, P, *split);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1024,6 +1085,32 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
         if (!rc) rc = upload(ctx, &m->push_lo, lo.data(), lo.size(), lo.size(), &bytes);
         if (!rc) rc = upload<uint32_t>(ctx, &m->push_count, nullptr, 0, n_blocks, &bytes);
     }
+    {
+        // sub-blocks of a split step (GLB_XCHG_SPLIT=<1..8>, default 4): chunk boundaries on CTA multiples, the row
+        // open at each boundary, and where the (row-ordered) fix-up / empty-row lists cross those rows
+        uint32_t S = env_u32("GLB_XCHG_SPLIT", 4);
+        S = S < 1 ? 1 : S > GLB_MAX_SPLIT ? GLB_MAX_SPLIT : S;
+        m->sub_chunk.assign(S + 1, L.n_chunks);
+        m->sub_row.assign(S + 1, row_end);
+        for (uint32_t sb = 0; sb < S; ++sb) {
+            uint32_t c = uint32_t(uint64_t(L.n_chunks) * sb / S) / kWarpsPerBlock * kWarpsPerBlock;
+            m->sub_chunk[sb] = c;
+            const uint32_t k = c < L.n_chunks ? (L.chunk_first[c] & ~GLB_FLAG) : uint32_t(L.nz_rows.size());
+            m->sub_row[sb] = sb == 0 ? row_begin : (k < L.nz_rows.size() ? L.nz_rows[k] : row_end);
+        }
+        auto cross = [&](const std::vector<uint32_t> &rows_of, std::vector<uint32_t> &out) {
+            out.assign(S + 1, uint32_t(rows_of.size()));
+            for (uint32_t sb = 0; sb <= S; ++sb)
+                out[sb] = uint32_t(std::lower_bound(rows_of.begin(), rows_of.end(), m->sub_row[sb]) - rows_of.begin());
+        };
+        std::vector<uint32_t> rs, rl;
+        for (const auto &e : L.fix_short) rs.push_back(e.row);
+        for (const auto &e : L.fix_long) rl.push_back(e.row);
+        cross(rs, m->sub_fs);
+        cross(rl, m->sub_fl);
+        cross(L.empty_rows, m->sub_em);
+        m->sub_fs[0] = m->sub_fl[0] = m->sub_em[0] = 0;
+    }
     if (!rc) rc = upload<float>(ctx, &m->head_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc) rc = upload<float>(ctx, &m->tail_carry, nullptr, 0, L.n_chunks, &bytes);
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -1082,7 +1169,7 @@ int glb_spmv_fused(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type
                    float *y, const glb_spmv_epilogue_t *ep) {
     int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
     if (rc) return rc;
-    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr, nullptr, GLB_VAL_F32);
+    return glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, nullptr, nullptr, GLB_VAL_F32, nullptr);
 }
 
 int glb_spmv_vt(glb_ctx_t ctx, glb_csr_t m, int val_type, int op, uint32_t zero_bits, int mask_type, const void *x, const void *mask,
@@ -1094,7 +1181,7 @@ int glb_spmv_vt(glb_ctx_t ctx, glb_csr_t m, int val_type, int op, uint32_t zero_
                              static_cast<float *>(y), ep);
     if (rc) return rc;
     return glb_launch_spmv(ctx, m, op, zero, mask_type, static_cast<const float *>(x), static_cast<const float *>(mask),
-                           static_cast<float *>(y), ep, nullptr, 0, nullptr, nullptr, nullptr, val_type);
+                           static_cast<float *>(y), ep, nullptr, 0, nullptr, nullptr, nullptr, val_type, nullptr);
 }
 
 int glb_spmv_exchange(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, glb_xchg_t xc, int src_vec, int dst_vec,
@@ -1123,7 +1210,7 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
     GLB_REQUIRE(n_steps >= 0, "negative step count");
     static const int forced = [] {
         const char *v = getenv("GLB_XCHG_MC");
-        return !v ? 1 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : !strcmp(v, "progressive") ? 3 : 1;
+        return !v ? 1 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : !strcmp(v, "progressive") ? 3 : !strcmp(v, "copy") ? 4 : 1;
     }();
     const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
@@ -1136,10 +1223,21 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         int rc = check_spmv_args(ctx, m, op, mask_type, x, mask, y, ep);
         if (rc) return rc;
         const GlbXchgWait *w = k > 0 ? &wait : nullptr;
-        if (xc->mc && xc->nranks > 1 && forced == 1) {
+        // (per-kernel timing and the tile variant take the plain sequence)
+        const int mode = (forced == 4 && (ctx->timing || m->tile_threads)) ? 1 : forced;
+        if (xc->nranks > 1 && mode == 4) {
+            // GLB_XCHG_MC=copy: split step -- sub-blocks of the shard on streams of their own, their finished rows
+            // copied to the peers by the copy engines while later sub-blocks compute, then one publishing kernel
+            GlbSpmvSplit sp;
+            sp.n_peers = 0;
+            for (int r = 0; r < xc->nranks; ++r)
+                if (r != xc->rank) sp.y_peers[sp.n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr, GLB_VAL_F32, &sp);
+            if (!rc) rc = glb_xchg_signal(ctx, xc, false);
+        } else if (xc->mc && xc->nranks > 1 && mode == 1) {
             // default: one push kernel after the SpMV kernels (all SMs store the finished slice in 16-byte
             // multimem.st; its last CTA publishes)
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr, GLB_VAL_F32);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr, GLB_VAL_F32, nullptr);
             if (!rc) rc = glb_xchg_push(ctx, xc, dv, m->row_begin, size_t(m->row_end - m->row_begin));
         } else if (xc->mc && xc->nranks > 1) {
             // GLB_XCHG_MC=progressive: completed blocks of rows are pushed from inside the main kernel while
@@ -1150,18 +1248,18 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
             // CTAs hold up that SM's L1 miss path, which is what bounds the SpMV.
             GlbSpmvMc mc;
             mc.y_mc = xc->mc + size_t(dv) * xc->n;
-            mc.progressive = forced == 3;
+            mc.progressive = mode == 3;
             mc.pub_flags_mc = xc->mc_flags;
             mc.pub_state = xc->d_state;
             mc.rank = xc->rank;
             bool published = false;
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, &published, GLB_VAL_F32);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, &published, GLB_VAL_F32, nullptr);
             if (!rc && !published) rc = glb_xchg_signal(ctx, xc, false);
         } else {
             int n_peers = 0;
             for (int r = 0; r < xc->nranks; ++r)
                 if (r != xc->rank) peers[n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
-            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w, nullptr, GLB_VAL_F32);
+            rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, peers, n_peers, nullptr, w, nullptr, GLB_VAL_F32, nullptr);
             if (!rc) rc = glb_xchg_signal(ctx, xc, false);
         }
         if (rc) return rc;
