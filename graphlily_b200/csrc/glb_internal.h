@@ -215,6 +215,7 @@ struct GlbSpmvMc {
 struct GlbSpmvSplit {
     float *y_peers[GLB_MAX_PEERS];
     int n_peers;
+    bool last_by_caller;  // the caller sends the last sub-block's rows itself (multicast push kernel)
 };
 // `wait`: acquire of the previous step's exchange, folded into the head of the launch's first kernel (or NULL)
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,

@@ -36,6 +36,7 @@
 // Algorithmic HBM bytes per launch: 8*nnz (cols+vals) + 4*nonempty_rows (nz_rows) + 4*ncols (x)
 // + 4*rows (y) [+ 4*rows mask], i.e. the CSR figure of SURVEY.md section 8d; the flag words add
 // 4 bytes per 32 non-zeros (1.6 %).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -641,13 +642,29 @@ static int launch_split(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const 
     const int S = int(m->sub_chunk.size()) - 1;
     if (!ctx->split_ev_head) {
         GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_head, cudaEventDisableTiming));
+        // Earlier sub-blocks get the higher stream priority: the block scheduler then drains them first instead of
+        // sharing the SMs evenly between the concurrent launches, so their rows are ready (and travelling) while the
+        // later ones still compute.
+        int prio_least = 0, prio_greatest = 0;
+        GLB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int s = 0; s < GLB_MAX_SPLIT; ++s) {
-            GLB_CUDA(cudaStreamCreateWithFlags(&ctx->split_stream[s], cudaStreamNonBlocking));
+            int prio = prio_greatest + s;
+            if (prio > prio_least) prio = prio_least;
+            GLB_CUDA(cudaStreamCreateWithPriority(&ctx->split_stream[s], cudaStreamNonBlocking, prio));
             GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_main[s], cudaEventDisableTiming));
             GLB_CUDA(cudaEventCreateWithFlags(&ctx->split_ev_done[s], cudaEventDisableTiming));
         }
     }
     GLB_CUDA(cudaEventRecord(ctx->split_ev_head, ctx->stream));  // after the head kernel (hot-column pack / bitmap, with the acquire)
+    // GLB_XCHG_TRACE=<n>: print the timeline of the n-th split step (device events; debugging, not while recording)
+    static const long trace_at = getenv("GLB_XCHG_TRACE") ? atol(getenv("GLB_XCHG_TRACE")) : -1;
+    static long call_no = 0;
+    const bool trace = trace_at >= 0 && call_no++ == trace_at;
+    cudaEvent_t tev[1 + 3 * GLB_MAX_SPLIT] = {};
+    if (trace) {
+        for (auto &e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], ctx->stream);
+    }
     for (int s = 0; s < S; ++s) {
         cudaStream_t st = ctx->split_stream[s];
         GLB_CUDA(cudaStreamWaitEvent(st, ctx->split_ev_head, 0));
@@ -657,6 +674,7 @@ static int launch_split(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const 
         int rc = dispatch_op(ctx, m, op, val_type, P, nullptr, st, kLaunchMain);
         if (rc) return rc;
         GLB_CUDA(cudaEventRecord(ctx->split_ev_main[s], st));
+        if (trace) cudaEventRecord(tev[1 + 3 * s], st);
         // rows of this sub-block that touch chunk boundaries (their spans may reach back into earlier sub-blocks) and its empty rows
         for (int t = 0; t < s; ++t) GLB_CUDA(cudaStreamWaitEvent(st, ctx->split_ev_main[t], 0));
         P.fix_short = m->fix_short + m->sub_fs[s];
@@ -667,12 +685,28 @@ static int launch_split(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const 
         P.n_empty = m->sub_em[s + 1] - m->sub_em[s];
         rc = dispatch_op(ctx, m, op, val_type, P, nullptr, st, kLaunchFixup);
         if (rc) return rc;
+        if (trace) cudaEventRecord(tev[2 + 3 * s], st);
         const uint32_t r0 = m->sub_row[s], r1 = m->sub_row[s + 1];
-        for (int p = 0; p < sp.n_peers && r1 > r0; ++p)
+        // (a copy-engine copy costs 12-17 us whatever its size: fine while other sub-blocks compute, too slow for the
+        // LAST one, whose rows the caller sends with the multicast push kernel when there is a multicast mapping)
+        for (int p = 0; p < sp.n_peers && r1 > r0 && !(sp.last_by_caller && s == S - 1); ++p)
             GLB_CUDA(cudaMemcpyAsync(sp.y_peers[p] + r0, P0.y + r0, sizeof(float) * size_t(r1 - r0), cudaMemcpyDeviceToDevice, st));
         GLB_CUDA(cudaEventRecord(ctx->split_ev_done[s], st));
+        if (trace) cudaEventRecord(tev[3 + 3 * s], st);
     }
     for (int s = 0; s < S; ++s) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->split_ev_done[s], 0));
+    if (trace) {
+        cudaDeviceSynchronize();
+        for (int s = 0; s < S; ++s) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * s]);
+            cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * s]);
+            cudaEventElapsedTime(&c, tev[0], tev[3 + 3 * s]);
+            fprintf(stderr, "[glb split] sub-block %d: chunks [%u, %u) rows [%u, %u) main done +%.1f us, fix-up done +%.1f us, copies done +%.1f us\n",
+                    s, m->sub_chunk[s], m->sub_chunk[s + 1], m->sub_row[s], m->sub_row[s + 1], a * 1e3, b * 1e3, c * 1e3);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return GLB_OK;
 }
 
@@ -1230,10 +1264,16 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
             // copied to the peers by the copy engines while later sub-blocks compute, then one publishing kernel
             GlbSpmvSplit sp;
             sp.n_peers = 0;
+            sp.last_by_caller = xc->mc != nullptr;
             for (int r = 0; r < xc->nranks; ++r)
                 if (r != xc->rank) sp.y_peers[sp.n_peers++] = xc->peer[r] + size_t(dv) * xc->n;
             rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, nullptr, w, nullptr, GLB_VAL_F32, &sp);
-            if (!rc) rc = glb_xchg_signal(ctx, xc, false);
+            if (!rc && sp.last_by_caller) {   // the last sub-block's rows by the push kernel, whose last CTA publishes
+                const uint32_t r0 = m->sub_row[m->sub_row.size() - 2];
+                rc = glb_xchg_push(ctx, xc, dv, r0, size_t(m->row_end - r0));
+            } else if (!rc) {
+                rc = glb_xchg_signal(ctx, xc, false);
+            }
         } else if (xc->mc && xc->nranks > 1 && mode == 1) {
             // default: one push kernel after the SpMV kernels (all SMs store the finished slice in 16-byte
             // multimem.st; its last CTA publishes)
