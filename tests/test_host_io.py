@@ -84,3 +84,28 @@ def test_generators_are_sorted_distinct_and_seeded():
     assert (dense == dense.T).all() and dense.diagonal().all()
     u = datasets.uniform_csr(1000, 1000, 10, seed=0)
     assert (np.diff(u.indptr.astype(np.int64)) == 10).all() and u.data[0] == np.float32(1e-3)
+
+
+def test_row_cuts_of_the_sharded_apps():
+    """ModuleCollection._cuts: equal slots under the NCCL allgather, nnz-balanced 32-row-aligned cuts over an
+    exchange (slices need not be equal there) -- computed identically on every rank, tiling all rows."""
+    from graphlily_b200 import datasets
+    from graphlily_b200.app import ModuleCollection
+    m = datasets.powerlaw_csr(4096, 4096, 150000, seed=3, max_degree=3000)
+    ip = m.indptr.astype(np.int64)
+    for world in (1, 2, 4, 8):
+        for exchange in (None, object()):
+            ranges = []
+            for rank in range(world):
+                mc = ModuleCollection()
+                mc.csr_matrix_ = m
+                mc.set_sharding(rank, world, exchange)
+                ranges.append(mc._row_range(m.num_rows))
+            assert ranges[0][0] == 0 and ranges[-1][1] == m.num_rows
+            assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))      # tiles, in rank order
+            if exchange is None or world == 1:
+                assert len({re - rb for rb, re in ranges}) == 1                          # equal slots
+            else:
+                assert all(rb % 32 == 0 for rb, _ in ranges)
+                nnz = [int(ip[re] - ip[rb]) for rb, re in ranges]
+                assert max(nnz) - min(nnz) <= 0.1 * m.nnz / world + 2 * 3000, nnz        # balanced up to one giant row
