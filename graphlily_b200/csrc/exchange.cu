@@ -112,6 +112,14 @@ GlbXchgWait glb_xchg_wait_desc(glb_xchg_t xc) {
     return w;
 }
 
+int glb_xchg_preload() {
+    cudaFuncAttributes fa;
+    GLB_CUDA(cudaFuncGetAttributes(&fa, xchg_signal_kernel));
+    GLB_CUDA(cudaFuncGetAttributes(&fa, xchg_wait_kernel));
+    GLB_CUDA(cudaFuncGetAttributes(&fa, xchg_push_signal_kernel));
+    return GLB_OK;
+}
+
 int glb_xchg_signal(glb_ctx_t ctx, glb_xchg_t xc, bool wait) {
     xchg_signal_kernel<<<1, 32, 0, ctx->stream>>>(xc->d_peer_flags, xc->local_flags, xc->mc_flags, xc->rank, xc->nranks,
                                                  xc->d_state, wait ? 1 : 0);

@@ -63,6 +63,10 @@ struct glb_ctx_s {
 #define GLB_MAX_SPLIT 8
     cudaStream_t split_stream[GLB_MAX_SPLIT] = {};
     cudaEvent_t split_ev_head = nullptr, split_ev_main[GLB_MAX_SPLIT] = {}, split_ev_done[GLB_MAX_SPLIT] = {};
+    // pusher CTAs of a row-sharded step (GLB_XCHG_MC=pusher): a kernel on a stream of its own beside the SpMV kernels
+    cudaStream_t pusher_stream = nullptr;
+    cudaEvent_t pusher_ev_fork = nullptr, pusher_ev_done = nullptr;
+    int pusher_smem_set[3] = {-1, -1, -1};
     // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]
@@ -132,7 +136,12 @@ struct glb_csr_s {
     // lists whose rows lie in each sub-block
     std::vector<uint32_t> sub_chunk, sub_row, sub_fs, sub_fl, sub_em;
     // progressive push of a row-sharded run over a multicast exchange (spmv.cu: push_block_when_complete)
-    uint32_t *push_bits = nullptr, *push_lo = nullptr, *push_count = nullptr;
+    uint32_t *push_bits = nullptr, *push_lo = nullptr, *push_count = nullptr;  // push_count[n_push_blocks] counts fix-up CTAs
+    uint32_t n_push_blocks = 0;
+    // pusher CTAs (spmv.cu: xchg_pusher_kernel): fix-up rows inside one push block / across blocks, per-block ranges
+    glb_fixup_t *fix_in = nullptr, *fix_def = nullptr;
+    uint32_t *blk_fs = nullptr, *blk_em = nullptr, *pusher_bits = nullptr;
+    uint32_t n_fix_def = 0;
     // scratch vectors for glb_spmv_host
     float *dx = nullptr, *dmask = nullptr, *dy = nullptr;
     float *dx2 = nullptr, *dmask2 = nullptr, *dy2 = nullptr;  // second slot of glb_spmv_host_batch
@@ -207,6 +216,7 @@ void glb_ctx_release(glb_ctx_t ctx);  // child destroyed; frees the context if i
 struct GlbSpmvMc {
     float *y_mc;
     bool progressive;
+    bool pusher;  // the kernels only COUNT finished CTAs per push block / fix-up CTAs; glb_launch_pusher's CTAs send the rows
     uint32_t *pub_flags_mc, *pub_state;
     int rank;
 };
@@ -221,5 +231,11 @@ struct GlbSpmvSplit {
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
                     const GlbXchgWait *wait, bool *published, int val_type, const GlbSpmvSplit *split);
+
+// The pusher kernel of one row-sharded step (spmv.cu): launched on ctx->pusher_stream BEFORE the step's SpMV kernels.
+int glb_xchg_preload();  // loads the exchange kernels (see glb_launch_pusher)
+bool glb_pusher_applies(glb_csr_t m, const float *y, const float *y_mc);
+int glb_launch_pusher(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *mask, float *y,
+                      const glb_spmv_epilogue_t *ep, float *y_mc, uint32_t *mc_flags, uint32_t *state, int rank);
 
 #endif  // GLB_INTERNAL_H_

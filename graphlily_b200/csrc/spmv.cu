@@ -88,6 +88,10 @@ struct SpmvParams {
     uint32_t *push_count;       // CTAs finished per push block (self-resetting)
     uint32_t push_row_base;
     uint32_t n_ctas;
+    // Pusher CTAs (GLB_XCHG_MC=pusher): the main kernel only counts finished CTAs per push block;
+    // xchg_pusher_kernel, resident beside it on SMs of its own, finishes the chunk-crossing / empty rows of every
+    // completed block, sends the block and finally publishes (no fix-up launch).
+    int push_count_only;
     uint32_t *pub_flags_mc;     // fix-up kernel: multicast mapping of the flag words (NULL: do not publish)
     uint32_t *pub_state;        // exchange state: [0] epoch, [1] CTA ticket
     int pub_rank;
@@ -326,9 +330,16 @@ __device__ __forceinline__ void push_block_when_complete(const SpmvParams &P) {
     if (threadIdx.x == 0) {
         const uint32_t first = blk * kPushCtas;
         const uint32_t in_block = P.n_ctas - first < kPushCtas ? P.n_ctas - first : kPushCtas;
-        __threadfence();
-        s_last = atomicAdd(P.push_count + blk, 1u) == in_block - 1;
+        if (P.push_count_only) {
+            // release at GPU scope, cumulative over the barrier above; no value needed.  (__threadfence + atomicAdd here --
+            // a MEMBAR.SC in every CTA's exit -- stretched the main kernel from 186 to 205 us on half of C2)
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.push_count + blk) : "memory");
+        } else {
+            __threadfence();
+            s_last = atomicAdd(P.push_count + blk, 1u) == in_block - 1;
+        }
     }
+    if (P.push_count_only) return;  // uniform: the pusher CTAs watch the counter
     __syncthreads();
     if (!s_last) return;
     __threadfence();  // the other CTAs' rows (counted above) are visible from here on
@@ -526,6 +537,175 @@ __global__ void __launch_bounds__(kThreads) spmv_fixup_kernel(const SpmvParams P
     }
 }
 
+// Pusher CTAs of a row-sharded step over a multicast exchange (GLB_XCHG_MC=pusher).  A handful of CTAs, each holding
+// an SM to itself (its shared-memory request leaves no room for a compute CTA), resident from the start of the step:
+// remote stores issued from SMs that ALSO run compute CTAs hold up those SMs' L1 request port -- the unit that bounds
+// the SpMV -- so the stores come from SMs that do nothing else.  CTA g watches push blocks g, g + G, ...: when all
+// kPushCtas main-kernel CTAs of a block have counted themselves done it
+//   1. finishes the block's chunk-crossing rows whose chunks all lie inside the block, and its empty rows (what the
+//      fix-up kernel does otherwise: there is NO fix-up launch in this mode),
+//   2. copies the block's rows to the multicast address in 16-byte multimem.st stores (the switch replicates them
+//      into every rank's x) while the later blocks still compute.
+// Once every block is out, the few rows that cross a block boundary (and the hub rows spanning > 32 chunks) are
+// finished and sent as scalars, every CTA fences its stores system-wide and the last one publishes the step's epoch.
+// Measured (2 GPUs, C2): a scalar multicast store costs an SM ~4 ns, so rows must travel in 16-byte pieces -- leaving
+// all chunk-crossing rows (1 in 43) to a later scalar pass cost 60 us per step.
+struct PusherParams {
+    float *y_mc;
+    const uint32_t *push_bits, *push_lo;  // bit clear = the row is sent late (crosses a block boundary / hub row)
+    uint32_t *push_count, *pusher_done;
+    const glb_fixup_t *fix_in, *fix_def;  // chunk-crossing rows inside one block (grouped by block) / across blocks
+    const uint32_t *blk_fs, *blk_em;      // per block: range of fix_in / of empty_rows
+    uint32_t n_fix_def;
+    uint32_t push_row_base, n_blocks, n_ctas;
+    uint32_t *mc_flags, *state;
+    int rank;
+    int debug;                  // GLB_XCHG_PUSHER_DEBUG=1: no data stores (timing experiment, results are WRONG)
+    unsigned long long *trace;  // GLB_XCHG_TRACE: [0] start [1] all blocks out [2] late rows fenced [3] published [4+2b] block b ready [5+2b] sent
+};
+constexpr uint32_t kPusherThreads = 1024;
+
+__device__ __forceinline__ unsigned long long glb_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void pusher_spin(const uint32_t *counter, uint32_t want, uint32_t *err) {
+    const long long t0 = clock64();
+    uint32_t seen;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        if (seen >= want) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll) {  // ~10 s: the SpMV kernels of this step never ran (see glb_xchg_spin)
+            *err = 1;
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+// One chunk-crossing row, one thread (carries read around L1: the main kernel wrote them during THIS kernel's life).
+template <int OP>
+__device__ __forceinline__ void pusher_fix_short(const SpmvParams &P, const glb_fixup_t e) {
+    const uint32_t c_end = e.c_end & ~GLB_FLAG;
+    const bool has_head = (e.c_end & GLB_FLAG) != 0;
+    const uint32_t c_stop = has_head ? c_end : c_end + 1;
+    float t = Semi<OP>::ident();
+    for (uint32_t c = e.c_begin; c < c_stop; ++c) t = Semi<OP>::add(t, __ldcg(P.tail_carry + c));
+    if (has_head) t = Semi<OP>::add(t, __ldcg(P.head_carry + c_end));
+    finish_row<OP, false>(P, e.row, t);
+}
+
+__device__ __forceinline__ void pusher_send_row(const SpmvParams &P, const PusherParams &Q, uint32_t row) {
+    const float v = *reinterpret_cast<volatile const float *>(P.y + row);  // this thread stored it just now
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(Q.y_mc + row), "f"(v) : "memory");
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kPusherThreads, 1) xchg_pusher_kernel(const SpmvParams P, const PusherParams Q) {
+    constexpr int U = 4;  // 16-byte loads in flight per thread before the first store
+    if (Q.trace && blockIdx.x == 0 && threadIdx.x == 0) Q.trace[0] = glb_now_ns();
+    for (uint32_t blk = blockIdx.x; blk < Q.n_blocks; blk += gridDim.x) {
+        if (threadIdx.x == 0) {
+            const uint32_t first = blk * kPushCtas;
+            pusher_spin(Q.push_count + blk, Q.n_ctas - first < kPushCtas ? Q.n_ctas - first : kPushCtas, Q.state + 2);
+            Q.push_count[blk] = 0;  // ready for the next step (which starts after this kernel)
+            if (Q.trace) Q.trace[4 + 2 * blk] = glb_now_ns();
+        }
+        __syncthreads();
+        for (uint32_t i = Q.blk_fs[blk] + threadIdx.x; i < Q.blk_fs[blk + 1]; i += kPusherThreads) pusher_fix_short<OP>(P, Q.fix_in[i]);
+        for (uint32_t i = Q.blk_em[blk] + threadIdx.x; i < Q.blk_em[blk + 1]; i += kPusherThreads)
+            finish_row<OP, false>(P, P.empty_rows[i], Semi<OP>::ident());
+        __syncthreads();  // the block's rows are final (the loads below go to L2, where those stores are)
+        const uint32_t lo = Q.push_lo[blk], hi = Q.push_lo[blk + 1];
+        for (uint32_t base = lo & ~3u; base < hi; base += 4u * kPusherThreads * U) {
+            float4 v[U];
+            uint32_t bits[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t r0 = base + 4u * (threadIdx.x + u * kPusherThreads);
+                bits[u] = 0;
+                if (r0 < hi) {
+                    const uint32_t rel = r0 - Q.push_row_base;
+                    bits[u] = (__ldg(Q.push_bits + (rel >> 5)) >> (rel & 31u)) & 0xfu;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (r0 + i < lo || r0 + i >= hi) bits[u] &= ~(1u << i);
+                    if (bits[u]) v[u] = __ldcg(reinterpret_cast<const float4 *>(P.y + r0));  // (exchange vectors are padded to 16 bytes)
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t r0 = base + 4u * (threadIdx.x + u * kPusherThreads);
+                if (Q.debug) {
+                    if (bits[u] && v[u].x == 1234.5f) Q.trace[0] = 0;  // keep the loads
+                } else if (bits[u] == 0xfu) {
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(Q.y_mc + r0), "f"(v[u].x),
+                                 "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                                 : "memory");
+                } else if (bits[u]) {
+                    const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (bits[u] & (1u << i))
+                            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(Q.y_mc + r0 + i), "f"(e[i]) : "memory");
+                }
+            }
+        }
+        if (Q.trace) {
+            __syncthreads();
+            if (threadIdx.x == 0) Q.trace[5 + 2 * blk] = glb_now_ns();
+        }
+    }
+    // every block complete (each pusher CTA has seen all of its blocks): the rows that cross block boundaries
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(Q.pusher_done, 1u);
+        pusher_spin(Q.pusher_done, gridDim.x, Q.state + 2);
+        if (Q.trace && blockIdx.x == 0) Q.trace[1] = glb_now_ns();
+    }
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kPusherThreads + threadIdx.x; i < Q.n_fix_def; i += gridDim.x * kPusherThreads) {
+        const glb_fixup_t e = Q.fix_def[i];
+        pusher_fix_short<OP>(P, e);
+        pusher_send_row(P, Q, e.row);
+    }
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        const uint32_t n_warps = gridDim.x * (kPusherThreads / 32);
+        for (uint32_t i = blockIdx.x * (kPusherThreads / 32) + (threadIdx.x >> 5); i < P.n_fix_long; i += n_warps) {  // warp-uniform
+            const glb_fixup_t e = P.fix_long[i];
+            const uint32_t c_end = e.c_end & ~GLB_FLAG;
+            const bool has_head = (e.c_end & GLB_FLAG) != 0;
+            const uint32_t c_stop = has_head ? c_end : c_end + 1;
+            float t = Semi<OP>::ident();
+            for (uint32_t c = e.c_begin + lane; c < c_stop; c += 32) t = Semi<OP>::add(t, __ldcg(P.tail_carry + c));
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) t = Semi<OP>::add(t, __shfl_xor_sync(kFull, t, d));
+            if (lane == 0) {
+                if (has_head) t = Semi<OP>::add(t, __ldcg(P.head_carry + c_end));
+                finish_row<OP, false>(P, e.row, t);
+                pusher_send_row(P, Q, e.row);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (Q.trace && blockIdx.x == 0 && threadIdx.x == 0) Q.trace[2] = glb_now_ns();
+    if (threadIdx.x == 0 && atomicAdd(Q.state + 1, 1u) == gridDim.x - 1) {
+        Q.state[1] = 0;
+        *Q.pusher_done = 0;
+        const uint32_t epoch = Q.state[0] + 1;
+        Q.state[0] = epoch;
+        // (release: ordered after this CTA's fence above and, through the ticket, after every other CTA's)
+        asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(Q.mc_flags + Q.rank), "r"(epoch) : "memory");
+        if (Q.trace) Q.trace[3] = glb_now_ns();
+    }
+}
+
 constexpr int kLaunchMain = 1, kLaunchFixup = 2;
 
 // `st`: the stream of this launch (the context's, or a sub-block stream of a split step); `which`: main kernel,
@@ -710,6 +890,138 @@ static int launch_split(glb_ctx_t ctx, glb_csr_t m, int op, int val_type, const 
     return GLB_OK;
 }
 
+bool glb_pusher_applies(glb_csr_t m, const float *y, const float *y_mc) {
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y_mc)) & 15u) == 0;
+    return m->pusher_bits && m->n_chunks && !m->tile_threads && aligned16;
+}
+
+// Fork: the pusher kernel starts with the step (its CTAs are resident before the main kernel fills the machine);
+// the caller joins ctx->pusher_ev_done into ctx->stream after the step's SpMV kernels.
+//   GLB_XCHG_PUSHERS=<n>         pusher CTAs (default 4)
+//   GLB_XCHG_PUSHER_SMEM_KB=<n>  shared memory each one requests (default 227 = the whole SM; 0: share the SM with compute CTAs)
+template <int OP>
+static int launch_pusher_op(glb_ctx_t ctx, const SpmvParams &P, const PusherParams &Q, uint32_t grid, int smem) {
+    if (ctx->pusher_smem_set[OP] != smem) {
+        GLB_CUDA(cudaFuncSetAttribute(xchg_pusher_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (smem) GLB_CUDA(cudaFuncSetAttribute(xchg_pusher_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->pusher_smem_set[OP] = smem;
+    }
+    xchg_pusher_kernel<OP><<<grid, kPusherThreads, smem, ctx->pusher_stream>>>(P, Q);
+    GLB_CUDA(cudaGetLastError());
+    return GLB_OK;
+}
+
+int glb_launch_pusher(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *mask, float *y,
+                      const glb_spmv_epilogue_t *ep, float *y_mc, uint32_t *mc_flags, uint32_t *state, int rank) {
+    auto env_u = [](const char *name, unsigned dflt) { const char *v = getenv(name); return v && *v ? unsigned(strtoul(v, nullptr, 10)) : dflt; };
+    static const uint32_t n_pushers = std::max(1u, std::min(32u, env_u("GLB_XCHG_PUSHERS", 4)));
+    static const int smem = int(std::min(227u, env_u("GLB_XCHG_PUSHER_SMEM_KB", 227))) * 1024;
+    if (!ctx->pusher_stream) {
+        // CUDA loads kernels lazily, and loading one can wait for running kernels to finish: a pusher kernel spinning on
+        // counters of an SpMV kernel that is still to be LOADED would never see them move.  Load everything a step can
+        // launch before the first pusher goes out.
+        cudaFuncAttributes fa;
+#define GLB_PRELOAD(k) GLB_CUDA(cudaFuncGetAttributes(&fa, k))
+#define GLB_PRELOAD_OP(OP)                                           \
+        GLB_PRELOAD((spmv_lane_kernel<OP, false, GLB_VAL_F32>));     \
+        GLB_PRELOAD((spmv_lane_kernel<OP, true, GLB_VAL_F32>));      \
+        GLB_PRELOAD((spmv_fixup_kernel<OP, GLB_VAL_F32>));           \
+        GLB_PRELOAD(xchg_pusher_kernel<OP>)
+        GLB_PRELOAD_OP(GLB_OP_MUL_ADD);
+        GLB_PRELOAD_OP(GLB_OP_LOGICAL_AND_OR);
+        GLB_PRELOAD_OP(GLB_OP_ADD_MIN);
+        GLB_PRELOAD((spmv_lane_bits_kernel<1, false>));
+        GLB_PRELOAD((spmv_lane_bits_kernel<1, true>));
+        GLB_PRELOAD((spmv_lane_bits_kernel<2, false>));
+        GLB_PRELOAD((spmv_lane_bits_kernel<2, true>));
+        GLB_PRELOAD(gather_hot_kernel);
+        GLB_PRELOAD(pack_bits_kernel);
+#undef GLB_PRELOAD_OP
+#undef GLB_PRELOAD
+        int rc = glb_xchg_preload();
+        if (rc) return rc;
+        int prio_least = 0, prio_greatest = 0;
+        GLB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        GLB_CUDA(cudaStreamCreateWithPriority(&ctx->pusher_stream, cudaStreamNonBlocking, prio_greatest));
+        GLB_CUDA(cudaEventCreateWithFlags(&ctx->pusher_ev_fork, cudaEventDisableTiming));
+        GLB_CUDA(cudaEventCreateWithFlags(&ctx->pusher_ev_done, cudaEventDisableTiming));
+    }
+    SpmvParams P;  // what finish_row and the fix-ups read
+    memset(&P, 0, sizeof(P));
+    P.y = y;
+    P.mask = mask;
+    P.zero = zero;
+    P.mask_type = mask_type;
+    if (ep) {
+        P.add_enable = ep->add_enable;
+        P.add_val = ep->add_val;
+        P.assign_inout = ep->assign_inout;
+        P.assign_val = ep->assign_val;
+        P.assign_mask_type = ep->assign_mask_type;
+    }
+    P.head_carry = m->head_carry;
+    P.tail_carry = m->tail_carry;
+    P.empty_rows = m->empty_rows;
+    P.fix_long = m->fix_long;
+    P.n_fix_long = m->n_fix_long;
+    PusherParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.y_mc = y_mc;
+    Q.push_bits = m->pusher_bits;
+    Q.push_lo = m->push_lo;
+    Q.push_count = m->push_count;
+    Q.pusher_done = m->push_count + m->n_push_blocks;
+    Q.fix_in = m->fix_in;
+    Q.fix_def = m->fix_def;
+    Q.blk_fs = m->blk_fs;
+    Q.blk_em = m->blk_em;
+    Q.n_fix_def = m->n_fix_def;
+    Q.push_row_base = m->row_begin & ~31u;
+    Q.n_blocks = m->n_push_blocks;
+    Q.n_ctas = (m->n_chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    Q.mc_flags = mc_flags;
+    Q.state = state;
+    Q.rank = rank;
+    static const int debug = int(env_u("GLB_XCHG_PUSHER_DEBUG", 0));
+    Q.debug = debug;
+    // GLB_XCHG_TRACE=<n>: timeline of the n-th pusher launch of the process (eager launches only), printed at the next one
+    static const long trace_at = getenv("GLB_XCHG_TRACE") ? atol(getenv("GLB_XCHG_TRACE")) : -1;
+    static long call_no = 0;
+    static unsigned long long *d_trace = nullptr;
+    if (trace_at >= 0) {
+        const size_t n_stamps = 4 + 2 * size_t(m->n_push_blocks);
+        if (call_no == trace_at) {
+            GLB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_trace), n_stamps * sizeof(unsigned long long)));
+            GLB_CUDA(cudaMemset(d_trace, 0, n_stamps * sizeof(unsigned long long)));
+            Q.trace = d_trace;
+        } else if (call_no == trace_at + 1 && d_trace) {
+            std::vector<unsigned long long> t(n_stamps);
+            GLB_CUDA(cudaDeviceSynchronize());
+            GLB_CUDA(cudaMemcpy(t.data(), d_trace, n_stamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            auto us = [&](size_t i) { return t[i] ? double(static_cast<long long>(t[i] - t[0])) * 1e-3 : -1.0; };
+            fprintf(stderr, "[glb pusher rank %d] %u blocks; all blocks out +%.1f us, late rows fenced +%.1f us, published +%.1f us\n", rank,
+                    m->n_push_blocks, us(1), us(2), us(3));
+            for (uint32_t b = 0; b < m->n_push_blocks; b += std::max(1u, m->n_push_blocks / 16))
+                fprintf(stderr, "[glb pusher rank %d]   block %u ready +%.1f us, sent +%.1f us\n", rank, b, us(4 + 2 * b), us(5 + 2 * b));
+            const uint32_t lastb = m->n_push_blocks - 1;
+            fprintf(stderr, "[glb pusher rank %d]   block %u ready +%.1f us, sent +%.1f us\n", rank, lastb, us(4 + 2 * lastb), us(5 + 2 * lastb));
+        }
+        ++call_no;
+    }
+    GLB_CUDA(cudaEventRecord(ctx->pusher_ev_fork, ctx->stream));
+    GLB_CUDA(cudaStreamWaitEvent(ctx->pusher_stream, ctx->pusher_ev_fork, 0));
+    const uint32_t grid = std::min(n_pushers, std::max(1u, m->n_push_blocks));
+    int rc = GLB_EINVAL;
+    switch (op) {
+        case GLB_OP_MUL_ADD: rc = launch_pusher_op<GLB_OP_MUL_ADD>(ctx, P, Q, grid, smem); break;
+        case GLB_OP_LOGICAL_AND_OR: rc = launch_pusher_op<GLB_OP_LOGICAL_AND_OR>(ctx, P, Q, grid, smem); break;
+        case GLB_OP_ADD_MIN: rc = launch_pusher_op<GLB_OP_ADD_MIN>(ctx, P, Q, grid, smem); break;
+    }
+    if (rc) return rc;
+    GLB_CUDA(cudaEventRecord(ctx->pusher_ev_done, ctx->pusher_stream));
+    return GLB_OK;
+}
+
 int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_type, const float *x, const float *mask,
                     float *y, const glb_spmv_epilogue_t *ep, float *const *y_peers, int n_peers, const GlbSpmvMc *mc,
                     const GlbXchgWait *wait, bool *published, int val_type, const GlbSpmvSplit *split) {
@@ -726,6 +1038,13 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
         P.pub_flags_mc = mc->pub_flags_mc;
         P.pub_state = mc->pub_state;
         P.pub_rank = mc->rank;
+    } else if (mc && mc->pusher) {  // (the caller checked glb_pusher_applies and launched the pusher kernel)
+        P.push_bits = m->push_bits;
+        P.push_lo = m->push_lo;
+        P.push_count = m->push_count;
+        P.push_row_base = m->row_begin & ~31u;
+        P.push_count_only = 1;
+        y_mc = nullptr;  // no kernel of this launch stores to the multicast address
     } else if (mc) {
         P.mc_rows_in_main = 1;
     }
@@ -786,6 +1105,7 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
     P.n_nz_rows = m->n_nz_rows;
+    if (P.push_count_only) return dispatch_op(ctx, m, op, val_type, P, published, ctx->stream, kLaunchMain);  // the pusher CTAs do the fix-ups
     if (!split) return dispatch_op(ctx, m, op, val_type, P, published, ctx->stream, kLaunchMain | kLaunchFixup);
     return launch_split(ctx, m, op, val_type, P, *split);
 }
@@ -1117,7 +1437,37 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
         lo[0] = row_begin;
         rc = upload(ctx, &m->push_bits, bits.data(), bits.size(), bits.size(), &bytes);
         if (!rc) rc = upload(ctx, &m->push_lo, lo.data(), lo.size(), lo.size(), &bytes);
-        if (!rc) rc = upload<uint32_t>(ctx, &m->push_count, nullptr, 0, n_blocks, &bytes);
+        if (!rc) rc = upload<uint32_t>(ctx, &m->push_count, nullptr, 0, n_blocks + 1, &bytes);
+        m->n_push_blocks = n_blocks;
+        // pusher CTAs (xchg_pusher_kernel): chunk-crossing rows whose chunks lie inside ONE push block are finished by the
+        // CTA that sends the block (fix_in, grouped by block); the ones across block boundaries and the hub rows follow at
+        // the end of the step (fix_def, fix_long: their bits are clear in pusher_bits); empty rows go with their block
+        const uint32_t chunks_per_block = kPushCtas * kWarpsPerBlock;
+        std::vector<glb_fixup_t> fix_in, fix_def;
+        std::vector<uint32_t> blk_fs(n_blocks + 1, 0), blk_em(n_blocks + 1, 0);
+        std::vector<uint32_t> pbits((size_t(row_end - base) + 31) / 32 + 1, 0u);
+        for (uint32_t r = row_begin; r < row_end; ++r) pbits[(r - base) >> 5] |= 1u << ((r - base) & 31u);
+        for (const auto &e : L.fix_short) {
+            const uint32_t b0 = e.c_begin / chunks_per_block, b1 = (e.c_end & ~GLB_FLAG) / chunks_per_block;
+            if (b0 == b1) {
+                fix_in.push_back(e);
+                blk_fs[b0 + 1]++;
+            } else {
+                fix_def.push_back(e);
+                pbits[(e.row - base) >> 5] &= ~(1u << ((e.row - base) & 31u));
+            }
+        }
+        for (const auto &e : L.fix_long) pbits[(e.row - base) >> 5] &= ~(1u << ((e.row - base) & 31u));
+        for (uint32_t j = 0; j < n_blocks; ++j) blk_fs[j + 1] += blk_fs[j];
+        for (uint32_t j = 0; j <= n_blocks; ++j)
+            blk_em[j] = uint32_t(std::lower_bound(L.empty_rows.begin(), L.empty_rows.end(), lo[j]) - L.empty_rows.begin());
+        blk_em[0] = 0;
+        m->n_fix_def = uint32_t(fix_def.size());
+        if (!rc) rc = upload(ctx, &m->fix_in, fix_in.data(), fix_in.size(), fix_in.size(), &bytes);
+        if (!rc) rc = upload(ctx, &m->fix_def, fix_def.data(), fix_def.size(), fix_def.size(), &bytes);
+        if (!rc) rc = upload(ctx, &m->blk_fs, blk_fs.data(), blk_fs.size(), blk_fs.size(), &bytes);
+        if (!rc) rc = upload(ctx, &m->blk_em, blk_em.data(), blk_em.size(), blk_em.size(), &bytes);
+        if (!rc) rc = upload(ctx, &m->pusher_bits, pbits.data(), pbits.size(), pbits.size(), &bytes);
     }
     {
         // sub-blocks of a split step (GLB_XCHG_SPLIT=<1..8>, default 4): chunk boundaries on CTA multiples, the row
@@ -1165,6 +1515,7 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
     cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits);
     cudaFree(m->push_bits); cudaFree(m->push_lo); cudaFree(m->push_count);
+    cudaFree(m->fix_in); cudaFree(m->fix_def); cudaFree(m->blk_fs); cudaFree(m->blk_em); cudaFree(m->pusher_bits);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
     cudaFree(m->dx2); cudaFree(m->dmask2); cudaFree(m->dy2);
     glb_ctx_release(m->ctx);
@@ -1244,7 +1595,7 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
     GLB_REQUIRE(n_steps >= 0, "negative step count");
     static const int forced = [] {
         const char *v = getenv("GLB_XCHG_MC");
-        return !v ? 1 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : !strcmp(v, "progressive") ? 3 : !strcmp(v, "copy") ? 4 : 1;
+        return !v ? 1 : !strcmp(v, "kernel") ? 1 : !strcmp(v, "fused") ? 2 : !strcmp(v, "progressive") ? 3 : !strcmp(v, "copy") ? 4 : !strcmp(v, "pusher") ? 5 : 1;
     }();
     const GlbXchgWait wait = glb_xchg_wait_desc(xc);
     float *peers[GLB_MAX_PEERS];
@@ -1258,7 +1609,8 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         if (rc) return rc;
         const GlbXchgWait *w = k > 0 ? &wait : nullptr;
         // (per-kernel timing and the tile variant take the plain sequence)
-        const int mode = (forced == 4 && (ctx->timing || m->tile_threads)) ? 1 : forced;
+        int mode = (forced == 4 && (ctx->timing || m->tile_threads)) ? 1 : forced;
+        if (mode == 5 && (ctx->timing || !xc->mc || !glb_pusher_applies(m, y, xc->mc + size_t(dv) * xc->n))) mode = 1;
         if (xc->nranks > 1 && mode == 4) {
             // GLB_XCHG_MC=copy: split step -- sub-blocks of the shard on streams of their own, their finished rows
             // copied to the peers by the copy engines while later sub-blocks compute, then one publishing kernel
@@ -1274,6 +1626,15 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
             } else if (!rc) {
                 rc = glb_xchg_signal(ctx, xc, false);
             }
+        } else if (xc->mc && xc->nranks > 1 && mode == 5) {
+            // GLB_XCHG_MC=pusher: a few CTAs on SMs of their own finish and send every completed block of rows while
+            // the later blocks compute, and publish (xchg_pusher_kernel; no fix-up launch)
+            rc = glb_launch_pusher(ctx, m, op, zero, mask_type, mask, y, ep, xc->mc + size_t(dv) * xc->n, xc->mc_flags, xc->d_state, xc->rank);
+            GlbSpmvMc mc;
+            memset(&mc, 0, sizeof(mc));
+            mc.pusher = true;
+            if (!rc) rc = glb_launch_spmv(ctx, m, op, zero, mask_type, x, mask, y, ep, nullptr, 0, &mc, w, nullptr, GLB_VAL_F32, nullptr);
+            if (!rc) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pusher_ev_done, 0));
         } else if (xc->mc && xc->nranks > 1 && mode == 1) {
             // default: one push kernel after the SpMV kernels (all SMs store the finished slice in 16-byte
             // multimem.st; its last CTA publishes)
