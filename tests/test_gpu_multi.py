@@ -27,6 +27,9 @@ def _worker(rank, world, port, kind):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
+    if kind == "multicast-pusher":   # the slice leaves through pusher CTAs beside the SpMV kernels (GLB_XCHG_MC=pusher)
+        os.environ["GLB_XCHG_MC"] = "pusher"
+        kind = "multicast"
     if kind == "multicast":   # torch symmetric memory rendezvous runs over the default (NCCL) group
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     else:
@@ -150,7 +153,7 @@ def _worker(rank, world, port, kind):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["peer", "multicast"])
+@pytest.mark.parametrize("kind", ["peer", "multicast", "multicast-pusher"])
 def test_exchange_and_apps_on_two_gpus(kind):
     from graphlily_b200 import capi
     if capi.device_count() < 2:
