@@ -132,6 +132,9 @@ SIGNATURES = {
     "glb_xchg_block_bytes": (C.c_size_t, [C.c_uint32, C.c_int]),
     "glb_xchg_adopt": (C.c_int, [_vp, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp)]),
     "glb_xchg_has_multicast": (C.c_int, [_vp]),
+    "glb_xchg_mc_supported": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "glb_xchg_mc_open": (C.c_int, [_vp, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int)]),
+    "glb_xchg_mc_bind": (C.c_int, [_vp]),
     "glb_xchg_vector": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "glb_xchg_allgather": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_size_t]),
     "glb_xchg_barrier": (C.c_int, [_vp, _vp]),
@@ -467,6 +470,49 @@ class Exchange:
         check(lib.glb_xchg_adopt(ctx.handle, int(n_floats), n_vectors, rank, nranks, arr,
                                  _vp(int(multicast_ptr)) if multicast_ptr else None, C.byref(h)))
         self.handle = h
+        return self
+
+    @classmethod
+    def open_multicast(cls, ctx, n_floats, rank, nranks, share_fd, agree, n_vectors=2):
+        """Exchange over an NVSwitch multicast object the LIBRARY creates (glb_xchg_mc_open / _bind; no framework maps
+        anything).  Collective.  ``share_fd(fd)``: rank 0 passes the multicast object's file descriptor, every rank gets
+        back a descriptor valid in its own process (rank 0: the same one); ``agree(ok) -> bool``: logical AND over the
+        ranks (doubles as the barrier between the steps).  Returns None (on every rank) when any step failed anywhere."""
+        self = cls.__new__(cls)
+        self.ctx, self.handle, self.n, self.rank, self.nranks = ctx, None, int(n_floats), rank, nranks
+        self.n_vectors, self._keep, self.error = n_vectors, None, None
+        sup = C.c_int(0)
+        if not agree(lib.glb_xchg_mc_supported(ctx.handle, C.byref(sup)) == 0 and sup.value != 0):
+            return None
+        h, fd = _vp(), C.c_int(-1)
+
+        def attempt(call):
+            try:
+                check(call())
+                return True
+            except GlbError as e:
+                self.error = e
+                return False
+        ok = True
+        if rank == 0:
+            ok = attempt(lambda: lib.glb_xchg_mc_open(ctx.handle, int(n_floats), n_vectors, 0, nranks, -1, C.byref(h), C.byref(fd)))
+        if not agree(ok):
+            return None
+        got = share_fd(fd.value if rank == 0 else None)
+        if rank != 0:
+            ok = got is not None and got >= 0 and attempt(
+                lambda: lib.glb_xchg_mc_open(ctx.handle, int(n_floats), n_vectors, rank, nranks, got, C.byref(h), None))
+        if got is not None and got >= 0:
+            os.close(got)   # the driver holds its own reference to the object
+        if ok:
+            self.handle = h
+        if not agree(ok):   # (also the barrier: every rank has added its device)
+            self.close()
+            return None
+        ok = attempt(lambda: lib.glb_xchg_mc_bind(self.handle))
+        if not agree(ok):
+            self.close()
+            return None
         return self
 
     @staticmethod

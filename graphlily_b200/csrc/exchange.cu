@@ -13,7 +13,9 @@
 // the kernel that opens the next SpMV (glb_xchg_wait_head, exchange.cuh).  The epoch lives in
 // device memory and is advanced by the publishing kernel, so a recorded launch sequence (CUDA
 // graph) of many steps replays correctly.
+#include <cuda.h>  // driver API TYPES only: the entry points are resolved at run time (cudaGetDriverEntryPoint)
 #include <string.h>
+#include <unistd.h>
 
 #include "exchange.cuh"
 #include "glb_internal.h"
@@ -223,6 +225,253 @@ int glb_xchg_connect(glb_xchg_t xc, int rank, int nranks, const void *handles) {
     return GLB_OK;
 }
 
+// ---- multicast exchange created through the C ABI ------------------------------------------------
+// NVSwitch multicast object + this rank's block + both mappings, made with the driver's virtual-memory API
+// (cuMulticastCreate / cuMulticastAddDevice / cuMemCreate / cuMulticastBindMem / cuMemMap) -- what
+// graphlily_b200/exchange.py otherwise asks torch's symmetric memory for.  The driver entry points are looked up
+// at run time, so the library still loads (and links) on a host without libcuda.
+//   rank 0:   glb_xchg_mc_open(..., fd_in = -1, &xc, &fd_out)  creates the object; fd_out is its POSIX file descriptor,
+//             which the host passes to the other ranks' processes (SCM_RIGHTS over a Unix socket, pidfd_getfd, ...)
+//   rank r:   glb_xchg_mc_open(..., fd_in = <that descriptor in THIS process>, &xc, NULL)
+//   -- host barrier: every rank has added its device --
+//   all:      glb_xchg_mc_bind(xc)   allocates + binds + maps; the exchange is then connected (multicast only: peers'
+//             blocks are not mapped one by one, every transfer goes through the switch)
+//   -- host barrier before the first use --
+namespace {
+
+struct DriverApi {
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle *, const CUmulticastObjectProp *) = nullptr;
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+    CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+    CUresult (*MulticastGetGranularity)(size_t *, const CUmulticastObjectProp *, CUmulticastGranularity_flags) = nullptr;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+    CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*DeviceGetAttribute)(int *, CUdevice_attribute, CUdevice) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    bool ok = false;
+};
+
+const DriverApi &driver_api() {
+    static const DriverApi api = [] {
+        DriverApi a;
+        bool ok = true;
+        auto get = [&](const char *name, void *slot) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+                cudaGetLastError();
+                ok = false;
+            }
+            memcpy(slot, &fn, sizeof(fn));
+        };
+        get("cuMulticastCreate", &a.MulticastCreate);
+        get("cuMulticastAddDevice", &a.MulticastAddDevice);
+        get("cuMulticastBindMem", &a.MulticastBindMem);
+        get("cuMulticastUnbind", &a.MulticastUnbind);
+        get("cuMulticastGetGranularity", &a.MulticastGetGranularity);
+        get("cuMemCreate", &a.MemCreate);
+        get("cuMemRelease", &a.MemRelease);
+        get("cuMemGetAllocationGranularity", &a.MemGetAllocationGranularity);
+        get("cuMemAddressReserve", &a.MemAddressReserve);
+        get("cuMemAddressFree", &a.MemAddressFree);
+        get("cuMemMap", &a.MemMap);
+        get("cuMemUnmap", &a.MemUnmap);
+        get("cuMemSetAccess", &a.MemSetAccess);
+        get("cuMemExportToShareableHandle", &a.MemExportToShareableHandle);
+        get("cuMemImportFromShareableHandle", &a.MemImportFromShareableHandle);
+        get("cuDeviceGet", &a.DeviceGet);
+        get("cuDeviceGetAttribute", &a.DeviceGetAttribute);
+        get("cuGetErrorString", &a.GetErrorString);
+        a.ok = ok;
+        return a;
+    }();
+    return api;
+}
+
+#define GLB_CU(call)                                                                  \
+    do {                                                                              \
+        const CUresult glb_cu_ = (call);                                              \
+        if (glb_cu_ != CUDA_SUCCESS) {                                                \
+            const char *msg_ = nullptr;                                               \
+            if (D.GetErrorString) D.GetErrorString(glb_cu_, &msg_);                   \
+            glb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, msg_ ? msg_ : "driver error"); \
+            return GLB_ECUDA;                                                         \
+        }                                                                             \
+    } while (0)
+
+CUmulticastObjectProp mc_prop(int nranks, size_t size) {
+    CUmulticastObjectProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.numDevices = unsigned(nranks);
+    prop.size = size;
+    prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+CUmemAllocationProp mc_alloc_prop(int device) {
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return ap;
+}
+
+void mc_release(glb_xchg_t xc) {
+    const DriverApi &D = driver_api();
+    if (!D.ok) return;
+    if (xc->mc) { D.MemUnmap(CUdeviceptr(reinterpret_cast<uintptr_t>(xc->mc)), xc->mc_size); D.MemAddressFree(CUdeviceptr(reinterpret_cast<uintptr_t>(xc->mc)), xc->mc_size); }
+    if (xc->local) { D.MemUnmap(CUdeviceptr(reinterpret_cast<uintptr_t>(xc->local)), xc->mc_size); D.MemAddressFree(CUdeviceptr(reinterpret_cast<uintptr_t>(xc->local)), xc->mc_size); }
+    if (xc->mc_bound) {
+        CUdevice dev;
+        if (D.DeviceGet(&dev, xc->ctx->device) == CUDA_SUCCESS) D.MulticastUnbind(xc->mc_handle, dev, 0, xc->mc_size);
+    }
+    if (xc->mem_handle) D.MemRelease(xc->mem_handle);
+    if (xc->mc_handle) D.MemRelease(xc->mc_handle);
+    xc->mc = nullptr;
+    xc->local = nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int glb_xchg_mc_supported(glb_ctx_t ctx, int *supported) {
+    GLB_REQUIRE(ctx && supported, "NULL argument");
+    *supported = 0;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    GLB_CUDA(cudaFree(nullptr));  // the primary context exists
+    const DriverApi &D = driver_api();
+    if (!D.ok) return GLB_OK;
+    CUdevice dev;
+    int v = 0;
+    if (D.DeviceGet(&dev, ctx->device) == CUDA_SUCCESS &&
+        D.DeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) == CUDA_SUCCESS)
+        *supported = v;
+    return GLB_OK;
+}
+
+int glb_xchg_mc_open(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, int fd_in, glb_xchg_t *out, int *fd_out) {
+    GLB_REQUIRE(ctx && out && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
+    GLB_REQUIRE(nranks >= 2 && nranks <= GLB_MAX_PEERS + 1 && rank >= 0 && rank < nranks, "bad rank");
+    GLB_REQUIRE((rank == 0) == (fd_in < 0), "rank 0 creates the multicast object (fd_in = -1); every other rank passes its descriptor");
+    GLB_REQUIRE(rank != 0 || fd_out, "rank 0 needs fd_out");
+    *out = nullptr;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    GLB_CUDA(cudaFree(nullptr));
+    const DriverApi &D = driver_api();
+    GLB_REQUIRE(D.ok, "this driver has no multicast entry points");
+    CUdevice dev;
+    GLB_CU(D.DeviceGet(&dev, ctx->device));
+    int supported = 0;
+    GLB_CU(D.DeviceGetAttribute(&supported, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev));
+    GLB_REQUIRE(supported, "the device does not support multicast objects (no NVSwitch?)");
+    // same size on every rank: the block rounded to the multicast granularity
+    const size_t bytes = glb_xchg_block_bytes(n_floats, n_vectors);
+    CUmulticastObjectProp prop = mc_prop(nranks, bytes);
+    size_t gran = 0, gran_alloc = 0;
+    GLB_CU(D.MulticastGetGranularity(&gran, &prop, CU_MULTICAST_GRANULARITY_MINIMUM));
+    const CUmemAllocationProp ap = mc_alloc_prop(ctx->device);
+    GLB_CU(D.MemGetAllocationGranularity(&gran_alloc, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (gran_alloc > gran) gran = gran_alloc;  // (powers of two)
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    prop.size = size;
+    CUmemGenericAllocationHandle mch = 0;
+    if (rank == 0) {
+        GLB_CU(D.MulticastCreate(&mch, &prop));
+        int fd = -1;
+        const CUresult r = D.MemExportToShareableHandle(&fd, mch, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+        if (r != CUDA_SUCCESS) {
+            D.MemRelease(mch);
+            glb_set_error("glb_xchg_mc_open: exporting the multicast object failed");
+            return GLB_ECUDA;
+        }
+        *fd_out = fd;
+    } else {
+        GLB_CU(D.MemImportFromShareableHandle(&mch, reinterpret_cast<void *>(static_cast<uintptr_t>(fd_in)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+        if (fd_out) *fd_out = -1;
+    }
+    const CUresult added = D.MulticastAddDevice(mch, dev);
+    if (added != CUDA_SUCCESS) {
+        D.MemRelease(mch);
+        glb_set_error("glb_xchg_mc_open: cuMulticastAddDevice failed (%d)", int(added));
+        return GLB_ECUDA;
+    }
+    glb_xchg_t xc = new glb_xchg_s();
+    xc->ctx = ctx;
+    glb_ctx_retain(ctx);
+    xc->n = n_floats;
+    xc->n_vectors = n_vectors;
+    xc->rank = rank;
+    xc->nranks = nranks;
+    xc->adopted = true;  // (nothing here is cudaMalloc / CUDA-IPC memory)
+    xc->mc_native = true;
+    xc->mc_handle = mch;
+    xc->mc_size = size;
+    *out = xc;
+    return GLB_OK;
+}
+
+int glb_xchg_mc_bind(glb_xchg_t xc) {
+    GLB_REQUIRE(xc && xc->mc_native && !xc->connected, "not an exchange opened with glb_xchg_mc_open (or bound already)");
+    glb_ctx_t ctx = xc->ctx;
+    GLB_CUDA(cudaSetDevice(ctx->device));
+    const DriverApi &D = driver_api();
+    CUdevice dev;
+    GLB_CU(D.DeviceGet(&dev, ctx->device));
+    const CUmemAllocationProp ap = mc_alloc_prop(ctx->device);
+    size_t gran = 0;
+    GLB_CU(D.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    GLB_REQUIRE(xc->mc_size % gran == 0, "multicast size is not a multiple of the allocation granularity");
+    CUmemGenericAllocationHandle mem = 0;
+    GLB_CU(D.MemCreate(&mem, xc->mc_size, &ap, 0));
+    xc->mem_handle = mem;
+    GLB_CU(D.MulticastBindMem(xc->mc_handle, 0, mem, 0, xc->mc_size, 0));
+    xc->mc_bound = true;
+    CUmemAccessDesc access;
+    memset(&access, 0, sizeof(access));
+    access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    access.location.id = ctx->device;
+    access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUdeviceptr uva = 0, mva = 0;
+    GLB_CU(D.MemAddressReserve(&uva, xc->mc_size, gran, 0, 0));
+    xc->local = reinterpret_cast<float *>(static_cast<uintptr_t>(uva));
+    GLB_CU(D.MemMap(uva, xc->mc_size, 0, mem, 0));
+    GLB_CU(D.MemSetAccess(uva, xc->mc_size, &access, 1));
+    GLB_CU(D.MemAddressReserve(&mva, xc->mc_size, gran, 0, 0));
+    xc->mc = reinterpret_cast<float *>(static_cast<uintptr_t>(mva));
+    GLB_CU(D.MemMap(mva, xc->mc_size, 0, xc->mc_handle, 0));
+    GLB_CU(D.MemSetAccess(mva, xc->mc_size, &access, 1));
+    GLB_CUDA(cudaMemset(xc->local, 0, xc->mc_size));
+    GLB_CUDA(cudaDeviceSynchronize());
+    const size_t vec_bytes = glb_xchg_block_bytes(xc->n, xc->n_vectors) - 256;
+    xc->local_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->local) + vec_bytes);
+    xc->mc_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(xc->mc) + vec_bytes);
+    xc->peer[xc->rank] = xc->local;  // the other ranks' blocks are reached through the switch only
+    xc->peer_flags[xc->rank] = xc->local_flags;
+    int rc = alloc_device_state(xc);
+    if (!rc && cudaMemcpy(xc->d_peer_flags, xc->peer_flags, sizeof(uint32_t *) * (GLB_MAX_PEERS + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+        glb_set_error("glb_xchg_mc_bind: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = GLB_ECUDA;
+    }
+    if (rc) return rc;
+    xc->connected = true;
+    return GLB_OK;
+}
+
+}  // extern "C"
+
 int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, void *const *blocks,
                    void *multicast_block, glb_xchg_t *out) {
     GLB_REQUIRE(ctx && out && blocks && n_floats > 0 && n_vectors >= 2 && n_vectors <= 4, "bad argument");
@@ -300,7 +549,9 @@ int glb_xchg_destroy(glb_xchg_t xc) {
     if (!xc) return GLB_OK;
     cudaSetDevice(xc->ctx->device);
     cudaStreamSynchronize(xc->ctx->stream);
-    if (!xc->adopted) {
+    if (xc->mc_native) {
+        mc_release(xc);
+    } else if (!xc->adopted) {
         for (int r = 0; r < xc->nranks; ++r)
             if (xc->connected && r != xc->rank && xc->peer[r]) cudaIpcCloseMemHandle(xc->peer[r]);
         cudaFree(xc->local);

@@ -190,6 +190,11 @@ struct glb_xchg_s {
     bool adopted = false;
     float *mc = nullptr;
     uint32_t *mc_flags = nullptr;  // multicast mapping of the flag words
+    // multicast object created through the C ABI (glb_xchg_mc_open / _bind, exchange.cu): driver handles to release
+    bool mc_native = false;
+    unsigned long long mc_handle = 0, mem_handle = 0;  // CUmemGenericAllocationHandle
+    size_t mc_size = 0;
+    bool mc_bound = false;
 };
 extern "C" int glb_xchg_signal_wait(glb_ctx_t ctx, glb_xchg_t xc);  // internal (not in the public header)
 struct GlbXchgWait;                                        // exchange.cuh

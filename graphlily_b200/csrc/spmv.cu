@@ -1610,6 +1610,8 @@ int glb_spmv_exchange_iterate(glb_ctx_t ctx, glb_csr_t m, int op, float zero, in
         const GlbXchgWait *w = k > 0 ? &wait : nullptr;
         // (per-kernel timing and the tile variant take the plain sequence)
         int mode = (forced == 4 && (ctx->timing || m->tile_threads)) ? 1 : forced;
+        for (int r = 0; mode == 4 && r < xc->nranks; ++r)
+            if (!xc->peer[r]) mode = 1;  // (an exchange made by glb_xchg_mc_open maps no peer block one by one)
         if (mode == 5 && (ctx->timing || !xc->mc || !glb_pusher_applies(m, y, xc->mc + size_t(dv) * xc->n))) mode = 1;
         if (xc->nranks > 1 && mode == 4) {
             // GLB_XCHG_MC=copy: split step -- sub-blocks of the shard on streams of their own, their finished rows

@@ -373,6 +373,18 @@ size_t glb_xchg_block_bytes(uint32_t n_floats, int n_vectors);
 int glb_xchg_adopt(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, void *const *blocks,
                    void *multicast_block, glb_xchg_t *out);
 int glb_xchg_has_multicast(glb_xchg_t xc);
+/* The same exchange with the NVSwitch multicast object, this rank's block and both mappings made by the library
+ * itself (CUDA driver virtual-memory API; no framework):
+ *   rank 0:       glb_xchg_mc_open(ctx, n, v, 0, nranks, -1, &xc, &fd) creates the multicast object and returns its POSIX
+ *                 file descriptor; the host hands it to the other ranks' processes (SCM_RIGHTS, pidfd_getfd, ...)
+ *   other ranks:  glb_xchg_mc_open(ctx, n, v, rank, nranks, fd_in_this_process, &xc, NULL)
+ *   -- host barrier (every rank has added its device to the object) --
+ *   all ranks:    glb_xchg_mc_bind(xc): allocate, bind, map; the exchange is connected (multicast transfers only)
+ *   -- host barrier, then use like any other exchange --
+ * glb_xchg_mc_supported: *supported != 0 if the device and driver offer multicast objects. */
+int glb_xchg_mc_supported(glb_ctx_t ctx, int *supported);
+int glb_xchg_mc_open(glb_ctx_t ctx, uint32_t n_floats, int n_vectors, int rank, int nranks, int fd_in, glb_xchg_t *out, int *fd_out);
+int glb_xchg_mc_bind(glb_xchg_t xc);
 int glb_xchg_vector(glb_xchg_t xc, int which, float **local_ptr);
 int glb_xchg_allgather(glb_ctx_t ctx, glb_xchg_t xc, int which, size_t offset, size_t count);
 int glb_xchg_barrier(glb_ctx_t ctx, glb_xchg_t xc);

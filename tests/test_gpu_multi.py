@@ -29,8 +29,8 @@ def _worker(rank, world, port, kind):
     torch.cuda.set_device(rank)
     if kind == "multicast-pusher":   # the slice leaves through pusher CTAs beside the SpMV kernels (GLB_XCHG_MC=pusher)
         os.environ["GLB_XCHG_MC"] = "pusher"
-        kind = "multicast"
-    if kind == "multicast":   # torch symmetric memory rendezvous runs over the default (NCCL) group
+        kind = "multicast-native"
+    if kind.startswith("multicast"):   # (torch symmetric memory rendezvous runs over the default NCCL group)
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,6 +46,9 @@ def _worker(rank, world, port, kind):
         xc, got = open_exchange(ctx, n_floats, rank, world, n_vectors=n_vectors, kind=kind,
                                 log=lambda *a: print("[test]", *a, flush=True))
         assert xc is not None, "no peer-mapped exchange on this box"
+        if kind.startswith("multicast"):   # an NVSwitch box: the requested flavour must be the one that opened
+            assert got == "multicast" and xc.has_multicast(), (kind, got)
+            assert bool(getattr(xc, "_keep", None)) == (kind == "multicast-torch"), "wrong flavour of the multicast exchange"
         if rank == 0:
             print(f"[test] exchange requested {kind}: got {got}, multicast mapping {xc.has_multicast()}", flush=True)
         return xc
@@ -153,7 +156,7 @@ def _worker(rank, world, port, kind):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["peer", "multicast", "multicast-pusher"])
+@pytest.mark.parametrize("kind", ["peer", "multicast-native", "multicast-torch", "multicast-pusher"])
 def test_exchange_and_apps_on_two_gpus(kind):
     from graphlily_b200 import capi
     if capi.device_count() < 2:
