@@ -82,6 +82,10 @@ private:
     }
 
     void push_setup(uint32_t source) {
+        if (exchange_) {
+            exchange_->barrier();   // no rank overwrites vectors a peer still reads from the previous run
+            SpMV_->home_buffers();
+        }
         SpMSpV_->home_lists();
         SpMSpV_->set_vector_single(source, 1);     // one source vertex (bfs.h:131-135), built on the device
         SpMSpV_->set_mask_constant(0, source, 1);  // distance: 0 but distance[source] = 1, built on the device
@@ -141,6 +145,7 @@ private:
 
     void push_step(uint32_t iter) {
         SpMSpV_->run();
+        exchange_frontier(SpMV_, SpMSpV_->results_buf, semiring_.zero, matrix_num_rows_);  // (row-sharded runs)
         std::swap(SpMSpV_->vector_buf, SpMSpV_->results_buf);  // the new frontier is the next input
         SparseAssign_->bind_mask_buf(SpMSpV_->vector_buf);
         SparseAssign_->run(iter + 1);
@@ -198,7 +203,8 @@ public:
             SpMV_->results_buf = exchange_->buffer(1);
             SpMV_->mask_buf = exchange_->buffer(2);
         }
-        if (world_ == 1) SpMSpV_->send_matrix_host_to_device();   // (the C++ mirror shards the pull direction only)
+        SpMSpV_->send_matrix_host_to_device(row_begin(), row_end(matrix_num_rows_));
+        if (exchange_) SpMSpV_->mask_buf = exchange_->buffer(2);   // the distance vector both directions update
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
@@ -214,9 +220,8 @@ public:
     }
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
-        assert(world_ == 1 && "the C++ mirror shards the pull direction only");
         push_setup(source);
-        if (!fused_) {
+        if (!fused_ || world_ > 1) {   // (sharded: the frontier exchange sits between the SpMSpV and the assign)
             for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);
             return SpMSpV_->send_mask_device_to_host();
         }
@@ -231,7 +236,7 @@ public:
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
-        if (fused_ && use_graphs_ && num_iterations >= 2) return pull_push_device(source, num_iterations, threshold);
+        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1) return pull_push_device(source, num_iterations, threshold);
         push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);
@@ -245,12 +250,16 @@ public:
         push_iterations_ = iter - 1;
         // switch from push to pull: the last frontier becomes the dense SpMV input, on the device
         SpMV_->bind_mask_buf(SpMSpV_->mask_buf);
-        SpMV_->home_buffers();
-        if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
-            SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
-        GLB_CHECK(glb_sparse_to_dense(runtime_->ctx(), SpMSpV_->vector_buf.sparse(), SpMV_->vector_buf.f32(), n,
-                                      graphlily::LogicalSemiring.zero));
+        if (world_ == 1) {   // (sharded: the frontier already sits in SpMV_->vector_buf, it travelled as a dense vector)
+            SpMV_->home_buffers();
+            if (!SpMV_->vector_buf.valid() || SpMV_->vector_buf.bytes() < sizeof(graphlily::val_t) * n)
+                SpMV_->vector_buf = DeviceBuffer(runtime_, sizeof(graphlily::val_t) * n);
+            GLB_CHECK(glb_sparse_to_dense(runtime_->ctx(), SpMSpV_->vector_buf.sparse(), SpMV_->vector_buf.f32(), n,
+                                          graphlily::LogicalSemiring.zero));
+        }
         pull_loop(iter, num_iterations);
+        if (exchange_)   // the pull levels updated the distance shard by shard
+            exchange_->allgather(SpMSpV_->mask_buf.exchange_vector(), row_begin(), row_end(n) - row_begin());
         return SpMSpV_->send_mask_device_to_host();  // the mask of SpMV on the host is not valid
     }
 

@@ -34,7 +34,8 @@ protected:
 
     // Row-range sharding over the ranks of one box (one process per GPU): this process owns the
     // rows [cuts_[rank], cuts_[rank + 1]) of the CSR, cut where the nnz prefix crosses r / world (32-row
-    // aligned); the slices of every iteration's result meet over the exchange.  Pull direction.
+    // aligned); the slices of every iteration's result meet over the exchange.  The push direction shards the CSC by
+    // the same row ranges and exchanges its frontier as a dense vector (exchange_frontier).
     int rank_ = 0, world_ = 1;
     Exchange *exchange_ = nullptr;
     std::vector<uint32_t> cuts_;
@@ -50,6 +51,24 @@ protected:
     }
     uint32_t row_begin() const { return cuts_.empty() ? 0 : cuts_[rank_]; }
     uint32_t row_end(uint32_t n) const { return cuts_.empty() ? n : cuts_[rank_ + 1]; }
+
+    // Row-sharded push: every rank's SpMSpV listed only the rows it owns.  The lists meet as ONE dense
+    // vector -- own slice reset and scattered, slices exchanged, the full vector listed again on every rank into the
+    // same list buffer -- so what follows (the sparse assign on the replicated distance vector, the next SpMSpV) sees
+    // the whole frontier.  The dense vector ALTERNATES between the SpMV module's two exchange vectors (idle while the
+    // push direction runs): the exchange's signal / wait says "every rank has written its slice of step k", not "every
+    // rank has finished reading step k", so a fast rank's slice of step k + 1 must not land in the vector a slow rank
+    // is still listing.  After the call the fresh frontier (dense) is spmv->vector_buf.
+    template <typename SpMVT>
+    void exchange_frontier(SpMVT *spmv, const DeviceBuffer &list, float zero, uint32_t n) {
+        if (world_ == 1) return;
+        DeviceBuffer dense = spmv->results_buf;
+        assert(dense.exchange_vector() >= 0 && "the SpMV module's vectors must live in the exchange");
+        GLB_CHECK(glb_sparse_to_dense_rows(runtime_->ctx(), list.sparse(), dense.f32(), row_begin(), row_end(n), zero));
+        exchange_->allgather(dense.exchange_vector(), row_begin(), row_end(n) - row_begin());
+        GLB_CHECK(glb_dense_to_sparse(runtime_->ctx(), dense.f32(), n, zero, list.sparse()));
+        std::swap(spmv->vector_buf, spmv->results_buf);
+    }
 
     // Launch replay.  The iteration loop of an app is a fixed launch sequence (same buffers, same
     // per-iteration scalars): it is recorded once per key as a CUDA graph (glb_graph_begin / _end)

@@ -113,6 +113,10 @@ private:
     }
 
     void push_setup(uint32_t source) {
+        if (exchange_) {
+            exchange_->barrier();
+            SpMV_->home_buffers();
+        }
         SpMSpV_->home_lists();
         SpMSpV_->set_vector_single(source, 0);                  // the source frontier (sssp.h:169-171), built on the device
         SpMSpV_->set_mask_constant(semiring_.zero, source, 0);  // distance (sssp.h:172-176), built on the device
@@ -217,7 +221,7 @@ public:
             SpMV_->vector_buf = exchange_->buffer(0);
             SpMV_->results_buf = exchange_->buffer(1);
         }
-        if (world_ == 1) SpMSpV_->send_matrix_host_to_device();   // (the C++ mirror shards the pull direction only)
+        SpMSpV_->send_matrix_host_to_device(row_begin(), row_end(matrix_num_rows_));
     }
 
     aligned_dense_vec_t pull(uint32_t source, uint32_t num_iterations) {
@@ -228,11 +232,11 @@ public:
     }
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
-        assert(world_ == 1 && "the C++ mirror shards the pull direction only");
         push_setup(source);
-        if (!fused_) {
+        if (!fused_ || world_ > 1) {   // (sharded: the frontier exchange sits between the SpMSpV and the relax)
             for (uint32_t iter = 1; iter <= num_iterations; iter++) {
                 SpMSpV_->run();
+                exchange_frontier(SpMV_, SpMSpV_->results_buf, semiring_.zero, matrix_num_rows_);
                 SparseAssign_->run();
             }
             return SpMSpV_->send_mask_device_to_host();
@@ -247,7 +251,7 @@ public:
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
-        if (fused_ && use_graphs_ && num_iterations >= 2) return pull_push_device(source, num_iterations, threshold);
+        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1) return pull_push_device(source, num_iterations, threshold);
         push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);
@@ -255,6 +259,7 @@ public:
         uint32_t vector_nnz;
         do {
             SpMSpV_->run();
+            exchange_frontier(SpMV_, SpMSpV_->results_buf, semiring_.zero, n);
             SparseAssign_->run();
             vector_nnz = SpMSpV_->get_results_nnz();
             iter++;

@@ -58,12 +58,19 @@ public:
     void load_and_format_matrix(CSCMatrix<float> const &csc_matrix_float) { csc_matrix_float_ = csc_matrix_float; }
 
     // Matrix upload + the result (rows + 1) and vector (cols + 1) lists, spmspv_module.h:290-370.
-    void send_matrix_host_to_device() {
+    void send_matrix_host_to_device() { send_matrix_host_to_device(0, csc_matrix_float_.num_rows); }
+    // Row shard of the push direction (one process per GPU): of every column only the entries whose row lies in
+    // [row_begin, row_end) go to this device; run() then lists only rows of the shard (ids stay global).
+    void send_matrix_host_to_device(uint32_t row_begin, uint32_t row_end) {
         const CSCMatrix<float> &m = csc_matrix_float_;
         glb_csc_destroy(matrix_);
         matrix_ = nullptr;
-        GLB_CHECK(glb_csc_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
-                                 m.adj_data.data(), &matrix_));
+        if (row_begin == 0 && row_end == m.num_rows)
+            GLB_CHECK(glb_csc_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
+                                     m.adj_data.data(), &matrix_));
+        else
+            GLB_CHECK(glb_csc_create_rows(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
+                                          m.adj_data.data(), row_begin, row_end, &matrix_));
         aligned_sparse_vec_t empty_rows(size_t(m.num_rows) + 1, idx_val_t{0, 0});
         aligned_sparse_vec_t empty_cols(size_t(m.num_cols) + 1, idx_val_t{0, 0});
         results_buf = upload(empty_rows);

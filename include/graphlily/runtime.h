@@ -82,6 +82,21 @@ public:
     Exchange(const std::shared_ptr<Runtime> &rt, uint32_t n_floats, int n_vectors) : rt_(rt), n_(n_floats), n_vectors_(n_vectors) {
         GLB_CHECK(glb_xchg_create(rt_->ctx(), n_floats, n_vectors, &xc_));
     }
+    // The same vectors behind an NVSwitch multicast object the library creates (glb_xchg_mc_open / _bind): a finished
+    // slice leaves the GPU once and the switch replicates it.  Rank 0 passes fd_in = -1 and receives the object's file
+    // descriptor in *fd_out, which the host hands to the other ranks' processes (SCM_RIGHTS over a Unix socket); they
+    // pass their copy as fd_in.  After a host barrier every rank calls bind(), and after another one the exchange is usable.
+    Exchange(const std::shared_ptr<Runtime> &rt, uint32_t n_floats, int n_vectors, int rank, int world, int fd_in, int *fd_out)
+        : rt_(rt), n_(n_floats), n_vectors_(n_vectors), rank_(rank), world_(world) {
+        GLB_CHECK(glb_xchg_mc_open(rt_->ctx(), n_floats, n_vectors, rank, world, fd_in, &xc_, fd_out));
+    }
+    void bind() { GLB_CHECK(glb_xchg_mc_bind(xc_)); }
+    static bool multicast_supported(const std::shared_ptr<Runtime> &rt) {
+        int s = 0;
+        GLB_CHECK(glb_xchg_mc_supported(rt->ctx(), &s));
+        return s != 0;
+    }
+    bool has_multicast() const { return glb_xchg_has_multicast(xc_) != 0; }
     ~Exchange() { glb_xchg_destroy(xc_); }
     Exchange(const Exchange &) = delete;
     Exchange &operator=(const Exchange &) = delete;
