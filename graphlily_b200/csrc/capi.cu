@@ -107,6 +107,7 @@ static void ctx_free(glb_ctx_t ctx) {
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->branch_stream) cudaStreamDestroy(ctx->branch_stream);
     if (ctx->split_ev_head) cudaEventDestroy(ctx->split_ev_head);
+    if (ctx->pipe_pushed) cudaEventDestroy(ctx->pipe_pushed);
     if (ctx->pusher_stream) cudaStreamDestroy(ctx->pusher_stream);
     if (ctx->pusher_ev_fork) cudaEventDestroy(ctx->pusher_ev_fork);
     if (ctx->pusher_ev_done) cudaEventDestroy(ctx->pusher_ev_done);

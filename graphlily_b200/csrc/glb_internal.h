@@ -70,6 +70,7 @@ struct glb_ctx_s {
     // copy streams + events of the pipelined host-buffer path (glb_spmv_host_batch), created on first use
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[3][2] = {};  // [uploaded | computed | downloaded][slot]
+    cudaEvent_t pipe_pushed = nullptr;  // host batch over an exchange: "the slice push of the current vector has left"
 };
 
 // ---------------------------------------------------------------- lane-segment CSR (SpMV)

@@ -1768,38 +1768,98 @@ static int spmv_host_batch(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int m
         int rc = glb_xchg_signal_wait(ctx, xc);
         if (rc) return rc;
     }
-    for (int k = 0; k < n_vectors; ++k) {
+    // GLB_BATCH_TRACE=1: device timeline of the first vectors of the batch (upload / kernels / download), to stderr
+    static const bool trace = getenv("GLB_BATCH_TRACE") != nullptr;
+    // Over an exchange the copies of the neighbouring vectors (upload k+1, download k-1) are held back until the slice
+    // push of vector k has left: the SM-issued NVLink stores of the push and the copy engines' PCIe traffic share the
+    // GPU's path to the outside, and a push that takes 20 us alone took 130-200 us beside two saturated PCIe directions
+    // (2 GPUs, C2; profiles/r2_host_batch_timeline_2gpu.txt).  GLB_BATCH_UNGATED=1 restores the free-running order.
+    static const bool gated = getenv("GLB_BATCH_UNGATED") == nullptr;
+    constexpr int kTraceVectors = 10;
+    cudaEvent_t tev[1 + 7 * kTraceVectors] = {};
+    auto stamp = [&](int k, int what, cudaStream_t st) {
+        if (!trace || k >= kTraceVectors) return;
+        cudaEvent_t &e = tev[k < 0 ? 0 : 1 + 7 * k + what];
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+    };
+    if (!ctx->pipe_pushed) GLB_CUDA(cudaEventCreateWithFlags(&ctx->pipe_pushed, cudaEventDisableTiming));
+    stamp(-1, 0, ctx->stream);
+    // upload k: slot k & 1 is free once the kernels of vector k-2 have read it
+    auto enqueue_upload = [&](int k, bool after_push) -> int {
         const int s = k & 1;
-        // upload k: slot s is free once the kernels of vector k-2 have read it
         if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, computed[s], 0));
+        if (after_push) GLB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->pipe_pushed, 0));
+        stamp(k, 0, ctx->copy_in);
         if (x_off < m->num_cols) {
             const size_t cnt = (x_off + x_cnt <= m->num_cols) ? x_cnt : m->num_cols - x_off;
             GLB_CUDA(cudaMemcpyAsync(xslot[s] + x_off, x_hosts[k] + x_off, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->copy_in));
         }
+        stamp(k, 1, ctx->copy_in);
         if (masked)   // the mask is row-local: only the shard's rows are read
             GLB_CUDA(cudaMemcpyAsync(*dms[s] + m->row_begin, mask_hosts[k] + m->row_begin, sizeof(float) * nr,
                                      cudaMemcpyHostToDevice, ctx->copy_in));
         GLB_CUDA(cudaEventRecord(uploaded[s], ctx->copy_in));
+        return GLB_OK;
+    };
+    auto enqueue_download = [&](int k, bool after_push) -> int {
+        const int s = k & 1;
+        GLB_CUDA(cudaStreamWaitEvent(ctx->copy_out, computed[s], 0));
+        if (after_push) GLB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_pushed, 0));
+        stamp(k, 5, ctx->copy_out);
+        GLB_CUDA(cudaMemcpyAsync(y_hosts[k] + m->row_begin, *dys[s] + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
+                                 ctx->copy_out));
+        stamp(k, 6, ctx->copy_out);
+        GLB_CUDA(cudaEventRecord(downloaded[s], ctx->copy_out));
+        return GLB_OK;
+    };
+    const bool hold = xc != nullptr && gated;
+    int rc = enqueue_upload(0, false);
+    if (rc) return rc;
+    for (int k = 0; k < n_vectors; ++k) {
+        const int s = k & 1;
+        if (!hold && k + 1 < n_vectors && (rc = enqueue_upload(k + 1, false))) return rc;
         // kernels k: need the upload, and the download of result k-2 must have drained dy[s]
         GLB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[s], 0));
         if (k >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[s], 0));
-        if (xc) {  // the slices of x meet over NVLink; the wait inside also orders slot reuse across ranks
-            int rc = glb_xchg_allgather(ctx, xc, s, x_off, x_cnt);
+        stamp(k, 2, ctx->stream);
+        if (xc) {  // the slices of x meet over NVLink; the wait also orders slot reuse across ranks
+            rc = glb_xchg_push(ctx, xc, s, x_off, x_cnt);
+            if (rc) return rc;
+            GLB_CUDA(cudaEventRecord(ctx->pipe_pushed, ctx->stream));
+            if (hold) {  // the copies that overlap this vector's SpMV start once its slice is out
+                if (k + 1 < n_vectors && (rc = enqueue_upload(k + 1, true))) return rc;
+                if (k >= 1 && (rc = enqueue_download(k - 1, true))) return rc;
+            }
+            rc = glb_xchg_wait(ctx, xc);
             if (rc) return rc;
         }
-        int rc = glb_spmv(ctx, m, op, zero, mask_type, xslot[s], masked ? *dms[s] : nullptr, *dys[s]);
+        stamp(k, 3, ctx->stream);
+        rc = glb_spmv(ctx, m, op, zero, mask_type, xslot[s], masked ? *dms[s] : nullptr, *dys[s]);
         if (rc) return rc;
+        stamp(k, 4, ctx->stream);
         GLB_CUDA(cudaEventRecord(computed[s], ctx->stream));
-        // download k
-        GLB_CUDA(cudaStreamWaitEvent(ctx->copy_out, computed[s], 0));
-        GLB_CUDA(cudaMemcpyAsync(y_hosts[k] + m->row_begin, *dys[s] + m->row_begin, sizeof(float) * nr, cudaMemcpyDeviceToHost,
-                                 ctx->copy_out));
-        GLB_CUDA(cudaEventRecord(downloaded[s], ctx->copy_out));
+        if (!hold && (rc = enqueue_download(k, false))) return rc;
     }
+    if (hold && (rc = enqueue_download(n_vectors - 1, false))) return rc;
     // the caller's stream ends after the last download, so stream-ordered work and events that follow see it
     GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[(n_vectors - 1) & 1], 0));
     if (n_vectors >= 2) GLB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded[n_vectors & 1], 0));
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        GLB_CUDA(cudaStreamSynchronize(ctx->copy_in));
+        GLB_CUDA(cudaStreamSynchronize(ctx->copy_out));
+        auto at = [&](int k, int what) {
+            float ms = 0;
+            cudaEvent_t e = tev[1 + 7 * k + what];
+            if (!e || cudaEventElapsedTime(&ms, tev[0], e) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+            return double(ms) * 1e3;
+        };
+        for (int k = 0; k < n_vectors && k < kTraceVectors; ++k)
+            fprintf(stderr, "[glb batch rank %d] vector %d: upload %.0f..%.0f us | exchange %.0f..%.0f | spmv ..%.0f | download %.0f..%.0f\n",
+                    xc ? xc->rank : 0, k, at(k, 0), at(k, 1), at(k, 2), at(k, 3), at(k, 4), at(k, 5), at(k, 6));
+        for (auto e : tev) if (e) cudaEventDestroy(e);
+    }
     return GLB_OK;
 }
 
