@@ -30,14 +30,16 @@ public:
         in_buf = upload(in_);
     }
     void allocate_out_buf(uint32_t len) {
-        out_.assign(len, 0);
+        out_.assign(len, vector_data_t(0));
         out_buf = DeviceBuffer(runtime_, sizeof(vector_data_t) * len);
     }
     void bind_in_buf(DeviceBuffer src_buf) { in_buf = src_buf; }
     void bind_out_buf(DeviceBuffer src_buf) { out_buf = src_buf; }
 
     void run(uint32_t len, vector_data_t val) {
-        GLB_CHECK(glb_ewise_add(ctx(), in_buf.f32(), out_buf.f32(), len, val));
+        using VT = graphlily::val_traits<vector_data_t>;
+        if (VT::id == GLB_VAL_F32) GLB_CHECK(glb_ewise_add(ctx(), in_buf.f32(), out_buf.f32(), len, float(val)));
+        else GLB_CHECK(glb_ewise_add_vt(ctx(), VT::id, in_buf.ptr(), out_buf.ptr(), len, VT::bits(val)));
         end_run();
     }
 

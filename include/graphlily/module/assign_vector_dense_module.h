@@ -45,7 +45,9 @@ public:
     void bind_inout_buf(DeviceBuffer src_buf) { inout_buf = src_buf; }
 
     void run(uint32_t len, vector_data_t val) {
-        GLB_CHECK(glb_assign_dense(ctx(), mask_buf.f32(), inout_buf.f32(), len, val, mask_type_));
+        using VT = graphlily::val_traits<vector_data_t>;
+        if (VT::id == GLB_VAL_F32) GLB_CHECK(glb_assign_dense(ctx(), mask_buf.f32(), inout_buf.f32(), len, float(val), mask_type_));
+        else GLB_CHECK(glb_assign_dense_vt(ctx(), VT::id, mask_buf.ptr(), inout_buf.ptr(), len, VT::bits(val), mask_type_));
         end_run();
     }
 

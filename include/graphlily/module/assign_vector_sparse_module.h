@@ -47,7 +47,7 @@ public:
         mask_ = mask;
         mask_buf = upload(mask_);
         if (generate_new_frontier_) {  // assign_vector_sparse_module.h:232-247: same capacity as the mask
-            new_frontier_.assign(mask_.size(), sparse_vector_data_t{0, 0});
+            new_frontier_.assign(mask_.size(), sparse_vector_data_t{0, vector_data_t(0)});
             new_frontier_buf = upload(new_frontier_);
         }
     }
@@ -65,13 +65,19 @@ public:
     // BFS mode: inout[mask[i].index] = val
     void run(vector_data_t val) {
         require_new_frontier(false);
-        GLB_CHECK(glb_assign_sparse(ctx(), mask_buf.sparse(), inout_buf.f32(), val));
+        using VT = graphlily::val_traits<vector_data_t>;
+        if (VT::id == GLB_VAL_F32) GLB_CHECK(glb_assign_sparse(ctx(), mask_buf.sparse(), inout_buf.f32(), float(val)));
+        else GLB_CHECK(glb_assign_sparse_vt(ctx(), VT::id, mask_buf.sparse(), inout_buf.ptr(), VT::bits(val)));
         end_run();
     }
     // SSSP mode: relax and emit the new frontier
     void run() {
         require_new_frontier(true);
-        GLB_CHECK(glb_assign_sparse_relax(ctx(), mask_buf.sparse(), inout_buf.f32(), new_frontier_buf.sparse()));
+        using VT = graphlily::val_traits<vector_data_t>;
+        if (VT::id == GLB_VAL_F32)
+            GLB_CHECK(glb_assign_sparse_relax(ctx(), mask_buf.sparse(), inout_buf.f32(), new_frontier_buf.sparse()));
+        else
+            GLB_CHECK(glb_assign_sparse_relax_vt(ctx(), VT::id, mask_buf.sparse(), inout_buf.ptr(), new_frontier_buf.sparse()));
         end_run();
     }
 

@@ -20,9 +20,10 @@ namespace module {
 
 template <typename matrix_data_t, typename vector_data_t, typename idx_val_t>
 class SpMSpVModule : public BaseModule {
-    static_assert(std::is_same<matrix_data_t, float>::value && std::is_same<vector_data_t, float>::value,
-                  "graphlily-b200 computes in fp32 (val_t = float)");
+    static_assert(std::is_same<matrix_data_t, vector_data_t>::value && sizeof(vector_data_t) == 4,
+                  "matrix and vector share one 32-bit value type: float, unsigned or graphlily::ufixed_32_8");
     static_assert(sizeof(idx_val_t) == sizeof(glb_idx_val_t), "idx_val_t must match the C ABI");
+    using VT = graphlily::val_traits<vector_data_t>;
 private:
     graphlily::MaskType mask_type_ = graphlily::kNoMask;
     graphlily::SemiringType semiring_ = graphlily::ArithmeticSemiring;
@@ -65,14 +66,20 @@ public:
         const CSCMatrix<float> &m = csc_matrix_float_;
         glb_csc_destroy(matrix_);
         matrix_ = nullptr;
+        const float *data = m.adj_data.data();
+        std::vector<uint32_t> words;   // the stored words of the value type ((val_t)x, spmspv_module.h:300-310)
+        if (VT::id != GLB_VAL_F32) {
+            words.resize(m.adj_data.size());
+            for (size_t i = 0; i < words.size(); i++) words[i] = VT::bits(VT::from_float(m.adj_data[i]));
+            data = reinterpret_cast<const float *>(words.data());
+        }
         if (row_begin == 0 && row_end == m.num_rows)
-            GLB_CHECK(glb_csc_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
-                                     m.adj_data.data(), &matrix_));
+            GLB_CHECK(glb_csc_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(), data, &matrix_));
         else
-            GLB_CHECK(glb_csc_create_rows(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
-                                          m.adj_data.data(), row_begin, row_end, &matrix_));
-        aligned_sparse_vec_t empty_rows(size_t(m.num_rows) + 1, idx_val_t{0, 0});
-        aligned_sparse_vec_t empty_cols(size_t(m.num_cols) + 1, idx_val_t{0, 0});
+            GLB_CHECK(glb_csc_create_rows(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(), data,
+                                          row_begin, row_end, &matrix_));
+        aligned_sparse_vec_t empty_rows(size_t(m.num_rows) + 1, idx_val_t{0, vector_data_t(0)});
+        aligned_sparse_vec_t empty_cols(size_t(m.num_cols) + 1, idx_val_t{0, vector_data_t(0)});
         results_buf = upload(empty_rows);
         vector_buf = upload(empty_cols);
     }
@@ -89,25 +96,33 @@ public:
     }
     void bind_mask_buf(DeviceBuffer src_buf) { mask_buf = src_buf; }
     void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        mask_buf = constant_on_device(mask_buf, get_num_rows(), value, true, index, index_value);
+        mask_buf = constant_on_device(mask_buf, get_num_rows(), graphlily::val_container(value), true, index,
+                                      graphlily::val_container(index_value));
     }
 
     void run() {
-        GLB_CHECK(glb_spmspv(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.sparse(),
-                             mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.sparse()));
+        const float *mask_ptr = mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32();
+        if (VT::id == GLB_VAL_F32)
+            GLB_CHECK(glb_spmspv(ctx(), matrix_, semiring_.op, float(semiring_.zero), mask_type_, vector_buf.sparse(), mask_ptr,
+                                 results_buf.sparse()));
+        else
+            GLB_CHECK(glb_spmspv_vt(ctx(), matrix_, VT::id, semiring_.op, VT::bits(vector_data_t(semiring_.zero)), mask_type_,
+                                    vector_buf.sparse(), mask_ptr, results_buf.sparse()));
         end_run();
     }
+    static constexpr bool fused_levels_available() { return VT::id == GLB_VAL_F32; }   // run_fused computes in fp32
 
     // A whole push level in one launch over explicit list buffers: SpMSpV + the sparse assign / relax of the
     // apps + (next != nullptr) the push-or-pull decision of pull_push taken on the device (glb_spmspv_fused).
     void run_fused(const DeviceBuffer &vector, const DeviceBuffer &results, const glb_spmspv_epilogue_t *epilogue,
                    const glb_spmspv_next_t *next) {
-        GLB_CHECK(glb_spmspv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector.sparse(),
+        assert(VT::id == GLB_VAL_F32 && "the fused push levels compute in fp32");
+        GLB_CHECK(glb_spmspv_fused(ctx(), matrix_, semiring_.op, float(semiring_.zero), mask_type_, vector.sparse(),
                                    mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results.sparse(), epilogue, next));
     }
     // the one-entry start frontier, written on the device (no blocking upload)
     void set_vector_single(uint32_t index, vector_data_t val) {
-        GLB_CHECK(glb_sparse_fill_one(ctx(), vector_buf.sparse(), index, val));
+        GLB_CHECK(glb_sparse_fill_one(ctx(), vector_buf.sparse(), index, graphlily::val_container(val)));
     }
     void home_lists() {  // canonical roles of the two list buffers at the start of a run: recorded sequences are found again
         if (vector_buf.valid() && results_buf.valid() && vector_buf.bytes() == results_buf.bytes() &&

@@ -25,8 +25,9 @@ namespace module {
 
 template <typename matrix_data_t, typename vector_data_t>
 class SpMVModule : public BaseModule {
-    static_assert(std::is_same<matrix_data_t, float>::value && std::is_same<vector_data_t, float>::value,
-                  "graphlily-b200 computes in fp32 (val_t = float)");
+    static_assert(std::is_same<matrix_data_t, vector_data_t>::value && sizeof(vector_data_t) == 4,
+                  "matrix and vector share one 32-bit value type: float, unsigned or graphlily::ufixed_32_8");
+    using VT = graphlily::val_traits<vector_data_t>;   // the kernels' value type (GLB_VAL_*): semiring.cuh
 private:
     graphlily::MaskType mask_type_ = graphlily::kNoMask;
     graphlily::SemiringType semiring_ = graphlily::ArithmeticSemiring;
@@ -64,8 +65,15 @@ public:
         if (row_end == 0xffffffffu) row_end = m.num_rows;
         glb_csr_destroy(matrix_);
         matrix_ = nullptr;
+        const float *data = m.adj_data.data();
+        std::vector<uint32_t> words;   // (val_t)x of the reference's formatter: the stored words of the value type
+        if (VT::id != GLB_VAL_F32) {
+            words.resize(m.adj_data.size());
+            for (size_t i = 0; i < words.size(); i++) words[i] = VT::bits(VT::from_float(m.adj_data[i]));
+            data = reinterpret_cast<const float *>(words.data());
+        }
         GLB_CHECK(glb_csr_create(ctx(), m.num_rows, m.num_cols, m.adj_indptr.data(), m.adj_indices.data(),
-                                 m.adj_data.data(), row_begin, row_end, &matrix_));
+                                 data, row_begin, row_end, &matrix_));
         results_buf = DeviceBuffer(runtime_, sizeof(vector_data_t) * m.num_rows);
         GLB_CHECK(glb_buffer_fill_f32(ctx(), results_buf.f32(), 0.0f, m.num_rows));
     }
@@ -96,14 +104,16 @@ public:
     }
     void set_vector_constant(vector_data_t value) {
         ensure_vector_buf();
-        vector_buf = constant_on_device(vector_buf, get_num_cols(), value);
+        vector_buf = constant_on_device(vector_buf, get_num_cols(), graphlily::val_container(value));
     }
     void set_vector_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
         ensure_vector_buf();
-        vector_buf = constant_on_device(vector_buf, get_num_cols(), value, true, index, index_value);
+        vector_buf = constant_on_device(vector_buf, get_num_cols(), graphlily::val_container(value), true, index,
+                                        graphlily::val_container(index_value));
     }
     void set_mask_constant(vector_data_t value, uint32_t index, vector_data_t index_value) {
-        mask_buf = constant_on_device(mask_buf, get_num_rows(), value, true, index, index_value);
+        mask_buf = constant_on_device(mask_buf, get_num_rows(), graphlily::val_container(value), true, index,
+                                      graphlily::val_container(index_value));
     }
 
     void run() {
@@ -112,16 +122,19 @@ public:
     }
 
     // One launch for SpMV + the eWiseAdd / dense assign the apps run right after it (glb_spmv_fused).
-    void run_fused(const glb_spmv_epilogue_t *epilogue) {
-        GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector_buf.f32(),
-                                 mask_type_ == graphlily::kNoMask ? nullptr : mask_buf.f32(), results_buf.f32(), epilogue));
-    }
+    // (for unsigned / ufixed_32_8 the epilogue's add_val / assign_val carry the word: graphlily::val_container)
+    void run_fused(const glb_spmv_epilogue_t *epilogue) { run_fused(vector_buf, mask_buf, results_buf, epilogue); }
 
     // The same launch over explicit buffers: the app loops ping-pong vector / results instead of copying.
     void run_fused(const DeviceBuffer &vector, const DeviceBuffer &mask, const DeviceBuffer &results,
                    const glb_spmv_epilogue_t *epilogue) {
-        GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, vector.f32(),
-                                 mask_type_ == graphlily::kNoMask ? nullptr : mask.f32(), results.f32(), epilogue));
+        const float *mask_ptr = mask_type_ == graphlily::kNoMask ? nullptr : mask.f32();
+        if (VT::id == GLB_VAL_F32)
+            GLB_CHECK(glb_spmv_fused(ctx(), matrix_, semiring_.op, float(semiring_.zero), mask_type_, vector.f32(), mask_ptr,
+                                     results.f32(), epilogue));
+        else
+            GLB_CHECK(glb_spmv_vt(ctx(), matrix_, VT::id, semiring_.op, VT::bits(vector_data_t(semiring_.zero)), mask_type_,
+                                  vector.ptr(), mask_ptr, results.ptr(), epilogue));
     }
 
     // Row-sharded pull loop in one call (glb_spmv_exchange_iterate): vector -> results -> vector ... over two
@@ -129,7 +142,8 @@ public:
     void iterate_exchange(Exchange &xc, const DeviceBuffer &vector, const DeviceBuffer &mask, const DeviceBuffer &results,
                           const glb_spmv_epilogue_t *eps, int n_steps) {
         assert(vector.exchange_vector() >= 0 && results.exchange_vector() >= 0);
-        GLB_CHECK(glb_spmv_exchange_iterate(ctx(), matrix_, semiring_.op, semiring_.zero, mask_type_, xc.handle(),
+        assert(VT::id == GLB_VAL_F32 && "row-sharded runs compute in fp32");
+        GLB_CHECK(glb_spmv_exchange_iterate(ctx(), matrix_, semiring_.op, float(semiring_.zero), mask_type_, xc.handle(),
                                             vector.exchange_vector(), results.exchange_vector(),
                                             mask_type_ == graphlily::kNoMask ? nullptr : mask.f32(), eps, n_steps, nullptr));
     }
