@@ -65,6 +65,7 @@ inline CSRMatrix<float> skewed_csr(uint32_t n, uint32_t seed) {
     return m;
 }
 
+#if !defined(GRAPHLILY_VAL_T_UNSIGNED) && !defined(GRAPHLILY_VAL_T_UFIXED)   // fp32 helpers over the fp32 oracle
 inline dense_t random_01(uint32_t n, uint32_t seed) {
     std::mt19937 rng(seed);
     dense_t v(n);
@@ -90,4 +91,5 @@ inline void verify(const dense_t &ref, const dense_t &got, bool exact) {
         if (!ok) MT_FAIL_(true, "mismatch at %zu: reference %.9g kernel %.9g", i, ref[i], got[i]);
     }
 }
+#endif  // fp32
 #endif

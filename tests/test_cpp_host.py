@@ -80,6 +80,17 @@ def test_cpp_modules_and_apps_on_gpu(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_valtypes_unsigned", "test_valtypes_ufixed"])
+def test_cpp_value_type_builds(name):
+    """the C++ mirror compiled with val_t = unsigned / ap_ufixed<32,8,AP_RND,AP_SAT>
+    (-DGRAPHLILY_VAL_T_UNSIGNED / _UFIXED, the choices of the reference's global.h:60-64): module classes and
+    BFS / SSSP bit for bit against the sequential model of those types (oracle/valtype_model.cpp)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libvaltype_model.so"], stdout=subprocess.DEVNULL)
+    out = _run(name)
+    assert "FAILED" not in out and out.count("[  OK  ]") >= 5
+
+
+@pytest.mark.gpu
 def test_cpp_sharded_apps_two_processes():
     """Row-sharded BFS / PageRank / SSSP from the C++ mirror: two processes, one GPU each, vectors in a
     CUDA-IPC peer exchange (no torch anywhere).  The binary reports SKIPPED on a 1-GPU box."""
