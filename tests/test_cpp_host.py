@@ -16,7 +16,7 @@ BIN = os.path.join(ROOT, "tests", "cpp", "bin")
 
 
 def _build():
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so", "libvaltype_model.so"], stdout=subprocess.DEVNULL)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "all"], stdout=subprocess.DEVNULL)
 
 
