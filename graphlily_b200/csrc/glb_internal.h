@@ -130,6 +130,8 @@ struct glb_csr_s {
     uint32_t *hot_cols = nullptr;  // rank -> column
     float *hot_x = nullptr;        // x[hot_cols[.]], rebuilt by every SpMV launch
     uint32_t *xbits = nullptr;     // or-and: one bit per stored column word, rebuilt by every or-and launch
+    uint32_t *mbits = nullptr;     // masked or-and: one bit per row of the shard (mask != 0), rebuilt with xbits
+    uint32_t uniform_groups = 0, last_groups = 0;  // all chunks but the last hold uniform_groups groups (0: they vary)
     bool all_nonzero = false;      // no stored value is 0.0f (or-and skips the value stream)
     int smem_carveout_pct = 20;
     uint32_t tile_threads = 0;     // > 0: persistent shared-memory-tile kernel with that many threads per CTA

@@ -73,6 +73,12 @@ struct SpmvParams {
     const float *hot_x;   // x values of the hot columns, packed (or x itself when every column is hot)
     const float *x_cold;  // x - tile_k: cold column words index it directly
     const uint32_t *xbits;  // or-and only: bit w = (x value of stored column word w) != 0, see pack_bits_kernel
+    // Shortcuts of the per-chunk chain of dependent loads (what a launch of a few waves is bound by: the BFS levels):
+    const uint32_t *mbits;  // or-and with a mask: bit (row - mbits_base) = mask[row] != 0 at launch (pack_bits_kernel), an L1 hit
+    uint32_t mbits_base;    //   instead of an L2 round trip per tested row
+    int rows_identity;      // the shard has no empty row: the k-th non-empty row is row0 + k, nz_rows need not be read
+    uint32_t row0;
+    uint32_t uniform_groups, last_groups;  // every chunk but the last holds uniform_groups groups (0: read chunk_goff)
     const float *mask;    // may alias assign_inout
     float *y;
     float *y_peer[GLB_MAX_PEERS];  // the same vector on the other GPUs of a row-sharded run (peer-mapped memory)
@@ -141,7 +147,11 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
 template <int OP, bool IN_MAIN = true, int VT = GLB_VAL_F32>
 __device__ __forceinline__ void finish_row(const SpmvParams &P, uint32_t row, float total) {
     float v = Semi<OP, VT>::with_zero(P.zero, total);
-    if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
+    if (VT == GLB_VAL_F32 && P.mbits) {  // (uniform) the mask as it was at launch, one bit per row
+        const uint32_t b = row - P.mbits_base;
+        const bool nz = (__ldg(P.mbits + (b >> 5)) >> (b & 31u)) & 1u;
+        if (P.mask_type == GLB_MASK_WRITE_TO_ZERO ? nz : (P.mask_type == GLB_MASK_WRITE_TO_ONE && !nz)) v = Val<VT>::zero();
+    } else if (P.mask_type == GLB_MASK_WRITE_TO_ZERO) {
         if (!Val<VT>::is_zero(ld_stream_f32(P.mask + row))) v = Val<VT>::zero();
     } else if (P.mask_type == GLB_MASK_WRITE_TO_ONE) {
         if (Val<VT>::is_zero(ld_stream_f32(P.mask + row))) v = Val<VT>::zero();
@@ -200,6 +210,18 @@ __device__ __forceinline__ uint32_t gather_bit(const uint32_t *xbits, uint32_t c
     return (__ldg(xbits + (c >> 5)) >> (c & 31u)) & 1u;
 }
 
+__device__ __forceinline__ uint32_t row_of(const SpmvParams &P, uint32_t ord) {
+    return P.rows_identity ? P.row0 + ord : ld_stream_u32(P.nz_rows + ord);
+}
+// mask[row] != 0, from the launch-time bitmap when there is one
+__device__ __forceinline__ bool mask_nonzero(const SpmvParams &P, uint32_t row) {
+    if (P.mbits) {
+        const uint32_t b = row - P.mbits_base;
+        return (__ldg(P.mbits + (b >> 5)) >> (b & 31u)) & 1u;
+    }
+    return ld_stream_f32(P.mask + row) != 0.0f;
+}
+
 // One chunk (up to 8 groups of 128 non-zeros) by one warp.  TILE: the hot vector is in shared
 // memory at tile_base (persistent kernel), else it is read through L1.
 // BITS (or-and only): 0 = fp32 x gathers, 1 = bitmap gathers + value stream (a != 0 is tested),
@@ -208,8 +230,15 @@ __device__ __forceinline__ uint32_t gather_bit(const uint32_t *xbits, uint32_t c
 template <int OP, bool TILE, int BITS = 0, bool MASKED = true, int VT = GLB_VAL_F32>
 __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_t chunk, const unsigned lane,
                                               float *const stage, const uint32_t tile_base) {
-    const uint32_t g0 = ld_stream_u32(P.chunk_goff + chunk);
-    const int n = int(ld_stream_u32(P.chunk_goff + chunk + 1) - g0);  // 1 .. GLB_MAX_GROUPS, warp-uniform
+    uint32_t g0;
+    int n;  // 1 .. GLB_MAX_GROUPS, warp-uniform
+    if (P.uniform_groups) {
+        g0 = chunk * P.uniform_groups;
+        n = int(chunk + 1 == P.n_chunks ? P.last_groups : P.uniform_groups);
+    } else {
+        g0 = ld_stream_u32(P.chunk_goff + chunk);
+        n = int(ld_stream_u32(P.chunk_goff + chunk + 1) - g0);
+    }
     const uint4 *gp = reinterpret_cast<const uint4 *>(P.stream) + size_t(g0) * 64 + lane;
     uint4 cq[kPrefetch + 1], aq[kPrefetch + 1];
 #pragma unroll
@@ -245,8 +274,13 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
         for (uint32_t j = 0; j <= cnt; ++j) {
             const uint32_t ord = ord_base + j;
             if (ord >= P.n_nz_rows) continue;  // the padding pseudo-row of the last chunk
-            const float mv = ld_stream_f32(P.mask + ld_stream_u32(P.nz_rows + ord));
-            lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? Val<VT>::is_zero(mv) : !Val<VT>::is_zero(mv);
+            if (VT == GLB_VAL_F32) {
+                const bool nz = mask_nonzero(P, row_of(P, ord));
+                lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? !nz : nz;
+            } else {
+                const float mv = ld_stream_f32(P.mask + row_of(P, ord));
+                lane_live |= (P.mask_type == GLB_MASK_WRITE_TO_ZERO) ? Val<VT>::is_zero(mv) : !Val<VT>::is_zero(mv);
+            }
         }
     }
     const bool chunk_live = !MASKED || __any_sync(kFull, lane_live);
@@ -313,7 +347,7 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
         if (k == 0 && !fresh) {
             P.head_carry[chunk] = val;  // row began in an earlier chunk
         } else {
-            finish_row<OP, true, VT>(P, ld_stream_u32(P.nz_rows + ord0 + k), val);
+            finish_row<OP, true, VT>(P, row_of(P, ord0 + k), val);
         }
     }
 }
@@ -396,9 +430,18 @@ __global__ void __launch_bounds__(kThreads, GLB_SPMV_MIN_BLOCKS) spmv_lane_bits_
 // landed (glb_xchg_wait_head); x is then read around L1 (ld.cg) -- peers wrote it.
 __global__ void __launch_bounds__(kThreads) pack_bits_kernel(const float *x, const uint32_t *__restrict__ hot_cols,
                                                            uint32_t *__restrict__ xbits, uint32_t tile_k, uint32_t n_hot,
-                                                           uint32_t num_cols, uint32_t n_words32, const GlbXchgWait wait) {
+                                                           uint32_t num_cols, uint32_t n_words32, const GlbXchgWait wait,
+                                                           const float *mask, uint32_t *__restrict__ mbits, uint32_t mbits_base,
+                                                           uint32_t row_begin, uint32_t row_end, uint32_t n_mwords) {
     glb_xchg_wait_head(wait);
-    const uint32_t w = blockIdx.x * kThreads + threadIdx.x;  // grid covers n_words32 * 32 exactly
+    const uint32_t w = blockIdx.x * kThreads + threadIdx.x;  // grid covers (n_words32 + n_mwords) * 32 exactly
+    if (w >= n_words32 * 32u) {  // warp-uniform: the mask of a masked launch, one bit per row of the shard
+        const uint32_t row = mbits_base + (w - n_words32 * 32u);
+        const bool nz = ((w >> 5) - n_words32) < n_mwords && row >= row_begin && row < row_end && mask[row] != 0.0f;
+        const unsigned mb = __ballot_sync(kFull, nz);
+        if ((threadIdx.x & 31u) == 0 && ((w >> 5) - n_words32) < n_mwords) mbits[(w >> 5) - n_words32] = mb;
+        return;
+    }
     bool t = false;
     if (w < tile_k) {
         const uint32_t c = n_hot ? __ldg(hot_cols + w) : w;
@@ -1069,9 +1112,17 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     if (head_is_pack) {
         // or-and: one bit per stored column word replaces the fp32 gathers
         const uint32_t n_words32 = (m->tile_k + m->num_cols + 31u) / 32u;
-        const uint32_t threads = n_words32 * 32u;
-        pack_bits_kernel<<<(threads + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(x, m->hot_cols, m->xbits, m->tile_k,
-                                                                                          m->n_hot, m->num_cols, n_words32, w);
+        //   GLB_SPMV_MASK_BITS=0   masked or-and launches read the fp32 mask (default 1: a bitmap packed with x)
+        static const bool mask_bits = !getenv("GLB_SPMV_MASK_BITS") || atoi(getenv("GLB_SPMV_MASK_BITS")) != 0;
+        const uint32_t mbase = m->row_begin & ~31u;
+        const uint32_t n_mwords = (mask_type != GLB_MASK_NONE && mask_bits && m->mbits) ? (m->row_end - mbase + 31u) / 32u : 0u;
+        const uint32_t threads = (n_words32 + n_mwords) * 32u;
+        pack_bits_kernel<<<(threads + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(
+            x, m->hot_cols, m->xbits, m->tile_k, m->n_hot, m->num_cols, n_words32, w, mask, m->mbits, mbase, m->row_begin, m->row_end, n_mwords);
+        if (n_mwords) {
+            P.mbits = m->mbits;
+            P.mbits_base = mbase;
+        }
         P.xbits = m->xbits;
         P.hot_x = x;
     } else if (m->n_hot && m->n_chunks) {  // pack the x values of the hot columns
@@ -1105,6 +1156,13 @@ int glb_launch_spmv(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_typ
     P.n_fix_long = m->n_fix_long;
     P.n_empty = m->n_empty;
     P.n_nz_rows = m->n_nz_rows;
+    static const bool shortcuts = !getenv("GLB_SPMV_SHORTCUTS") || atoi(getenv("GLB_SPMV_SHORTCUTS")) != 0;
+    if (shortcuts) {
+        P.rows_identity = m->n_empty == 0 && m->n_nz_rows == m->row_end - m->row_begin;
+        P.row0 = m->row_begin;
+        P.uniform_groups = m->uniform_groups;
+        P.last_groups = m->last_groups;
+    }
     if (P.push_count_only) return dispatch_op(ctx, m, op, val_type, P, published, ctx->stream, kLaunchMain);  // the pusher CTAs do the fix-ups
     if (!split) return dispatch_op(ctx, m, op, val_type, P, published, ctx->stream, kLaunchMain | kLaunchFixup);
     return launch_split(ctx, m, op, val_type, P, *split);
@@ -1419,6 +1477,13 @@ int glb_csr_create(glb_ctx_t ctx, uint32_t num_rows, uint32_t num_cols, const ui
     //   GLB_SPMV_BITS=0              or-and SpMV gathers fp32 x like the other semirings (default 1: bitmap)
     if (!rc && env_u32("GLB_SPMV_BITS", 1) && L.n_chunks)
         rc = upload<uint32_t>(ctx, &m->xbits, nullptr, 0, (size_t(L.tile_k) + num_cols + 31) / 32 + 1, &bytes);
+    if (!rc && m->xbits) rc = upload<uint32_t>(ctx, &m->mbits, nullptr, 0, (size_t(row_end - (row_begin & ~31u)) + 31) / 32 + 1, &bytes);
+    {
+        bool uniform = L.n_chunks > 0;
+        for (uint32_t c = 0; uniform && c + 1 < L.n_chunks; ++c) uniform = L.chunk_goff[c + 1] - L.chunk_goff[c] == L.max_groups;
+        m->uniform_groups = uniform ? L.max_groups : 0;
+        m->last_groups = uniform ? L.chunk_goff[L.n_chunks] - L.chunk_goff[L.n_chunks - 1] : 0;
+    }
     if (!rc && L.n_chunks) {
         // progressive push of a row-sharded run (push_block_when_complete): which rows the main kernel
         // writes, and the row boundaries of the blocks of kPushCtas consecutive CTAs
@@ -1513,7 +1578,7 @@ int glb_csr_destroy(glb_csr_t m) {
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->stream); cudaFree(m->flags); cudaFree(m->chunk_goff); cudaFree(m->chunk_first); cudaFree(m->nz_rows);
     cudaFree(m->fix_short); cudaFree(m->fix_long); cudaFree(m->empty_rows);
-    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits);
+    cudaFree(m->head_carry); cudaFree(m->tail_carry); cudaFree(m->hot_cols); cudaFree(m->hot_x); cudaFree(m->xbits); cudaFree(m->mbits);
     cudaFree(m->push_bits); cudaFree(m->push_lo); cudaFree(m->push_count);
     cudaFree(m->fix_in); cudaFree(m->fix_def); cudaFree(m->blk_fs); cudaFree(m->blk_em); cudaFree(m->pusher_bits);
     cudaFree(m->dx); cudaFree(m->dmask); cudaFree(m->dy);
