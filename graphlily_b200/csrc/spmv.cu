@@ -603,7 +603,6 @@ struct PusherParams {
     uint32_t push_row_base, n_blocks, n_ctas;
     uint32_t *mc_flags, *state;
     int rank;
-    int debug;                  // GLB_XCHG_PUSHER_DEBUG=1: no data stores (timing experiment, results are WRONG)
     unsigned long long *trace;  // GLB_XCHG_TRACE: [0] start [1] all blocks out [2] late rows fenced [3] published [4+2b] block b ready [5+2b] sent
 };
 constexpr uint32_t kPusherThreads = 1024;
@@ -682,9 +681,7 @@ __global__ void __launch_bounds__(kPusherThreads, 1) xchg_pusher_kernel(const Sp
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t r0 = base + 4u * (threadIdx.x + u * kPusherThreads);
-                if (Q.debug) {
-                    if (bits[u] && v[u].x == 1234.5f) Q.trace[0] = 0;  // keep the loads
-                } else if (bits[u] == 0xfu) {
+                if (bits[u] == 0xfu) {
                     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(Q.y_mc + r0), "f"(v[u].x),
                                  "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
                                  : "memory");
@@ -1025,8 +1022,6 @@ int glb_launch_pusher(glb_ctx_t ctx, glb_csr_t m, int op, float zero, int mask_t
     Q.mc_flags = mc_flags;
     Q.state = state;
     Q.rank = rank;
-    static const int debug = int(env_u("GLB_XCHG_PUSHER_DEBUG", 0));
-    Q.debug = debug;
     // GLB_XCHG_TRACE=<n>: timeline of the n-th pusher launch of the process (eager launches only), printed at the next one
     static const long trace_at = getenv("GLB_XCHG_TRACE") ? atol(getenv("GLB_XCHG_TRACE")) : -1;
     static long call_no = 0;

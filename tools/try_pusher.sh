@@ -1,5 +1,7 @@
 #!/bin/bash
-# Exchange-mode comparison at N ranks (gpurun --gpus N): SpMV bench line only, parity checked by every rank.
+# Exchange-mode comparison at N ranks (gpurun --gpus N): the SpMV bench line only, parity checked by every rank.
+#   bash tools/try_pusher.sh <N>            kernel (default exchange) vs pusher CTAs with 4 and 8 pushers
+#   CFGS="3 6" GLB_XCHG_TRACE=6 bash ...    other pusher counts; timeline of the 6th eager step of rank 0
 N=${1:-2}
 mkdir -p gpurun_out
 run() {  # run <tag> <env...>
@@ -17,5 +19,5 @@ print('GTEPS', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'parit
 [ -n "$SKIP_KERNEL" ] || run kernel GLB_XCHG_MC=kernel
 CFGS=${CFGS:-4 8}
 for cfg in $CFGS; do
-    run pusher$cfg$TAG GLB_XCHG_MC=pusher GLB_XCHG_PUSHERS=$cfg $EXTRA
+    run pusher$cfg GLB_XCHG_MC=pusher GLB_XCHG_PUSHERS=$cfg
 done
