@@ -62,7 +62,7 @@ private:
                 }
                 DeviceBuffer v = vec, r = res;
                 for (uint32_t iter = first_iter; iter <= num_iterations; iter++) {
-                    glb_spmv_epilogue_t ep = {0, 0.0f, mask.f32(), float(iter + 1), GLB_MASK_WRITE_TO_ONE};
+                    glb_spmv_epilogue_t ep = {0, 0.0f, mask.f32(), graphlily::val_container(graphlily::val_t(float(iter + 1))), GLB_MASK_WRITE_TO_ONE};
                     SpMV_->run_fused(v, mask, r, &ep);
                     std::swap(v, r);
                 }
@@ -221,7 +221,7 @@ public:
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
         push_setup(source);
-        if (!fused_ || world_ > 1) {   // (sharded: the frontier exchange sits between the SpMSpV and the assign)
+        if (!fused_ || world_ > 1 || !SpMSpV_->fused_levels_available()) {   // (sharded: the frontier exchange sits between the SpMSpV and the assign; the fused levels compute in fp32)
             for (uint32_t iter = 1; iter <= num_iterations; iter++) push_step(iter);
             return SpMSpV_->send_mask_device_to_host();
         }
@@ -236,7 +236,8 @@ public:
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
-        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1) return pull_push_device(source, num_iterations, threshold);
+        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1 && SpMSpV_->fused_levels_available())
+            return pull_push_device(source, num_iterations, threshold);
         push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);

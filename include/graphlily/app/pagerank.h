@@ -73,11 +73,12 @@ public:
         const uint32_t n = matrix_num_rows_;
         const float teleport = (1 - damping) / n;
         if (exchange_) exchange_->barrier();   // no rank overwrites vectors a peer still reads from the previous run
-        SpMV_->set_vector_constant(float(1.0 / n));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
+        SpMV_->set_vector_constant(graphlily::val_t(float(1.0 / n)));  // rank0 = 1 / N (pagerank.h:81-82), built on the device
         if (fused_ || exchange_) {
             DeviceBuffer vec = SpMV_->vector_buf, res = SpMV_->results_buf;
             replay({2, key_of(SpMV_->device_matrix()), key_of(teleport), num_iterations, key_of(vec.ptr()), key_of(res.ptr())}, [&] {
-                glb_spmv_epilogue_t ep = {1, teleport, nullptr, 0.0f, 0};
+                // (the scalar travels as a word of val_t: the float itself, or its unsigned / Q8.24 conversion)
+                glb_spmv_epilogue_t ep = {1, graphlily::val_container(graphlily::val_t(teleport)), nullptr, 0.0f, 0};
                 if (exchange_) {
                     std::vector<glb_spmv_epilogue_t> eps(num_iterations, ep);
                     SpMV_->iterate_exchange(*exchange_, vec, DeviceBuffer(), res, eps.data(), int(num_iterations));
@@ -95,7 +96,7 @@ public:
             eWiseAdd_->bind_out_buf(SpMV_->vector_buf);
             for (uint32_t iter = 1; iter <= num_iterations; iter++) {
                 SpMV_->run();
-                eWiseAdd_->run(n, teleport);
+                eWiseAdd_->run(n, graphlily::val_t(teleport));
             }
         }
         return SpMV_->send_vector_device_to_host();

@@ -233,7 +233,7 @@ public:
 
     aligned_dense_vec_t push(uint32_t source, uint32_t num_iterations) {
         push_setup(source);
-        if (!fused_ || world_ > 1) {   // (sharded: the frontier exchange sits between the SpMSpV and the relax)
+        if (!fused_ || world_ > 1 || !SpMSpV_->fused_levels_available()) {   // (sharded: the frontier exchange sits between the SpMSpV and the relax; the fused levels compute in fp32)
             for (uint32_t iter = 1; iter <= num_iterations; iter++) {
                 SpMSpV_->run();
                 exchange_frontier(SpMV_, SpMSpV_->results_buf, semiring_.zero, matrix_num_rows_);
@@ -251,7 +251,8 @@ public:
     }
 
     aligned_dense_vec_t pull_push(uint32_t source, uint32_t num_iterations, float threshold = 0.05) {
-        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1) return pull_push_device(source, num_iterations, threshold);
+        if (fused_ && use_graphs_ && num_iterations >= 2 && world_ == 1 && SpMSpV_->fused_levels_available())
+            return pull_push_device(source, num_iterations, threshold);
         push_iterations_device_ = false;
         const uint32_t n = matrix_num_rows_;
         push_setup(source);

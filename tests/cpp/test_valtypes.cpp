@@ -7,6 +7,7 @@
 // launch sequence) against the same graphs run through the model operator by operator.  "Parity unpinned": the
 // reference ships no artefact that pins its device numerics; the model follows the documented ap_ufixed semantics.
 #include "graphlily/app/bfs.h"
+#include "graphlily/app/pagerank.h"
 #include "graphlily/app/sssp.h"
 #include "graphlily/module/add_scalar_vector_dense_module.h"
 #include "graphlily/module/assign_vector_dense_module.h"
@@ -241,6 +242,10 @@ TEST(ValTypes, BfsAndSssp) {
         expect_words(dist, bfs.pull(src, iters), "BFS pull");
         expect_words(dist, bfs.push(src, iters), "BFS push");
         expect_words(dist, bfs.pull_push(src, iters, 0.05f), "BFS pull_push");
+        bfs.set_fused(true);   // the pull levels run fused (one launch, the assign in the SpMV write-back); push stays unfused
+        expect_words(dist, bfs.pull(src, iters), "BFS pull, fused");
+        expect_words(dist, bfs.push(src, iters), "BFS push, fused requested");
+        expect_words(dist, bfs.pull_push(src, iters, 0.05f), "BFS pull_push, fused requested");
     }
     {
         CSRMatrix<float> m = g;
@@ -291,7 +296,44 @@ TEST(ValTypes, BfsAndSssp) {
         // threshold 1.1: every level but the last pushes (sssp.h:214), the last one pulls from the distance vector
         expect_words(pull_from(push_levels(iters - 1), 1), sssp.pull_push(src, iters, 1.1f), "SSSP pull_push");
         EXPECT_EQ(sssp.get_push_iterations(), iters - 1);
+        sssp.set_fused(true);
+        expect_words(pull_from(x0, iters), sssp.pull(src, iters), "SSSP pull, fused");
+        expect_words(push_levels(iters), sssp.push(src, iters), "SSSP push, fused requested");
     }
+}
+
+// PageRank on val_t (the shipped bitstream's configuration is Q8.24): rank = A' rank + teleport, saturating, both the
+// reference's two-launch sequence and the fused one
+TEST(ValTypes, PageRank) {
+    auto rt = std::make_shared<Runtime>(0);
+    CSRMatrix<float> g = uniform_csr(3000, 9, 31, 1.0f);
+    const float damping = 0.9f;
+    const uint32_t iters = 6;
+    CSRMatrix<float> m = g;
+    io::util_round_csr_matrix_dim(m, 128, 128);
+    io::util_normalize_csr_matrix_by_outdegree(m);
+    for (auto &x : m.adj_data) x = x * damping;
+    const uint32_t n = m.num_rows;
+    const std::vector<uint32_t> data = words_of(m.adj_data);
+    const uint32_t teleport = VT::bits(val_t((1 - damping) / n));
+    std::vector<uint32_t> x(n, VT::bits(val_t(float(1.0 / n)))), y(n);
+    for (uint32_t it = 0; it < iters; it++) {
+        vt_spmv(VT::id, n, n, m.adj_indptr.data(), m.adj_indices.data(), data.data(), kMulAdd, 0, kNoMask, x.data(), nullptr, y.data());
+        vt_ewise_add(VT::id, y.data(), x.data(), n, teleport);
+    }
+    for (bool fused : {false, true}) {
+        app::PageRank pr(16, 1024, 256);
+        pr.set_runtime(rt);
+        pr.set_fused(fused);
+        pr.load_and_format_matrix(g, damping, true);
+        pr.send_matrix_host_to_device();
+        expect_words(x, pr.pull(damping, iters), fused ? "PageRank, fused" : "PageRank");
+    }
+#if defined(GRAPHLILY_VAL_T_UFIXED)
+    double sum = 0;
+    for (uint32_t w : x) sum += double(w) / 16777216.0;
+    EXPECT_TRUE(sum > 0.5 && sum < 1.5);   // ranks still sum to about 1 in Q8.24 (quantisation of 1 / N and of the weights)
+#endif
 }
 
 MINI_TEST_MAIN
