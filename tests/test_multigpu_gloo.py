@@ -136,3 +136,34 @@ def test_row_sharded_push_protocol_matches_oracle(tmp_path, oracle):
     ref = oracle.port.bfs(g, 0, 5)
     got = [np.load(tmp_path / f"d{r}.npy") for r in range(world)]
     assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], ref)
+
+
+def _fd_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from graphlily_b200.exchange import _share_fd_over_unix_socket
+    share = _share_fd_over_unix_socket(rank, world)
+    fd = None
+    if rank == 0:   # stands in for the multicast object's descriptor: any fd must arrive as the SAME open file
+        fd = os.open(os.path.join(out_dir, "object"), os.O_RDWR | os.O_CREAT)
+        os.write(fd, b"multicast-object")
+    got = share(fd)
+    assert got is not None and got >= 0
+    if rank != 0:   # a descriptor of this process onto rank 0's open file (positional I/O: the ranks share one file offset)
+        assert os.pread(got, 16, 0) == b"multicast-object"
+        os.pwrite(got, b"+seen-by-%d" % rank, 16 + 16 * rank)
+    dist.barrier()
+    if rank == 0:
+        data = os.pread(fd, 256, 0)
+        assert data.startswith(b"multicast-object") and data.count(b"+seen-by-") == world - 1, data
+    os.close(got)
+    dist.destroy_process_group()
+
+
+def test_descriptor_travels_from_rank0_to_every_rank(tmp_path):
+    """The host's only part in the library-made multicast exchange (capi.Exchange.open_multicast): ONE file
+    descriptor goes from rank 0 to the other ranks' processes (SCM_RIGHTS over an abstract Unix socket whose name
+    travels over torch.distributed)."""
+    world = 3
+    mp.spawn(_fd_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
