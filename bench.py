@@ -460,7 +460,8 @@ def main():
            "d2h_bytes_per_step": 4 * n, "ms_per_step": batch_ms, "steps": e2e_steps,
            "api": (f"glb_spmv_host_batch_exchange: {e2e_steps} vectors from a ring of {ring} pinned host x buffers; every rank "
                    "uploads its 1/N slice of x, the slices meet over NVLink, SpMV, y slice -> pinned host; "
-                   "upload / kernels / download of consecutive vectors overlap" if sliced else
+                   "upload / kernels / download of consecutive vectors overlap (the copies of the neighbouring vectors start "
+                   "once the slice push of the current one has left)" if sliced else
                    f"glb_spmv_host_batch: {e2e_steps} vectors from a ring of {ring} pinned host x buffers -> device, SpMV, "
                    "y slice -> pinned host y buffers; upload / kernels / download of consecutive vectors overlap"),
            "batch_matches_single_call_bitwise": batch_same,
