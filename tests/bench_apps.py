@@ -158,6 +158,28 @@ def run_app(name, env, scale=1.0, reps=5, check=True, copy_results=False, hbm_pe
     if hbm_peak_gbs and roof["achieved"]:
         roof["peak"], roof["frac"] = hbm_peak_gbs, roof["achieved"] / hbm_peak_gbs
     modes["pull"]["roofline"] = roof
+    if name == "bfs" and world == 1 and "loop_only_ms_per_iteration" in modes["push"]:
+        # SpMSpV (one fused launch per push level): SURVEY.md 8d bytes = 8 B per non-zero of the frontier's columns + the two
+        # lists, summed over the levels of this run (frontier of level L = vertices at distance L, from the result itself).
+        # Reported against the HBM peak as the contract asks; the operator is bound by L2 reduction atomics and, for small
+        # frontiers, by the launch + grid-barrier floor, which is what the low fraction shows.
+        d = results["push"]
+        col_nnz = np.bincount(np.asarray(a.csr_matrix_.indices), minlength=n).astype(np.int64)   # entries per CSC column
+        total, per_level = 0, []
+        for level in range(1, iters + 1):
+            frontier = np.nonzero(d == np.float32(level))[0]
+            nxt = int((d == np.float32(level + 1)).sum())
+            b_level = 8 * int(col_nnz[frontier].sum()) + 8 * len(frontier) + 8 * nxt
+            per_level.append({"frontier": int(len(frontier)), "column_nnz": int(col_nnz[frontier].sum()), "bytes": b_level})
+            total += b_level
+        loop_s = modes["push"]["loop_only_ms_per_iteration"] * iters * 1e-3
+        sroof = {"bound": "hbm", "kernel": "spmspv_kernel<or-and> + fused sparse assign, one launch per level",
+                 "algorithmic_bytes_all_levels": total, "levels": per_level, "loop_ms": loop_s * 1e3,
+                 "achieved": total / loop_s / 1e9, "unit": "GB/s",
+                 "limiter": "L2 reduction atomics (large frontiers) / launch + grid barriers (small ones)"}
+        if hbm_peak_gbs:
+            sroof["peak"], sroof["frac"] = hbm_peak_gbs, sroof["achieved"] / hbm_peak_gbs
+        modes["push"]["roofline"] = sroof
 
     verdict = None
     # every rank's result must be bit-identical to rank 0's (the exchange delivered every slice)
