@@ -288,6 +288,7 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
     // the lane's run: serial reduction in registers; every flagged element closes the open row
     float *sp = stage + excl;
     float acc = Semi<OP, VT>::ident();
+    uint32_t run_bits = 0;  // BITS only
 #pragma unroll
     for (int g = 0; g < GLB_MAX_GROUPS; ++g) {
         if (g < n) {
@@ -299,17 +300,29 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
             const uint4 a4 = (BITS != 2) ? aq[g % (kPrefetch + 1)] : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
             const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (BITS) {
+                // or-and over a bitmap x: a product is ONE bit.  The lane collects the bits of its run in a word (element r at
+                // bit r) and cuts it into rows afterwards with the flag word -- ~6 instructions per non-zero instead of the
+                // ~30 of the generic reduce-and-test-the-flag loop, which left this kernel issue-bound (56 % issue slots busy).
+                if (!MASKED || lane_live) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t bit = gather_bit(P.xbits, c[e]);
+                        if (BITS == 1) bit &= (__uint_as_float(a[e]) != 0.0f) ? 1u : 0u;  // a stored 0.0 contributes nothing
+                        run_bits |= bit << (4 * g + e);
+                    }
+                }
+                continue;
+            }
             float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (!MASKED || lane_live) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (BITS) xv[e] = __uint_as_float(gather_bit(P.xbits, c[e]) * 0x3f800000u);  // 0.0f / 1.0f
-                    else xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
-                }
+                for (int e = 0; e < 4; ++e)
+                    xv[e] = TILE ? gather_x_tile(tile_base, P.x_cold, P.tile_k, c[e]) : gather_x(P.hot_x, P.x_cold, P.tile_k, c[e]);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float prod = (BITS == 2) ? xv[e] : Semi<OP, VT>::mul(__uint_as_float(a[e]), xv[e]);
+                float prod = Semi<OP, VT>::mul(__uint_as_float(a[e]), xv[e]);
                 if (MASKED && !lane_live) prod = Semi<OP, VT>::ident();  // every row of this lane is masked out
                 if (fw & (1u << (4 * g + e))) {
                     *sp++ = acc;
@@ -318,6 +331,19 @@ __device__ __forceinline__ void process_chunk(const SpmvParams &P, const uint32_
                 acc = Semi<OP, VT>::add(acc, prod);
             }
         }
+    }
+    if (BITS) {
+        // rows of the run: the k-th flag (element p starts a new row) closes the segment [lo, p); the tail after the last
+        // flag stays open in `acc`.  OR over a segment = "any bit of run_bits inside it".
+        uint32_t f = fw, lo_mask = 0xffffffffu;  // lo_mask: bits at and above the start of the open segment
+        while (f) {
+            const uint32_t p = __ffs(int(f)) - 1;
+            f &= f - 1;
+            const uint32_t below_p = (1u << p) - 1u;
+            *sp++ = (run_bits & below_p & lo_mask) ? 1.0f : 0.0f;
+            lo_mask = ~below_p;
+        }
+        acc = (run_bits & lo_mask) ? 1.0f : 0.0f;
     }
 
     // stitch rows that cross lanes: segmented inclusive scan of the lane tails (a lane holding a
