@@ -7,6 +7,8 @@
 #include <iterator>
 
 #include "graphlily/app/sssp.h"
+#include <random>
+
 #include "test_util.h"
 
 static CSRMatrix<float> csr_matrix_1() {  // [[1,2,3,4],[5,0,6,0],[0,7,0,0],[0,0,0,8]]
@@ -180,6 +182,36 @@ TEST(Global, ConvertSparseVecToDenseVec) {
     auto d = graphlily::convert_sparse_vec_to_dense_vec<sparse_t, dense_t, float>(s, 5, 255.0f);
     dense_t expect = {5.0f, 255.0f, 255.0f, 7.0f, 255.0f};
     EXPECT_TRUE(d == expect);
+}
+
+// The host-side value class of the Q8.24 val_t (global.h) against the software ap_ufixed<32, 8, AP_RND, AP_SAT> of the
+// oracle (oracle/shim/ap_fixed.h through libvaltype_model): same word for every double, and the traits of the three types.
+extern "C" uint32_t vt_ufixed_from_double(double x);
+extern "C" double vt_ufixed_to_double(uint32_t w);
+
+TEST(Global, UfixedHostClassAndValTraits) {
+    using graphlily::ufixed_32_8;
+    std::mt19937_64 rng(7);
+    std::uniform_real_distribution<double> small(0.0, 1.0), wide(-10.0, 300.0);
+    for (int i = 0; i < 200000; i++) {
+        const double x = (i % 3 == 0) ? small(rng) : (i % 3 == 1) ? wide(rng) : double(rng() % (1ull << 32)) / 16777216.0 + ((i % 2) ? 2.98023223876953125e-08 : 0.0);
+        const uint32_t w = ufixed_32_8(x).word();
+        if (w != vt_ufixed_from_double(x)) MT_FAIL_(true, "ufixed_32_8(%.17g) = %08x, ap_ufixed gives %08x", x, w, vt_ufixed_from_double(x));
+    }
+    for (uint32_t w : {0u, 1u, 1u << 24, 0x7fffffffu, 0xffffffffu})
+        EXPECT_TRUE(ufixed_32_8::from_word(w).to_double() == vt_ufixed_to_double(w));
+    EXPECT_EQ(ufixed_32_8(1).word(), 1u << 24);
+    EXPECT_EQ(ufixed_32_8(-1.0).word(), 0u);
+    EXPECT_EQ(ufixed_32_8(1e9).word(), 0xffffffffu);
+    EXPECT_EQ(graphlily::val_traits<float>::id, GLB_VAL_F32);
+    EXPECT_EQ(graphlily::val_traits<unsigned>::id, GLB_VAL_U32);
+    EXPECT_EQ(graphlily::val_traits<ufixed_32_8>::id, GLB_VAL_UFIXED);
+    EXPECT_EQ(graphlily::val_traits<unsigned>::from_float(3.9f), 3u);       // (val_t)x of the reference's formatter truncates
+    EXPECT_EQ(graphlily::val_traits<unsigned>::from_float(-2.0f), 0u);
+    float f = graphlily::val_container(ufixed_32_8(0.5));
+    uint32_t bits;
+    std::memcpy(&bits, &f, 4);
+    EXPECT_EQ(bits, 1u << 23);
 }
 
 MINI_TEST_MAIN
